@@ -1,0 +1,19 @@
+"""CPU oracle for the articulated-Gaussian-splat render path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is part of the product:
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import it, and only as the checker or as the
+timed CPU baseline.  ``manus_b200`` never imports this package.
+
+Parity status
+-------------
+* pose path (P1-P4: LBS, covariance, SH->RGB, activations): PINNED against the
+  reference's own Python (``/root/reference/src``) through the golden vectors in
+  ``tests/golden/pose_golden_*.npz`` made by ``tests/golden/make_golden_pose.py``.
+* rasterizer (R2/R3) and ``distCUDA2`` (K1): **parity unpinned** -- the Inria
+  ``diff-gaussian-rasterization`` / ``simple-knn`` sources are not present in
+  ``/root/reference`` (cloned un-pinned at install time, ``setup_env.sh:4-13``);
+  the restatement follows their published algorithm as recorded in SURVEY.md
+  Appendix A / B and is cross-checked by an independent autograd restatement and
+  analytic known-answer tests only.
+"""
