@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Headline benchmark: forward+backward frames/s of the articulated-Gaussian-splat render path at 1920x1080 with a
+500k-Gaussian composite hand+object scene (BASELINE.json), plus the HBM roofline of the dominant kernel, the end-to-end
+number through the public API with host inputs, and the CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step = one training view per rank: pose kernel (LBS + covariance + SH->RGB) -> rasterizer forward -> loss =
+sum(image * G) with a fixed G ~ U[0,1] -> rasterizer backward -> pose backward into the flat
+per-Gaussian gradient buffer -> (N > 1) one NCCL all-reduce of that buffer.  Views shard across ranks (weak scaling:
+every rank renders one view per step); value = views per second over all ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fwd+bwd frames/sec at 1080p, 500k Gaussians; achieved HBM GB/s vs peak"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gaussians", type=int, default=500_000)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--views", type=int, default=50)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def frame_bytes(n_hand, n_obj, D, P):
+    """Algorithmic HBM bytes of one forward+backward frame (SURVEY.md section 8d / BASELINE.md section 4)."""
+    return 1204 * n_hand + 1036 * n_obj + 244 * D + 40 * P
+
+
+# algorithmic bytes of one launch of each kernel; N = Gaussians, D = instances, P = pixels
+KERNEL_BYTES = {
+    "pose_forward": lambda N, Nh, D, P, V: (236 + 52) * N + 84 * Nh,
+    "pose_backward": lambda N, Nh, D, P, V: (52 + 236 + 236) * N + 84 * Nh,
+    "preprocess": lambda N, Nh, D, P, V: 76 * N,
+    "blend_forward": lambda N, Nh, D, P, V: 40 * D + 20 * P,
+    "blend_backward": lambda N, Nh, D, P, V: 40 * D + 20 * P + 44 * V,
+    "preprocess_backward": lambda N, Nh, D, P, V: 104 * N,
+    "radix_scatter": lambda N, Nh, D, P, V: None, "radix_hist": lambda N, Nh, D, P, V: None,
+}
+
+
+def cpu_baseline_frame(scene, width, height, view, threads):
+    """One forward+backward frame of the same workload on the host: PyTorch-CPU restatement of the reference's pose step
+    (oracle/pose_ref.py, autograd) + the C restatement of the rasterizer (oracle/raster_ref.c) on `threads` threads."""
+    import numpy as np
+    import torch
+
+    from manus_b200 import synth
+    from oracle import pose_ref
+    from oracle.raster_ref import RasterRef
+
+    torch.set_num_threads(threads)
+    cam = synth.camera(view, width, height)
+    t = lambda a: torch.tensor(a)
+    names = ["xyz", "log_scale", "quat", "opacity_logit", "f_dc", "f_rest"]
+    G = np.random.default_rng(7).uniform(0, 1, (3, height, width)).astype(np.float32)
+    ref = RasterRef("f32")
+    t0 = time.perf_counter()
+    leaves = {k: t(getattr(scene, k)).requires_grad_(True) for k in names}
+    nh = scene.n_hand
+    parts = []
+    if nh:
+        tfs = pose_ref.bone_transforms(t(synth.posed_bones(view)), t(scene.bones_rest), True)
+        parts.append(pose_ref.pose_gaussians_ref(*[leaves[k][:nh] for k in names], t(scene.skin_wts), tfs, t(cam.camera_center)))
+    if nh < scene.n:
+        parts.append(pose_ref.pose_gaussians_ref(*[leaves[k][nh:] for k in names], None, None, t(cam.camera_center)))
+    outs = [torch.cat([p[i] for p in parts], 0) for i in range(4)]
+    t1 = time.perf_counter()
+    img, radii, D = ref.forward(outs[0].detach().numpy(), outs[3].detach().numpy(), colors_precomp=outs[2].detach().numpy(),
+                                cov3D_precomp=outs[1].detach().numpy(), viewmatrix=cam.world_view_transform,
+                                projmatrix=cam.full_proj_transform, campos=cam.camera_center, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                                W=width, H=height, bg=np.ones(3, np.float32), nthreads=threads)
+    t2 = time.perf_counter()
+    g = ref.backward(G, nthreads=threads)
+    t3 = time.perf_counter()
+    torch.autograd.backward(outs, [t(g["means3D"]), t(g["cov3D"]), t(g["colors"]), t(g["opacity"])])
+    t4 = time.perf_counter()
+    ref.close()
+    return dict(total_s=t4 - t0, pose_fwd_s=t1 - t0, raster_fwd_s=t2 - t1, raster_bwd_s=t3 - t2, pose_bwd_s=t4 - t3, D=D)
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's path on the host cores.  The reference's own CUDA rasterizer is not part of
+    /root/reference (third-party, cloned at install time) so nothing can be compiled into oracle/_ref; this times the CPU
+    port (oracle/) with all host threads, one full frame per step."""
+    if rank != 0:
+        return
+    from manus_b200 import synth
+
+    threads = os.cpu_count() or 1
+    scene = synth.make_composite(args.gaussians, seed=0)
+    for i in range(min(args.warmup, 1)):
+        cpu_baseline_frame(scene, args.width, args.height, i, threads)
+    times = []
+    for i in range(args.steps):
+        times.append(cpu_baseline_frame(scene, args.width, args.height, i % args.views, threads)["total_s"])
+    ms = 1e3 * sum(times) / len(times)
+    val = 1e3 / ms
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "one full 1080p frame (pose fwd+bwd in PyTorch-CPU, raster fwd+bwd in C) per step"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"composite hand+object {args.gaussians} Gaussians (60% skinned by 20+1 bones, 40% static), "
+                        f"{args.views} shipped views/poses at {args.width}x{args.height}, SH degree 3, white background",
+            "global_views_per_step": world, "parallelism": f"view-sharded dp{world}, one all-reduce of the flat gradient buffer",
+            "l2": "working set per step (parameters 118 MB + gradients 118 MB + instance records) exceeds the 126 MB L2 and the view "
+                  "changes every step; no explicit flush",
+            "loss": "sum(image * G), G ~ U[0,1] fixed (seed 7)"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from manus_b200 import _lib, synth
+    from manus_b200 import build as mb_build
+    from manus_b200.dist import SceneRenderer
+    from manus_b200.rasterizer import set_capacity_mode
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: manus_b200 has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        mb_build.build()
+    if world > 1:
+        dist.barrier()
+    _lib.lib()
+
+    W, H, K, WU = args.width, args.height, args.steps, max(args.warmup, 3)
+    scene = synth.make_composite(args.gaussians, seed=0)
+    r = SceneRenderer(scene, dev, W, H)
+    n_hand, n_obj = scene.n_hand, scene.n - scene.n_hand
+    views = list(range(args.views))
+    my_view = lambda it: views[(it * world + rank) % len(views)]
+    G_host = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(7)).pin_memory()
+    G_dev = G_host.to(dev)
+    staged = {}
+    for v in views:
+        _, c, b = r.view_inputs_host(v)
+        staged[v] = (c.to(dev), b.to(dev))
+
+    def step_resident(it):
+        v = my_view(it)
+        out = r.render(v, sink=r.flat.grads, cam_dev=staged[v][0], bones_dev=staged[v][1])
+        loss = (out["render"] * G_dev).sum()
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(r.flat.grad)
+        return loss, out
+
+    g_buf = torch.empty_like(G_dev)
+
+    def step_e2e(it):
+        v = my_view(it)
+        _, c, b = r.view_inputs_host(v)
+        g_buf.copy_(G_host, non_blocking=True)                 # the step's target image, from pinned host memory
+        out = r.render(v, sink=r.flat.grads, cam_dev=c.to(dev, non_blocking=True), bones_dev=b.to(dev, non_blocking=True))
+        loss = (out["render"] * g_buf).sum()
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(r.flat.grad)
+        return float(loss)                                      # device -> host read of the step's result
+
+    # ---- untimed: instance / visible counts of every view (exact mode), then reserve mode (no host sync per frame)
+    from manus_b200 import rasterizer as _rz
+    set_capacity_mode("exact")
+    D_all, V_all = view_counts(r, staged, views)
+    set_capacity_mode("reserve", margin=1.1)
+    _rz._Plan.high_water[(dev.index, scene.n, H, W)] = max(D_all)
+
+    def timed(fn, steps, sampler=None):
+        for it in range(WU):
+            fn(it)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx = sampler if sampler is not None else _Null()
+        with ctx:
+            e0.record()
+            for it in range(steps):
+                fn(WU + it)
+            e1.record()
+            torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    sampler = ClockSampler(local_rank)
+    ms_step = timed(step_resident, K, sampler)
+    clocks = sampler.summary()
+    ms_e2e = timed(step_e2e, K)
+
+    # ---- per-kernel pass (CUDA events around every launch, on the launching stream): roofline of the dominant kernel
+    _lib.profile_enable(True)
+    _lib.profile_report()
+    for it in range(K):
+        step_resident(WU + it)
+    torch.cuda.synchronize()
+    prof = _lib.profile_report()
+    _lib.profile_enable(False)
+    seen = [my_view(WU + it) for it in range(K)]
+    D_mean = float(np.mean([D_all[v] for v in seen]))
+    V_mean = float(np.mean([V_all[v] for v in seen]))
+    P = W * H
+    peak, peak_src = measured_peaks()
+    total_ms = sum(ms for _, ms in prof.values())
+    top = max(prof.items(), key=lambda kv: kv[1][1])
+    top_name, (top_n, top_ms) = top
+    per_launch_ms = top_ms / top_n
+    fb = KERNEL_BYTES.get(top_name, lambda *a: None)(scene.n, n_hand, D_mean, P, V_mean)
+    roofline = {"bound": "hbm", "kernel": top_name, "achieved": (fb / (per_launch_ms * 1e-3) / 1e9) if fb else None, "peak": peak,
+                "unit": "GB/s", "frac": (fb / (per_launch_ms * 1e-3) / 1e9 / peak) if fb else None, "traffic": None,
+                "peak_source": peak_src, "launch_ms": per_launch_ms, "share_of_step": top_ms / total_ms if total_ms else None,
+                "algorithmic_bytes_per_launch": fb,
+                "kernels_ms_per_step": {k: round(ms / K, 5) for k, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
+    launches_per_step = sum(n for n, _ in prof.values()) / K
+    fbytes = frame_bytes(n_hand, n_obj, D_mean, P)
+    value = world * 1e3 / ms_step
+    e2e_val = world * 1e3 / ms_e2e
+    h2d = G_host.numel() * 4 + (35 + 2 + 320) * 4
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": WU, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+            "gpu_launches": int(round(launches_per_step * K)),
+            "roofline": roofline,
+            "frame": {"num_rendered_mean": D_mean, "visible_mean": V_mean, "algorithmic_bytes": fbytes,
+                      "achieved_gbps": fbytes * (1e3 / ms_step) / 1e9, "frac_of_hbm_peak": fbytes * (1e3 / ms_step) / 1e9 / peak,
+                      "allreduce_bytes": r.flat.allreduce_bytes() if world > 1 else 0}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cb = cpu_baseline_frame(scene, W, H, 0, threads)
+        line["cpu_baseline"] = {"value": 1.0 / cb["total_s"], "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "one full 1080p frame of the same scene (view 0): pose fwd+bwd in PyTorch-CPU + raster "
+                                          "fwd+bwd in C (oracle/), all host threads", "breakdown_s": {k: round(v, 4) for k, v in cb.items() if k != "D"}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def view_counts(r, staged, views):
+    """(num_rendered, num_visible) of every view via mb_raster_query, for the bytes-per-frame bookkeeping."""
+    import torch
+
+    from manus_b200 import rasterizer as rz
+    from manus_b200.pose import bone_transforms, pose_gaussians
+
+    Ds, Vs = {}, {}
+    for v in views:
+        cam, _, _ = r.view_inputs_host(v)
+        with torch.no_grad():
+            leaves = [p.detach() for p in r.flat.leaves()]
+            bone_tf = bone_transforms(staged[v][1].view(-1, 4, 4), r.bones_rest, True) if r.n_hand else None
+            px, pc, col, op = pose_gaussians(*leaves, r.skin, bone_tf, staged[v][0][32:35], r.sh_degree, r.flat.isotropic, r.n_hand)
+            settings = rz.GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, r.bg, 1.0, staged[v][0][0:16],
+                                                        staged[v][0][16:32], r.sh_degree, staged[v][0][32:35], False, False)
+            _, _, st = rz.rasterize_forward(settings, px, op.reshape(-1), colors_precomp=col, cov3D_precomp=pc)
+            Ds[v], Vs[v], _ = rz.raster_query(st)
+    return Ds, Vs
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,171 @@
+/*
+ * manus_b200.h -- C ABI of the B200-native articulated-Gaussian-splat render path.
+ *
+ * Plain pointers and sizes only (no torch types).  Every pointer is a DEVICE pointer unless the
+ * parameter name ends in _host.  All arrays are dense fp32 unless stated.  All entry points enqueue
+ * work on `stream` and return immediately (0 = ok, non-zero = error; text via mb_last_error()).
+ * The library is sm_100a only and has no CPU path.
+ *
+ * What each group replaces in the reference (paths relative to /root/reference):
+ *
+ *   mb_raster_*      the pybind module diff_gaussian_rasterization._C (third-party submodule, not in the tree;
+ *                    installed by setup_env.sh:6,9-10) that GaussianRasterizer.forward/backward call:
+ *                    rasterize_gaussians / rasterize_gaussians_backward / mark_visible.  Only call site in MANUS:
+ *                    src/utils/gaussian_utils.py:378-416 (settings :378-391, call :407-416).
+ *   mb_pose_*        the inline PyTorch pre-raster step, which has no operator boundary in the reference:
+ *                    src/modules/hand_dynamic.py:86-137 (LBS of means and covariances),
+ *                    src/models/gaussian.py:48-93 (activations, covariance build),
+ *                    src/utils/gaussian_utils.py:248-314,431-449 + src/utils/sh_utils.py:57-120 (SH -> RGB).
+ *   mb_dist2_knn3    simple_knn._C.distCUDA2 (third-party submodule, setup_env.sh:7,12-13); call site
+ *                    src/models/gaussian.py:110.
+ *
+ * Matrix convention: viewmatrix / projmatrix are the 16 floats MANUS passes (world_view_transform and
+ * full_proj_transform of src/utils/cam_utils.py:58-63, row-vector convention), i.e. element [4*col+row] of the
+ * usual column-vector matrix.  bone_tf is [B,4,4] row-major column-vector transforms (x' = T x), as produced by
+ * einsum("nij,njk->nik", posed, inv(rest)) in hand_dynamic.py:93-95.
+ */
+#ifndef MANUS_B200_H
+#define MANUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st *mb_stream_t; /* == cudaStream_t */
+
+#define MB_OK 0
+#define MB_ERR_INVALID 1   /* bad argument (shape / null / alignment) */
+#define MB_ERR_CUDA 2      /* a CUDA runtime call or kernel launch failed */
+#define MB_ERR_WORKSPACE 3 /* caller-provided workspace too small */
+
+int mb_version(void);
+const char *mb_last_error(void); /* thread-local, valid until the next call on this thread */
+int mb_device_sm_count(void);    /* SM count of the current device (148 on B200); <0 on error */
+
+/* Per-kernel timing with CUDA events on the launching stream (used by bench.py for the roofline numbers).
+ * mb_profile_report synchronises the device and writes one line "kernel_name launches total_ms" per kernel launched
+ * since the last report into buf (NUL terminated, truncated to cap). */
+void mb_profile_enable(int on);
+int mb_profile_report(char *buf, size_t cap);
+
+/* ------------------------------------------------------------------------------------------------
+ * Rasterizer.  Mirrors RasterizeGaussiansCUDA / RasterizeGaussiansBackwardCUDA / markVisible of the upstream
+ * extension; the three opaque byte buffers play the role of upstream's
+ * geomBuffer / binningBuffer / imgBuffer and must be kept alive (unmodified) from forward to backward.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mb_raster_inputs {
+    int32_t num_points;       /* P */
+    int32_t image_width;      /* GaussianRasterizationSettings.image_width  */
+    int32_t image_height;     /* GaussianRasterizationSettings.image_height */
+    int32_t sh_degree;        /* active degree D (0..3); used only when shs != NULL */
+    int32_t sh_coeffs;        /* M = second dim of shs ([P,M,3]); 0 when shs == NULL */
+    int32_t prefiltered;      /* accepted, unused (as upstream) */
+    int32_t debug;            /* 1: synchronise + check after every stage */
+    float tanfovx, tanfovy;
+    float scale_modifier;
+    const float *background;     /* [3]  */
+    const float *means3D;        /* [P,3] */
+    const float *opacities;      /* [P] (the [P,1] tensor) */
+    const float *colors_precomp; /* [P,3] or NULL   } exactly one of the two */
+    const float *shs;            /* [P,M,3] or NULL } */
+    const float *cov3D_precomp;  /* [P,6] (xx,xy,xz,yy,yz,zz) or NULL } exactly one of */
+    const float *scales;         /* [P,3] or NULL                      } cov3D_precomp | (scales & rotations) */
+    const float *rotations;      /* [P,4] (r,x,y,z), used as given (not normalised) or NULL */
+    const float *viewmatrix;     /* [16] */
+    const float *projmatrix;     /* [16] */
+    const float *campos;         /* [3]  */
+} mb_raster_inputs;
+
+size_t mb_raster_geom_bytes(int32_t num_points);
+size_t mb_raster_binning_bytes(int64_t capacity, int32_t image_width, int32_t image_height);
+size_t mb_raster_image_bytes(int32_t image_width, int32_t image_height);
+
+/* Stage 1: per-Gaussian projection (cull, cov2D, conic, radius, tile count, SH->RGB when shs is given), depth
+ * ordering and the instance offsets.  Writes radii[P] (0 for culled) and, if num_rendered_host != NULL (pinned host
+ * memory), enqueues an async copy of num_rendered (= sum of tiles touched) into it.  No host synchronisation. */
+int mb_raster_forward_geom(const mb_raster_inputs *in, void *geom, size_t geom_bytes, int32_t *radii,
+                           int64_t *num_rendered_host, mb_stream_t stream);
+
+/* Stage 2: instance emission, per-tile ordering, tile ranges, per-tile front-to-back alpha blend.
+ * `capacity` = number of instances `binning` was sized for; if num_rendered > capacity nothing is written out of
+ * bounds, the image is incomplete and the overflow is reported by mb_raster_query().  out_color is [3,H,W]. */
+int mb_raster_forward_render(const mb_raster_inputs *in, void *geom, void *binning, size_t binning_bytes,
+                             int64_t capacity, void *image_buf, size_t image_bytes, float *out_color, mb_stream_t stream);
+
+/* Reads back (synchronises `stream`) the counters of the last forward held in `geom`:
+ * num_rendered, number of visible Gaussians, overflow flag (1 if num_rendered exceeded capacity). */
+int mb_raster_query(const void *geom, int64_t *num_rendered, int64_t *num_visible, int32_t *overflow, mb_stream_t stream);
+
+/* Backward.  dL_dout is addressed as dL_dout[c*stride_c + y*stride_y + x*stride_x] (element strides), so both the
+ * contiguous [3,H,W] tensor and the permuted view of an [H,W,3] tensor (src/utils/gaussian_utils.py:418) are read
+ * in place.  Every output row is written (zeros for culled Gaussians); outputs for absent inputs may be NULL
+ * (dL_dsh when shs == NULL; dL_dscales / dL_drotations when cov3D_precomp != NULL; dL_dcolors is written in both
+ * colour modes).  grad_scratch: mb_raster_backward_scratch_bytes(P) bytes. */
+size_t mb_raster_backward_scratch_bytes(int32_t num_points);
+int mb_raster_backward(const mb_raster_inputs *in, const int32_t *radii, const void *geom, const void *binning,
+                       int64_t capacity /* as given to forward_render */, const void *image_buf, const float *dL_dout, int64_t stride_c, int64_t stride_y, int64_t stride_x,
+                       void *grad_scratch, size_t scratch_bytes, float *dL_dmeans2D /*[P,3]*/, float *dL_dcolors /*[P,3]*/,
+                       float *dL_dopacity /*[P]*/, float *dL_dmeans3D /*[P,3]*/, float *dL_dcov3D /*[P,6]*/,
+                       float *dL_dsh /*[P,M,3]*/, float *dL_dscales /*[P,3]*/, float *dL_drotations /*[P,4]*/,
+                       mb_stream_t stream);
+
+/* markVisible: out[i] = 1 iff the point is in front of the near plane (view-space z > 0.2). */
+int mb_mark_visible(const float *means3D, int32_t num_points, const float *viewmatrix, const float *projmatrix,
+                    uint8_t *out, mb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused pre-raster step (LBS + covariance + SH->RGB + activations), forward and backward.
+ * Gaussians [0, num_skinned) are articulated (tf = sum_b w_b T_b); [num_skinned, num_points) are static (tf = I),
+ * which covers hand-only (num_skinned = N), object-only (0) and composite scenes (src/modules/composite.py:50-60).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mb_pose_inputs {
+    int32_t num_points;
+    int32_t num_skinned;
+    int32_t num_bones;      /* B = columns of skin_wts = rows of bone_tf (identity "background" bone included) */
+    int32_t sh_degree;      /* 0..3 */
+    int32_t sh_coeffs;      /* K = 1 + second dim of f_rest; must be >= (sh_degree+1)^2 */
+    int32_t isotropic;      /* 1: log_scale is [N,1] (opts.isotropic_scaling) */
+    const float *xyz;           /* [N,3]  _xyz */
+    const float *log_scale;     /* [N,3] or [N,1]  _scaling (pre-exp) */
+    const float *quat;          /* [N,4]  _rotation (raw; normalised inside like build_rotation) */
+    const float *opacity_logit; /* [N]    _opacity (pre-sigmoid) */
+    const float *f_dc;          /* [N,1,3] _features_dc */
+    const float *f_rest;        /* [N,K-1,3] _features_rest */
+    const float *skin_wts;      /* [num_skinned,B] or NULL when num_skinned == 0 */
+    const float *bone_tf;       /* [B,4,4] */
+    const float *campos;        /* [3] */
+} mb_pose_inputs;
+
+/* tf_out: optional [num_skinned,4,4] (the reference materialises it; the fused path does not need it). */
+int mb_pose_forward(const mb_pose_inputs *in, float *posed_xyz /*[N,3]*/, float *posed_cov6 /*[N,6]*/,
+                    float *colors /*[N,3]*/, float *opacity /*[N]*/, float *tf_out, mb_stream_t stream);
+
+/* g_skin_wts: optional [num_skinned,B].  All other outputs are required and fully written. */
+int mb_pose_backward(const mb_pose_inputs *in, const float *g_posed_xyz, const float *g_posed_cov6, const float *g_colors,
+                     const float *g_opacity, float *g_xyz, float *g_log_scale, float *g_quat, float *g_opacity_logit,
+                     float *g_f_dc, float *g_f_rest, float *g_skin_wts, mb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * distCUDA2: mean squared distance to the 3 nearest other points (exact).
+ * ---------------------------------------------------------------------------------------------- */
+size_t mb_knn_workspace_bytes(int32_t num_points);
+int mb_dist2_knn3(const float *points /*[N,3]*/, int32_t num_points, float *out /*[N]*/, void *workspace,
+                  size_t workspace_bytes, mb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Utility exported for tests: stable LSD radix sort of (u32 key, u32 value) pairs on key bits [0, end_bit).
+ * n may be given on the host (n_host >= 0) or read from device memory (*n_dev, when n_host < 0, bounded by max_n).
+ * Result lands in keys_out / vals_out.  workspace: mb_sort_workspace_bytes(max_n).
+ * ---------------------------------------------------------------------------------------------- */
+size_t mb_sort_workspace_bytes(int64_t max_n);
+int mb_radix_sort_pairs(uint32_t *keys_in, uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out, int64_t n_host,
+                        const uint32_t *n_dev, int64_t max_n, int32_t end_bit, void *workspace, size_t workspace_bytes,
+                        mb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MANUS_B200_H */

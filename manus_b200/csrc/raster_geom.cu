@@ -1,0 +1,350 @@
+// Rasterizer stage 1 and binning:  per-Gaussian projection, depth ordering, instance
+// emission, per-tile ordering, tile ranges and the 48-B blend records (Appendix A.2, re-designed: Gaussians are
+// depth-sorted ONCE (P keys), instances are emitted in depth order and then only need a stable partition by tile id
+// (ceil(log2(tiles)/8) = 2 radix passes over D) instead of upstream's 6-pass 64-bit sort over D).
+//
+// This translation unit is compiled with --fmad=false: every quantity that feeds an integer decision (near cull,
+// radius ceil, tile rectangle truncation, depth order) is evaluated with individually rounded IEEE operations in a
+// fixed order, so radii / tiles touched / instance lists are reproducible bit-for-bit on any IEEE machine.
+#include "raster_state.cuh"
+
+namespace mb {
+
+struct PreArgs {
+    int P, W, H, gx, gy, deg, M;
+    float tanx, tany, focx, focy, scale_mod;
+    const float *means3D, *opac, *cov3D_precomp, *scales, *rots, *shs, *view, *proj, *campos;
+    GeomState g;
+    int32_t *radii;
+};
+
+__device__ __forceinline__ void tile_rect(float px, float py, int rad, int gx, int gy, int &x0, int &y0, int &x1, int &y1) {
+    x0 = min(gx, max(0, (int)((px - rad) / kTile)));
+    y0 = min(gy, max(0, (int)((py - rad) / kTile)));
+    x1 = min(gx, max(0, (int)((px + rad + kTile - 1) / kTile)));
+    y1 = min(gy, max(0, (int)((py + rad + kTile - 1) / kTile)));
+}
+
+template <bool kPrecompCov, bool kSH>
+__global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
+    __shared__ float cam[36];
+    const int tid = threadIdx.x;
+    if (tid < 16) cam[tid] = a.view[tid];
+    else if (tid < 32) cam[tid] = a.proj[tid - 16];
+    else if (tid < 35) cam[tid] = a.campos[tid - 32];
+    __syncthreads();
+    const float *v = cam, *p = cam + 16;
+    const int i = blockIdx.x * 256 + tid;
+    bool visible = false;
+    if (i < a.P) {
+        int radius = 0;
+        uint32_t tiles = 0, key = 0xffffffffu;
+        const float mx = a.means3D[3 * i], my = a.means3D[3 * i + 1], mz = a.means3D[3 * i + 2];
+        // A.1 step 2: view space
+        const float tx0 = v[0] * mx + v[4] * my + v[8] * mz + v[12];
+        const float ty0 = v[1] * mx + v[5] * my + v[9] * mz + v[13];
+        const float tz = v[2] * mx + v[6] * my + v[10] * mz + v[14];
+        if (tz > kNearZ) {
+            // step 3
+            const float hx = p[0] * mx + p[4] * my + p[8] * mz + p[12];
+            const float hy = p[1] * mx + p[5] * my + p[9] * mz + p[13];
+            const float hw = p[3] * mx + p[7] * my + p[11] * mz + p[15];
+            const float pw = 1.0f / (hw + 0.0000001f);
+            const float ndcx = hx * pw, ndcy = hy * pw;
+            // step 4: 3-D covariance
+            float c6[6];
+            if (kPrecompCov) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) c6[k] = a.cov3D_precomp[6 * (size_t)i + k];
+            } else {
+                float R[9], L[9];
+                quat_to_rot(a.rots[4 * i], a.rots[4 * i + 1], a.rots[4 * i + 2], a.rots[4 * i + 3], R);
+                const float s[3] = {a.scale_mod * a.scales[3 * i], a.scale_mod * a.scales[3 * i + 1], a.scale_mod * a.scales[3 * i + 2]};
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) L[3 * r + k] = R[3 * r + k] * s[k];
+                float S[9];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) acc += L[3 * r + k] * L[3 * c + k];
+                        S[3 * r + c] = acc;
+                    }
+                c6[0] = S[0]; c6[1] = S[1]; c6[2] = S[2]; c6[3] = S[4]; c6[4] = S[5]; c6[5] = S[8];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) a.g.cov3D[6 * (size_t)i + k] = c6[k];
+            }
+            // step 5: EWA projection with the clamped view-space point
+            const float limx = 1.3f * a.tanx, limy = 1.3f * a.tany;
+            float rx = tx0 / tz, ry = ty0 / tz;
+            rx = rx < -limx ? -limx : (rx > limx ? limx : rx);
+            ry = ry < -limy ? -limy : (ry > limy ? limy : ry);
+            const float tx = rx * tz, ty = ry * tz;
+            const float J00 = a.focx / tz, J02 = -(a.focx * tx) / (tz * tz);
+            const float J11 = a.focy / tz, J12 = -(a.focy * ty) / (tz * tz);
+            float M0[3], M1[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                M0[k] = J00 * v[4 * k + 0] + J02 * v[4 * k + 2];
+                M1[k] = J11 * v[4 * k + 1] + J12 * v[4 * k + 2];
+            }
+            const float S[9] = {c6[0], c6[1], c6[2], c6[1], c6[3], c6[4], c6[2], c6[4], c6[5]};
+            float SM0[3], SM1[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                SM0[k] = S[3 * k] * M0[0] + S[3 * k + 1] * M0[1] + S[3 * k + 2] * M0[2];
+                SM1[k] = S[3 * k] * M1[0] + S[3 * k + 1] * M1[1] + S[3 * k + 2] * M1[2];
+            }
+            const float ca = M0[0] * SM0[0] + M0[1] * SM0[1] + M0[2] * SM0[2] + kLowPass;
+            const float cb = M0[0] * SM1[0] + M0[1] * SM1[1] + M0[2] * SM1[2];
+            const float cc = M1[0] * SM1[0] + M1[1] * SM1[1] + M1[2] * SM1[2] + kLowPass;
+            // steps 6-7
+            const float det = ca * cc - cb * cb;
+            if (det != 0.0f) {
+                const float di = 1.0f / det;
+                const float mid = 0.5f * (ca + cc);
+                float disc = mid * mid - det;
+                if (disc < 0.1f) disc = 0.1f;
+                const float sq = sqrtf(disc);
+                const float l1 = mid + sq, l2 = mid - sq;
+                const int rad = (int)ceilf(3.0f * sqrtf(l1 > l2 ? l1 : l2));
+                // steps 8-9
+                const float px = ((ndcx + 1.0f) * a.W - 1.0f) * 0.5f, py = ((ndcy + 1.0f) * a.H - 1.0f) * 0.5f;
+                int x0, y0, x1, y1;
+                tile_rect(px, py, rad, a.gx, a.gy, x0, y0, x1, y1);
+                const int area = (x1 - x0) * (y1 - y0);
+                if (area > 0) {
+                    visible = true;
+                    radius = rad;
+                    tiles = (uint32_t)area;
+                    key = __float_as_uint(tz);
+                    a.g.rect[i] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
+                    a.g.xy[i] = make_float2(px, py);
+                    a.g.depth[i] = tz;
+                    a.g.conic_opacity[i] = make_float4(cc * di, -cb * di, ca * di, a.opac[i]);
+                    if (kSH) {   // step 10: colour from SH in the world-space view direction
+                        float dx = mx - cam[32], dy = my - cam[33], dz = mz - cam[34];
+                        const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+                        dx *= inv; dy *= inv; dz *= inv;
+                        float basis[16];
+                        sh_basis(a.deg, dx, dy, dz, basis);
+                        const int nb = (a.deg + 1) * (a.deg + 1);
+                        const float *sh = a.shs + (size_t)i * a.M * 3;
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            float r = 0.f;
+                            for (int k = 0; k < nb; ++k) r += basis[k] * sh[3 * k + ch];
+                            r += 0.5f;
+                            if (r < 0.f) { mask |= 1u << ch; r = 0.f; }
+                            a.g.rgb[3 * (size_t)i + ch] = r;
+                        }
+                        a.g.clamped[i] = mask;
+                    }
+                }
+            }
+        }
+        a.radii[i] = radius;
+        a.g.tiles_touched[i] = tiles;
+        a.g.depth_key[i] = key;
+        a.g.ident[i] = (uint32_t)i;
+    }
+    const unsigned vis = __ballot_sync(0xffffffffu, visible);
+    if ((tid & 31) == 0 && vis) atomicAdd(&a.g.counters[kCntVisible], (uint32_t)__popc(vis));
+}
+
+// one thread per depth-sorted Gaussian: writes its (tile id, gaussian id) run at its exclusive offset
+__global__ void __launch_bounds__(256) emit_instances_kernel(int P, int gx, const uint32_t *__restrict__ sorted_idx,
+                                                             const uint32_t *__restrict__ offsets,
+                                                             const uint32_t *__restrict__ tiles_touched,
+                                                             const ushort4 *__restrict__ rect,
+                                                             uint32_t *__restrict__ counters, int64_t capacity,
+                                                             uint32_t *__restrict__ tile_out, uint32_t *__restrict__ gid_out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (int64_t)counters[kCntRendered] > capacity) counters[kCntOverflow] = 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
+        const uint32_t g = sorted_idx[i];
+        if (tiles_touched[g] == 0) continue;
+        const ushort4 r = rect[g];
+        int64_t pos = offsets[i];
+        for (int y = r.y; y < r.w; ++y)
+            for (int x = r.x; x < r.z; ++x, ++pos)
+                if (pos < capacity) {
+                    tile_out[pos] = (uint32_t)(y * gx + x);
+                    gid_out[pos] = g;
+                }
+    }
+}
+
+// tile ranges + 48-B blend records, one thread per sorted instance
+__global__ void __launch_bounds__(256) finalize_instances_kernel(const uint32_t *__restrict__ counters, int64_t capacity,
+                                                                 const uint32_t *__restrict__ tile_sorted,
+                                                                 const uint32_t *__restrict__ gid_sorted,
+                                                                 const float2 *__restrict__ xy,
+                                                                 const float4 *__restrict__ conic_opacity,
+                                                                 const float *__restrict__ rgb, uint2 *__restrict__ ranges,
+                                                                 Record *__restrict__ records) {
+    int64_t n = counters[kCntRendered];
+    if (n > capacity) n = capacity;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t t = tile_sorted[i], g = gid_sorted[i];
+        if (i == 0 || tile_sorted[i - 1] != t) ranges[t].x = (uint32_t)i;
+        if (i == n - 1 || tile_sorted[i + 1] != t) ranges[t].y = (uint32_t)(i + 1);
+        const float2 c = xy[g];
+        const float4 co = conic_opacity[g];
+        Record r;
+        r.a = make_float4(c.x, c.y, co.x, co.y);
+        r.b = make_float4(co.z, co.w, rgb[3 * (size_t)g], rgb[3 * (size_t)g + 1]);
+        r.c = make_float4(rgb[3 * (size_t)g + 2], __uint_as_float(g), 0.f, 0.f);
+        records[i] = r;
+    }
+}
+
+int validate_raster_inputs(const mb_raster_inputs *in, const char *who) {
+    MB_REQUIRE(in != nullptr, "%s: null inputs", who);
+    MB_REQUIRE(in->num_points >= 0 && in->image_width > 0 && in->image_height > 0, "%s: bad sizes P=%d W=%d H=%d", who,
+               in->num_points, in->image_width, in->image_height);
+    MB_REQUIRE((in->colors_precomp != nullptr) != (in->shs != nullptr),
+               "%s: Please provide excatly one of either SHs or precomputed colors!", who);
+    const bool sr = in->scales != nullptr && in->rotations != nullptr;
+    MB_REQUIRE((in->cov3D_precomp != nullptr) != sr && ((in->scales != nullptr) == (in->rotations != nullptr)),
+               "%s: Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!", who);
+    MB_REQUIRE(in->num_points == 0 || (in->means3D && in->opacities), "%s: means3D / opacities missing", who);
+    MB_REQUIRE(in->background && in->viewmatrix && in->projmatrix && in->campos, "%s: camera tensors missing", who);
+    if (in->shs) {
+        MB_REQUIRE(in->sh_degree >= 0 && in->sh_degree <= 3, "%s: sh_degree %d not in 0..3", who, in->sh_degree);
+        MB_REQUIRE(in->sh_coeffs >= (in->sh_degree + 1) * (in->sh_degree + 1) && in->sh_coeffs <= 16,
+                   "%s: shs has %d coefficients, degree %d needs %d (max 16)", who, in->sh_coeffs, in->sh_degree,
+                   (in->sh_degree + 1) * (in->sh_degree + 1));
+    }
+    MB_REQUIRE(in->tanfovx > 0.f && in->tanfovy > 0.f, "%s: tanfov must be positive", who);
+    return MB_OK;
+}
+
+static int tile_bits(int tiles) {
+    int b = 0;
+    while ((1 << b) < tiles) ++b;
+    return b < 1 ? 1 : b;
+}
+
+// emission + per-tile ordering + ranges + records; shared with the render entry point (raster_blend.cu)
+int build_instances(const mb_raster_inputs *in, const RasterDims &d, const GeomState &g, const BinningState &b,
+                    const ImageState &im, int64_t capacity, cudaStream_t s) {
+    const bool dbg = in->debug != 0;
+    const int grid_p = max(1, min((d.P + 255) / 256, sm_count() * 8));
+    MB_CUDA(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)d.tiles, s));
+    {
+    KernelTimer kt("emit_instances", s);
+    emit_instances_kernel<<<grid_p, 256, 0, s>>>(d.P, d.gx, g.sorted_idx, g.offsets, g.tiles_touched, g.rect, g.counters,
+                                                 capacity, b.tile_a, b.gid_a);
+    }
+    int rc = check_launch("emit_instances", dbg, s);
+    if (rc) return rc;
+    SortWorkspace ws = carve_sort_workspace(b.sort_ws, capacity > 0 ? capacity : 1);
+    rc = radix_sort_pairs(b.tile_a, b.gid_a, b.tile_b, b.gid_b, -1, g.counters + kCntRendered, capacity, 0, tile_bits(d.tiles),
+                          ws, s, dbg);
+    if (rc) return rc;
+    const int grid_d = (int)max((int64_t)1, min((capacity + 255) / 256, (int64_t)sm_count() * 16));
+    {
+    KernelTimer kt("finalize_instances", s);
+    finalize_instances_kernel<<<grid_d, 256, 0, s>>>(g.counters, capacity, b.tile_b, b.gid_b, g.xy, g.conic_opacity,
+                                                     in->shs ? g.rgb : in->colors_precomp, im.ranges, b.records);
+    }
+    return check_launch("finalize_instances", dbg, s);
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" size_t mb_raster_geom_bytes(int32_t num_points) { return GeomState::carve(nullptr, num_points).bytes; }
+
+extern "C" size_t mb_raster_binning_bytes(int64_t capacity, int32_t, int32_t) {
+    return BinningState::carve(nullptr, capacity).bytes;
+}
+
+extern "C" size_t mb_raster_image_bytes(int32_t w, int32_t h) { return ImageState::carve(nullptr, w, h).bytes; }
+
+extern "C" int mb_raster_forward_geom(const mb_raster_inputs *in, void *geom, size_t geom_bytes, int32_t *radii,
+                                      int64_t *num_rendered_host, mb_stream_t stream) {
+    int rc = validate_raster_inputs(in, "mb_raster_forward_geom");
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const RasterDims d = raster_dims(in);
+    MB_REQUIRE(geom != nullptr && (d.P == 0 || radii != nullptr), "mb_raster_forward_geom: null geom / radii");
+    GeomState g = GeomState::carve(geom, d.P);
+    if (geom_bytes < g.bytes) {
+        set_error("mb_raster_forward_geom: geom buffer has %zu bytes, needs %zu", geom_bytes, g.bytes);
+        return MB_ERR_WORKSPACE;
+    }
+    const bool dbg = in->debug != 0;
+    MB_CUDA(cudaMemsetAsync(g.counters, 0, sizeof(uint32_t) * kNumCounters, s));
+    if (d.P > 0) {
+        PreArgs a;
+        a.P = d.P; a.W = d.W; a.H = d.H; a.gx = d.gx; a.gy = d.gy; a.deg = in->sh_degree; a.M = in->sh_coeffs;
+        a.tanx = in->tanfovx; a.tany = in->tanfovy; a.focx = d.focx; a.focy = d.focy; a.scale_mod = in->scale_modifier;
+        a.means3D = in->means3D; a.opac = in->opacities; a.cov3D_precomp = in->cov3D_precomp; a.scales = in->scales;
+        a.rots = in->rotations; a.shs = in->shs; a.view = in->viewmatrix; a.proj = in->projmatrix; a.campos = in->campos;
+        a.g = g; a.radii = radii;
+        const int grid = (d.P + 255) / 256;
+        {
+        KernelTimer kt("preprocess", s);
+        if (in->cov3D_precomp) {
+            if (in->shs) preprocess_kernel<true, true><<<grid, 256, 0, s>>>(a);
+            else preprocess_kernel<true, false><<<grid, 256, 0, s>>>(a);
+        } else {
+            if (in->shs) preprocess_kernel<false, true><<<grid, 256, 0, s>>>(a);
+            else preprocess_kernel<false, false><<<grid, 256, 0, s>>>(a);
+        }
+        }
+        rc = check_launch("preprocess", dbg, s);
+        if (rc) return rc;
+        // depth order (stable; culled Gaussians carry key 0xffffffff and sink to the end)
+        SortWorkspace ws = carve_sort_workspace(g.sort_ws, d.P);
+        rc = radix_sort_pairs(g.depth_key, g.ident, g.sorted_key, g.sorted_idx, d.P, nullptr, d.P, 0, 32, ws, s, dbg);
+        if (rc) return rc;
+        // instance offsets in depth order; total = num_rendered
+        rc = exclusive_scan_gather(g.tiles_touched, g.sorted_idx, g.offsets, g.counters + kCntRendered, d.P, g.scan_partials,
+                                   s, dbg);
+        if (rc) return rc;
+    }
+    if (num_rendered_host) {
+        // 64-bit host slot, 32-bit device counter: clear the high word first
+        *num_rendered_host = 0;
+        MB_CUDA(cudaMemcpyAsync(num_rendered_host, g.counters + kCntRendered, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    }
+    return MB_OK;
+}
+
+extern "C" int mb_raster_query(const void *geom, int64_t *num_rendered, int64_t *num_visible, int32_t *overflow,
+                               mb_stream_t stream) {
+    MB_REQUIRE(geom != nullptr, "mb_raster_query: null geom");
+    uint32_t host[kNumCounters];
+    GeomState g = GeomState::carve(const_cast<void *>(geom), 1);
+    MB_CUDA(cudaMemcpyAsync(host, g.counters, sizeof(host), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    MB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (num_rendered) *num_rendered = host[kCntRendered];
+    if (num_visible) *num_visible = host[kCntVisible];
+    if (overflow) *overflow = (int32_t)host[kCntOverflow];
+    return MB_OK;
+}
+
+__global__ void mark_visible_kernel(const float *__restrict__ means3D, int P, const float *__restrict__ view,
+                                    uint8_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float z = view[2] * means3D[3 * i] + view[6] * means3D[3 * i + 1] + view[10] * means3D[3 * i + 2] + view[14];
+    out[i] = z > kNearZ ? 1 : 0;
+}
+
+extern "C" int mb_mark_visible(const float *means3D, int32_t num_points, const float *viewmatrix, const float *projmatrix,
+                               uint8_t *out, mb_stream_t stream) {
+    MB_REQUIRE(num_points >= 0, "mb_mark_visible: negative count");
+    if (num_points == 0) return MB_OK;
+    MB_REQUIRE(means3D && viewmatrix && projmatrix && out, "mb_mark_visible: null pointer");
+    mark_visible_kernel<<<(num_points + 255) / 256, 256, 0, (cudaStream_t)stream>>>(means3D, num_points, viewmatrix, out);
+    return check_launch("mark_visible", false, (cudaStream_t)stream);
+}

@@ -1,0 +1,177 @@
+"""View-sharded data parallelism for the render path.
+
+The reference trains one view per optimizer step on one GPU and emulates larger batches with gradient accumulation
+(``final_loss / accum_iter``, /root/reference/src/modules/hand_dynamic.py:248,259-277).  Here every rank holds the same
+Gaussians, renders its own view forward + backward, and the per-Gaussian parameter gradients -- which are plain sums
+over views -- are combined by ONE all-reduce of a single flat buffer per step (59 floats per Gaussian at SH degree 3:
+xyz 3 | f_dc 3 | f_rest 45 | opacity 1 | scaling 3 | rotation 4, the six Adam param groups of
+src/models/gaussian.py:133-140).  There is no exchange inside a frame.
+
+``FlatGaussians`` owns the flat parameter / gradient buffers and hands out the six per-parameter views;
+``shard_views`` is the round-robin view assignment; ``allreduce_gradients`` is the collective (NCCL on GPUs; gloo in the
+CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+PARAM_ORDER = ("xyz", "f_dc", "f_rest", "opacity_logit", "log_scale", "quat")
+
+
+def param_widths(sh_coeffs: int = 16, isotropic: bool = False) -> Dict[str, int]:
+    return {"xyz": 3, "f_dc": 3, "f_rest": 3 * (sh_coeffs - 1), "opacity_logit": 1, "log_scale": 1 if isotropic else 3, "quat": 4}
+
+
+def param_shapes(n: int, sh_coeffs: int = 16, isotropic: bool = False):
+    return {"xyz": (n, 3), "f_dc": (n, 1, 3), "f_rest": (n, sh_coeffs - 1, 3), "opacity_logit": (n, 1),
+            "log_scale": (n, 1 if isotropic else 3), "quat": (n, 4)}
+
+
+class FlatGaussians:
+    """All parameters of a GaussianModel in one contiguous fp32 buffer, gradients in a second one of the same layout
+    (segment per parameter, so every view is a dense tensor the kernels can read / write directly)."""
+
+    def __init__(self, n: int, device, sh_coeffs: int = 16, isotropic: bool = False):
+        self.n, self.sh_coeffs, self.isotropic = n, sh_coeffs, isotropic
+        widths = param_widths(sh_coeffs, isotropic)
+        self.floats_per_gaussian = sum(widths.values())
+        self.data = torch.zeros(n * self.floats_per_gaussian, dtype=torch.float32, device=device)
+        self.grad = torch.zeros_like(self.data)
+        self.params: Dict[str, torch.Tensor] = {}
+        self.grads: Dict[str, torch.Tensor] = {}
+        off = 0
+        shapes = param_shapes(n, sh_coeffs, isotropic)
+        for name in PARAM_ORDER:
+            cnt = n * widths[name]
+            self.params[name] = self.data[off: off + cnt].view(shapes[name])
+            self.grads[name] = self.grad[off: off + cnt].view(shapes[name])
+            off += cnt
+
+    @classmethod
+    def from_scene(cls, scene, device):
+        fg = cls(scene.n, device, sh_coeffs=1 + scene.f_rest.shape[1], isotropic=scene.log_scale.shape[1] == 1)
+        for name in PARAM_ORDER:
+            fg.params[name].copy_(torch.as_tensor(getattr(scene, name)).reshape(fg.params[name].shape))
+        return fg
+
+    def leaves(self) -> List[torch.Tensor]:
+        """The six parameters as autograd leaves, in the order pose_gaussians takes them
+        (xyz, log_scale, quat, opacity_logit, f_dc, f_rest)."""
+        order = ("xyz", "log_scale", "quat", "opacity_logit", "f_dc", "f_rest")
+        return [self.params[k].detach().requires_grad_(True) for k in order]
+
+    def scratch_like_grad(self) -> "FlatGaussians":
+        """A second gradient buffer with the same layout (for accumulating more than one view per rank and step)."""
+        other = FlatGaussians.__new__(FlatGaussians)
+        other.n, other.sh_coeffs, other.isotropic = self.n, self.sh_coeffs, self.isotropic
+        other.floats_per_gaussian = self.floats_per_gaussian
+        other.data, other.params = self.data, self.params
+        other.grad = torch.zeros_like(self.grad)
+        other.grads = {}
+        off = 0
+        for name in PARAM_ORDER:
+            cnt = self.grads[name].numel()
+            other.grads[name] = other.grad[off: off + cnt].view(self.grads[name].shape)
+            off += cnt
+        return other
+
+    def allreduce_bytes(self) -> int:
+        return self.grad.numel() * 4
+
+
+def shard_views(views: Sequence[int], rank: int, world_size: int) -> List[int]:
+    """Round-robin: rank r renders views {v : index(v) mod R == r}."""
+    return [v for i, v in enumerate(views) if i % world_size == rank]
+
+
+def allreduce_gradients(flat_grad: torch.Tensor, world_size: Optional[int] = None, average: bool = True) -> None:
+    """One in-place SUM all-reduce of the flat per-Gaussian gradient buffer; ``average`` divides by the number of views
+    in the step, which is exactly the reference's ``final_loss / accum_iter`` scaling."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+        world_size = dist.get_world_size()
+    if average and world_size and world_size > 1:
+        flat_grad.div_(world_size)
+
+
+def sharded_step(flat: FlatGaussians, my_views: Sequence[int],
+                 render_backward: Callable[[FlatGaussians, int, Dict[str, torch.Tensor]], torch.Tensor],
+                 scratch: Optional[FlatGaussians] = None, global_views: Optional[int] = None) -> torch.Tensor:
+    """Gradients of one optimisation step.  ``render_backward(flat, view, sink)`` runs forward + backward of one view and
+    OVERWRITES the tensors in ``sink`` (layout of ``flat.grads``) with that view's parameter gradients, returning the scalar
+    loss.  The first view writes straight into the flat all-reduce buffer, further views of the same rank go through
+    ``scratch`` and are added.  Then ONE all-reduce (SUM) of the flat buffer and a division by the global number of views
+    (the reference's ``final_loss / accum_iter``).  ``global_views`` = number of views of this step over all ranks (every
+    rank can compute it from the view list); when omitted it is obtained with a second tiny all-reduce and a host read.
+    Returns the mean loss over all views of the step (device scalar)."""
+    dev = flat.grad.device
+    total = torch.zeros((), device=dev)
+    if len(my_views) == 0:
+        flat.grad.zero_()
+    for j, v in enumerate(my_views):
+        if j == 0:
+            loss = render_backward(flat, v, flat.grads)
+        else:
+            if scratch is None:
+                scratch = flat.scratch_like_grad()
+            loss = render_backward(flat, v, scratch.grads)
+            flat.grad.add_(scratch.grad)
+        total = total + loss.detach().reshape(())
+    n_views = float(len(my_views))
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
+        stats = torch.stack([total, torch.tensor(n_views, device=dev)])
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        total = stats[0]
+        n_views = float(global_views) if global_views is not None else float(stats[1])
+    if n_views > 1:
+        flat.grad.div_(n_views)
+    return total / max(n_views, 1.0)
+
+
+class SceneRenderer:
+    """Everything one rank needs to render views of a (hand | object | composite) scene forward + backward through the
+    public API: resident parameters (flat), skin weights, rest bones, and per-view cameras / bone poses."""
+
+    def __init__(self, scene, device, width: int = 1920, height: int = 1080, bg=(1.0, 1.0, 1.0), sh_degree: int = 3):
+        from . import synth
+
+        self.device, self.W, self.H, self.sh_degree = device, width, height, sh_degree
+        self.flat = FlatGaussians.from_scene(scene, device)
+        self.n_hand = scene.n_hand
+        self.skin = None if scene.skin_wts is None else torch.as_tensor(scene.skin_wts).to(device)
+        self.bones_rest = None if scene.bones_rest is None else torch.as_tensor(scene.bones_rest).to(device)
+        self.bg = torch.tensor(bg, dtype=torch.float32, device=device)
+        self._synth = synth
+        self._cams = {}
+
+    def view_inputs_host(self, view: int):
+        """Per-step inputs as pinned host tensors: camera (view 16 | proj 16 | centre 3 | fovx, fovy) and posed bones [20,16]."""
+        if view not in self._cams:
+            cam = self._synth.camera(view, self.W, self.H)
+            import numpy as np
+            packed = np.concatenate([cam.world_view_transform.reshape(-1), cam.full_proj_transform.reshape(-1),
+                                     cam.camera_center.reshape(-1), [cam.fovx, cam.fovy]]).astype("float32")
+            bones = self._synth.posed_bones(view).reshape(-1).astype("float32")
+            self._cams[view] = (cam, torch.from_numpy(packed).pin_memory(), torch.from_numpy(bones).pin_memory())
+        return self._cams[view]
+
+    def render(self, view: int, sink: Optional[Dict[str, torch.Tensor]] = None, cam_dev=None, bones_dev=None):
+        """Forward of one view through render_fused; returns the result dict (image is out['render'], HWC)."""
+        from .cameras import Camera
+        from .pose import bone_transforms
+        from .render import render_fused
+
+        cam, cam_host, bones_host = self.view_inputs_host(view)
+        if cam_dev is None:
+            cam_dev = cam_host.to(self.device, non_blocking=True)
+            bones_dev = bones_host.to(self.device, non_blocking=True)
+        dcam = Camera(cam.width, cam.height, cam.fovx, cam.fovy, cam_dev[0:16].view(4, 4), cam_dev[16:32].view(4, 4), cam_dev[32:35], None)
+        bone_tf = None
+        if self.n_hand > 0:
+            bone_tf = bone_transforms(bones_dev.view(-1, 4, 4), self.bones_rest, True)
+        return render_fused(self.flat.leaves(), self.skin, bone_tf, dcam, self.bg, self.sh_degree, self.flat.isotropic,
+                            self.n_hand, grad_sink=sink)

@@ -1,0 +1,265 @@
+"""Drop-in host side of the tile rasterizer: ``GaussianRasterizationSettings`` / ``GaussianRasterizer``.
+
+Same names, argument meaning, return values and error behaviour as the ``diff_gaussian_rasterization`` package MANUS
+imports (/root/reference/src/utils/gaussian_utils.py:18-21) and calls (:378-416): 12-field NamedTuple settings,
+``GaussianRasterizer(raster_settings)(means3D, means2D, opacities, shs, colors_precomp, scales, rotations,
+cov3D_precomp) -> (color[3,H,W], radii[N] int32)``, gradients for (means3D, means2D, sh, colors_precomp, opacities,
+scales, rotations, cov3Ds_precomp) with ``means2D`` receiving dL/d(NDC-scaled screen xy) as [N,3] (z = 0) -- the
+side channel ``add_densification_stats`` reads (src/models/gaussian.py:335-338).  SURVEY.md section 8b.
+
+All arithmetic happens in the CUDA library behind the C ABI (include/manus_b200.h); torch is used for memory and
+the current stream only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import ptr
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+def _dense(t: Optional[torch.Tensor], shape=None) -> Optional[torch.Tensor]:
+    """fp32, contiguous, on the GPU; None / empty -> None.  Callers hand over slices and [1,4,4] / [1,3] camera tensors."""
+    if t is None or t.numel() == 0:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    t = t.contiguous()
+    return t if shape is None else t.reshape(shape)
+
+
+class _Plan:
+    """How instance capacity is chosen.  'exact': one host read of num_rendered per forward (what upstream does).
+    'reserve': no host synchronisation -- capacity is the high-water mark of earlier frames times a margin; an overflow
+    is detected at the next host read and the frame is redone exactly."""
+    mode = "exact"
+    margin = 1.3
+    high_water = {}
+
+
+def set_capacity_mode(mode: str, margin: float = 1.3) -> None:
+    assert mode in ("exact", "reserve")
+    _Plan.mode, _Plan.margin = mode, margin
+    _Plan.high_water.clear()
+
+
+class RasterState:
+    """Opaque state kept from forward to backward (upstream: geomBuffer / binningBuffer / imgBuffer / num_rendered)."""
+    __slots__ = ("inputs", "keep", "geom", "binning", "image", "capacity", "num_rendered", "radii", "host_count", "event", "key")
+
+    def resolve(self) -> int:
+        """num_rendered of this frame (waits for the count copy if it is still in flight); raises on overflow."""
+        if self.num_rendered < 0:
+            self.event.synchronize()
+            self.num_rendered = int(self.host_count.item())
+            _Plan.high_water[self.key] = max(_Plan.high_water.get(self.key, 0), self.num_rendered)
+            if self.num_rendered > self.capacity:
+                raise _lib.ManusB200Error(
+                    f"instance capacity overflow: frame needed {self.num_rendered} instances, {self.capacity} were reserved; "
+                    "the image of this frame is incomplete. Use set_capacity_mode('exact') or a larger margin.")
+        return self.num_rendered
+
+
+def _make_inputs(settings: GaussianRasterizationSettings, means3D, opacities, colors_precomp, shs, cov3D_precomp, scales,
+                 rotations, keep: list) -> _lib.RasterInputs:
+    dev = means3D.device
+    bg = _dense(settings.bg.to(dev), (3,))
+    view = _dense(settings.viewmatrix.to(dev), (16,))
+    proj = _dense(settings.projmatrix.to(dev), (16,))
+    cam = _dense(settings.campos.to(dev), (3,))
+    keep += [bg, view, proj, cam]
+    ri = _lib.RasterInputs()
+    ri.num_points = means3D.shape[0]
+    ri.image_width, ri.image_height = int(settings.image_width), int(settings.image_height)
+    ri.sh_degree = int(settings.sh_degree)
+    ri.sh_coeffs = 0 if shs is None else int(shs.shape[1])
+    ri.prefiltered, ri.debug = int(bool(settings.prefiltered)), int(bool(settings.debug))
+    ri.tanfovx, ri.tanfovy = float(settings.tanfovx), float(settings.tanfovy)
+    ri.scale_modifier = float(settings.scale_modifier)
+    ri.background, ri.viewmatrix, ri.projmatrix, ri.campos = ptr(bg), ptr(view), ptr(proj), ptr(cam)
+    ri.means3D, ri.opacities = ptr(means3D), ptr(opacities)
+    ri.colors_precomp, ri.shs = ptr(colors_precomp), ptr(shs)
+    ri.cov3D_precomp, ri.scales, ri.rotations = ptr(cov3D_precomp), ptr(scales), ptr(rotations)
+    return ri
+
+
+def rasterize_forward(settings: GaussianRasterizationSettings, means3D, opacities, colors_precomp=None, shs=None,
+                      cov3D_precomp=None, scales=None, rotations=None, capacity: Optional[int] = None):
+    """-> (color[3,H,W], radii[N], RasterState).  Inputs must already be dense fp32 CUDA tensors (or None)."""
+    L = _lib.lib()
+    if not means3D.is_cuda:
+        raise _lib.ManusB200Error("manus_b200 rasterizer needs CUDA tensors (there is no CPU path)")
+    dev = means3D.device
+    N, H, W = means3D.shape[0], int(settings.image_height), int(settings.image_width)
+    st = RasterState()
+    st.keep = [means3D, opacities, colors_precomp, shs, cov3D_precomp, scales, rotations]
+    st.inputs = _make_inputs(settings, means3D, opacities, colors_precomp, shs, cov3D_precomp, scales, rotations, st.keep)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        st.geom = torch.empty(L.mb_raster_geom_bytes(N), dtype=torch.uint8, device=dev)
+        st.image = torch.empty(L.mb_raster_image_bytes(W, H), dtype=torch.uint8, device=dev)
+        st.radii = torch.empty(N, dtype=torch.int32, device=dev)
+        color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        st.key = (dev.index, N, H, W)
+        st.host_count = torch.zeros(1, dtype=torch.int64).pin_memory()
+        _lib.check(L.mb_raster_forward_geom(C.byref(st.inputs), ptr(st.geom), st.geom.numel(), ptr(st.radii),
+                                            st.host_count.data_ptr(), stream), "mb_raster_forward_geom")
+        st.event = torch.cuda.Event()
+        st.event.record(torch.cuda.current_stream(dev))
+        st.num_rendered = -1
+        if capacity is None and _Plan.mode == "reserve" and st.key in _Plan.high_water:
+            capacity = int(_Plan.high_water[st.key] * _Plan.margin) + 1024      # no host synchronisation
+        elif capacity is None:
+            st.capacity = 1 << 62
+            capacity = st.resolve()                                              # one 8-byte host read, like upstream
+        st.capacity = int(capacity)
+        st.binning = torch.empty(L.mb_raster_binning_bytes(st.capacity, W, H), dtype=torch.uint8, device=dev)
+        _lib.check(L.mb_raster_forward_render(C.byref(st.inputs), ptr(st.geom), ptr(st.binning), st.binning.numel(), st.capacity,
+                                              ptr(st.image), st.image.numel(), ptr(color), stream), "mb_raster_forward_render")
+    return color, st.radii, st
+
+
+def raster_query(st: RasterState):
+    """(num_rendered, num_visible, overflow) of a finished forward; synchronises the current stream."""
+    L = _lib.lib()
+    nr, nv, ov = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+    dev = st.geom.device
+    with torch.cuda.device(dev):
+        _lib.check(L.mb_raster_query(ptr(st.geom), C.byref(nr), C.byref(nv), C.byref(ov),
+                                     torch.cuda.current_stream(dev).cuda_stream), "mb_raster_query")
+    return nr.value, nv.value, ov.value
+
+
+def rasterize_backward(st: RasterState, grad_color: torch.Tensor):
+    """grad_color: [3,H,W] with ANY strides (the permuted HWC view the MANUS losses produce is read in place)."""
+    L = _lib.lib()
+    ri = st.inputs
+    N, M = ri.num_points, ri.sh_coeffs
+    dev = st.geom.device
+    if grad_color.dtype != torch.float32:
+        grad_color = grad_color.float()
+    sc, sy, sx = grad_color.stride()
+    new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    g_means2D, g_colors, g_opacity, g_means3D, g_cov3D = new(N, 3), new(N, 3), new(N, 1), new(N, 3), new(N, 6)
+    g_sh = new(N, M, 3) if ri.shs else None
+    g_scales = new(N, 3) if not ri.cov3D_precomp else None
+    g_rot = new(N, 4) if not ri.cov3D_precomp else None
+    with torch.cuda.device(dev):
+        scratch = torch.empty(L.mb_raster_backward_scratch_bytes(N), dtype=torch.uint8, device=dev)
+        _lib.check(L.mb_raster_backward(C.byref(ri), ptr(st.radii), ptr(st.geom), ptr(st.binning), st.capacity, ptr(st.image),
+                                        ptr(grad_color), sc, sy, sx, ptr(scratch), scratch.numel(), ptr(g_means2D),
+                                        ptr(g_colors), ptr(g_opacity), ptr(g_means3D), ptr(g_cov3D), ptr(g_sh), ptr(g_scales),
+                                        ptr(g_rot), torch.cuda.current_stream(dev).cuda_stream), "mb_raster_backward")
+    return g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rot
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+        d = lambda t: _dense(t)
+        m3, op = d(means3D), d(opacities)
+        if m3 is None:   # N == 0: upstream returns early with the background image
+            H, W = int(raster_settings.image_height), int(raster_settings.image_width)
+            dev = means3D.device
+            color = raster_settings.bg.to(dev).float().reshape(3, 1, 1).expand(3, H, W).contiguous()
+            ctx.state = None
+            return color, torch.zeros(0, dtype=torch.int32, device=dev)
+        if m3.dim() != 2 or m3.shape[1] != 3:
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")
+        color, radii, st = rasterize_forward(raster_settings, m3, op.reshape(-1), d(colors_precomp), d(sh), d(cov3Ds_precomp),
+                                             d(scales), d(rotations))
+        ctx.state = st
+        ctx.shapes = (means3D.shape, means2D.shape, opacities.shape)
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii):
+        st = ctx.state
+        if st is None:
+            return (None,) * 9
+        st.resolve()
+        g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rot = rasterize_backward(st, grad_out_color)
+        m3_shape, m2_shape, op_shape = ctx.shapes
+        ctx.state = None
+        return (g_means3D.reshape(m3_shape), g_means2D.reshape(m2_shape), g_sh, g_colors if not st.inputs.shs else None,
+                g_opacity.reshape(op_shape), g_scales, g_rot, g_cov3D if st.inputs.cov3D_precomp else None, None)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                                     raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions: torch.Tensor) -> torch.Tensor:
+        L = _lib.lib()
+        with torch.no_grad():
+            p = _dense(positions)
+            n = 0 if p is None else p.shape[0]
+            out = torch.zeros(n, dtype=torch.uint8, device=positions.device)
+            if n:
+                rs = self.raster_settings
+                view, proj = _dense(rs.viewmatrix.to(p.device), (16,)), _dense(rs.projmatrix.to(p.device), (16,))
+                with torch.cuda.device(p.device):
+                    _lib.check(L.mb_mark_visible(ptr(p), n, ptr(view), ptr(proj), ptr(out),
+                                                 torch.cuda.current_stream(p.device).cuda_stream), "mb_mark_visible")
+            return out.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        empty = torch.Tensor([])
+        return rasterize_gaussians(means3D, means2D, empty if shs is None else shs,
+                                   empty if colors_precomp is None else colors_precomp, opacities,
+                                   empty if scales is None else scales, empty if rotations is None else rotations,
+                                   empty if cov3D_precomp is None else cov3D_precomp, self.raster_settings)
+
+
+def debug_views(st: RasterState):
+    """Typed views into the opaque buffers of a finished forward (layout: manus_b200/csrc/raster_state.cuh).
+    For tests and diagnostics only: {'final_T' [H,W], 'n_contrib' [H,W], 'ranges' [tiles,2], 'records' [cap,12],
+    'point_list' [num_rendered] (gaussian id per sorted instance)}."""
+    al = lambda n: (n + 255) // 256 * 256
+    H, W = st.inputs.image_height, st.inputs.image_width
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    px = H * W
+    img = st.image
+    o1 = al(px * 4)
+    o2 = o1 + al(px * 4)
+    final_T = img[: px * 4].view(torch.float32).reshape(H, W)
+    n_contrib = img[o1: o1 + px * 4].view(torch.int32).reshape(H, W)
+    ranges = img[o2: o2 + tiles * 8].view(torch.int32).reshape(tiles, 2)
+    cap = max(st.capacity, 1)
+    ro = 4 * al(cap * 4)
+    records = st.binning[ro: ro + cap * 48].view(torch.float32).reshape(cap, 12)
+    n = st.resolve()
+    point_list = records[: min(n, cap), 9].contiguous().view(torch.int32)
+    return dict(final_T=final_T, n_contrib=n_contrib, ranges=ranges, records=records, point_list=point_list)

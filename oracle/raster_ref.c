@@ -187,31 +187,55 @@ static void blend_tile(ctx_t *c, int tl, float *out_color) {
         }
 }
 
-typedef struct { ctx_t *c; float *out; int next, ntile; pthread_mutex_t mu; } tile_job_t;
+/* CPU-baseline timing only: blend just the tiles with (tile % stride) == offset (bench.py reports the sample). */
+static int g_tile_stride = 1, g_tile_offset = 0;
+void raster_ref_set_tile_sampling(int stride, int offset) { g_tile_stride = stride < 1 ? 1 : stride; g_tile_offset = offset; }
+static int tile_selected(int t) { return g_tile_stride == 1 || (t % g_tile_stride) == g_tile_offset; }
+
+typedef struct bwd_acc { real *gm2, *gcon, *gop, *gcol; } bwd_acc_t;
+static void bwd_tile(const ctx_t *c, int tl, const float *dL_dout, bwd_acc_t *a);
+
+typedef struct {
+    ctx_t *c; float *out;                         /* forward */
+    const float *dL_dout; bwd_acc_t *acc;         /* backward: one private accumulator set per thread */
+    int next, ntile, backward, nthreads_started;
+    pthread_mutex_t mu;
+} tile_job_t;
 
 static void *tile_worker(void *arg) {
     tile_job_t *j = (tile_job_t *)arg;
+    pthread_mutex_lock(&j->mu);
+    const int me = j->nthreads_started++;
+    pthread_mutex_unlock(&j->mu);
     for (;;) {
         pthread_mutex_lock(&j->mu);
         int t0 = j->next; j->next += 8;
         pthread_mutex_unlock(&j->mu);
         if (t0 >= j->ntile) break;
-        for (int t = t0; t < t0 + 8 && t < j->ntile; t++) blend_tile(j->c, t, j->out);
+        for (int t = t0; t < t0 + 8 && t < j->ntile; t++) {
+            if (!tile_selected(t)) continue;
+            if (j->backward) bwd_tile(j->c, t, j->dL_dout, &j->acc[me]);
+            else blend_tile(j->c, t, j->out);
+        }
     }
     return NULL;
 }
 
-static void run_tiles(ctx_t *c, float *out_color, int nthreads) {
-    tile_job_t j; j.c = c; j.out = out_color; j.next = 0; j.ntile = c->gx * c->gy;
-    pthread_mutex_init(&j.mu, NULL);
-    if (nthreads <= 1) tile_worker(&j);
+static void run_job(tile_job_t *j, int nthreads) {
+    j->next = 0; j->nthreads_started = 0; j->ntile = j->c->gx * j->c->gy;
+    pthread_mutex_init(&j->mu, NULL);
+    if (nthreads <= 1) tile_worker(j);
     else {
         pthread_t th[256];
-        if (nthreads > 256) nthreads = 256;
-        for (int i = 0; i < nthreads; i++) pthread_create(&th[i], NULL, tile_worker, &j);
+        for (int i = 0; i < nthreads; i++) pthread_create(&th[i], NULL, tile_worker, j);
         for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
     }
-    pthread_mutex_destroy(&j.mu);
+    pthread_mutex_destroy(&j->mu);
+}
+
+static void run_tiles(ctx_t *c, float *out_color, int nthreads) {
+    tile_job_t j; memset(&j, 0, sizeof(j)); j.c = c; j.out = out_color;
+    run_job(&j, nthreads > 256 ? 256 : nthreads);
 }
 
 /* ---- forward ----------------------------------------------------------------------------------- */
@@ -345,64 +369,80 @@ void raster_ref_get_state(const ctx_t *c, float *xy, float *depth, float *conic,
 }
 
 /* ---- backward (A.4) ------------------------------------------------------------------------------ */
+static void bwd_tile(const ctx_t *c, int tl, const float *dL_dout, bwd_acc_t *a) {
+    const int W = c->W, H = c->H;
+    int tx0 = (tl % c->gx) * TILE, ty0 = (tl / c->gx) * TILE;
+    int64_t r0 = c->range[2 * tl], r1 = c->range[2 * tl + 1];
+    if (r1 <= r0) return;
+    for (int ly = 0; ly < TILE; ly++)
+        for (int lx = 0; lx < TILE; lx++) {
+            int x = tx0 + lx, y = ty0 + ly;
+            if (x >= W || y >= H) continue;
+            size_t pix = (size_t)y * W + x;
+            const real Tfinal = c->finalT[pix];
+            real T = Tfinal;
+            const int last_contributor = c->ncontrib[pix];
+            real dpix[3] = {dL_dout[pix], dL_dout[(size_t)W * H + pix], dL_dout[2 * (size_t)W * H + pix]};
+            real accum[3] = {0, 0, 0}, last_color[3] = {0, 0, 0}, last_alpha = 0;
+            int contributor = (int)(r1 - r0);
+            for (int64_t k = r1 - 1; k >= r0; k--) {
+                contributor--;
+                if (contributor >= last_contributor) continue;
+                int g = c->list[k];
+                real dx = c->xy[2 * g] - (real)x, dy = c->xy[2 * g + 1] - (real)y;
+                real cx = c->conic[3 * g], cy = c->conic[3 * g + 1], cz = c->conic[3 * g + 2], op = c->opac[g];
+                real power = (real)-0.5 * (cx * dx * dx + cz * dy * dy) - cy * dx * dy;
+                if (power > 0) continue;
+                real G = (real)(sizeof(real) == 4 ? expf((float)power) : exp((double)power));
+                real al = op * G; if (al > (real)0.99) al = (real)0.99;
+                if (al < (real)(1.0 / 255.0)) continue;
+                T = T / (1 - al);
+                real dch = al * T, dL_dalpha = 0;
+                for (int ch = 0; ch < 3; ch++) {
+                    real col = c->rgb[3 * (size_t)g + ch];
+                    accum[ch] = last_alpha * last_color[ch] + (1 - last_alpha) * accum[ch];
+                    last_color[ch] = col;
+                    dL_dalpha += (col - accum[ch]) * dpix[ch];
+                    a->gcol[3 * (size_t)g + ch] += dch * dpix[ch];
+                }
+                dL_dalpha *= T;
+                last_alpha = al;
+                real bgdot = c->bg[0] * dpix[0] + c->bg[1] * dpix[1] + c->bg[2] * dpix[2];
+                dL_dalpha += (-Tfinal / (1 - al)) * bgdot;
+                real dL_dG = op * dL_dalpha; /* quirk 1: 0.99 clamp not masked */
+                real gdx = G * dx, gdy = G * dy;
+                real dG_ddelx = -gdx * cx - gdy * cy, dG_ddely = -gdy * cz - gdx * cy;
+                a->gm2[2 * g] += dL_dG * dG_ddelx * ((real)0.5 * W);
+                a->gm2[2 * g + 1] += dL_dG * dG_ddely * ((real)0.5 * H);
+                a->gcon[3 * g] += (real)-0.5 * gdx * dx * dL_dG;
+                a->gcon[3 * g + 1] += (real)-0.5 * gdx * dy * dL_dG;
+                a->gcon[3 * g + 2] += (real)-0.5 * gdy * dy * dL_dG;
+                a->gop[g] += G * dL_dalpha;
+            }
+        }
+}
+
+/* nthreads <= 1: single thread, tile order then pixel order (deterministic -- the checker).  nthreads > 1 (CPU-baseline
+ * timing): tiles are spread over threads with private accumulators that are summed at the end. */
 void raster_ref_backward(const ctx_t *c, const float *dL_dout /*3*H*W*/, const float *shs, const float *scales,
                          const float *rots, float *dL_dmean2D /*N*3*/, float *dL_dcolors /*N*3*/, float *dL_dopacity /*N*/,
                          float *dL_dmean3D /*N*3*/, float *dL_dcov3D /*N*6*/, float *dL_dsh /*N*M*3*/, float *dL_dscales /*N*3*/,
-                         float *dL_drots /*N*4*/, float *dL_dconic_out /*N*3 (x,y,w) optional*/) {
-    const int N = c->N, W = c->W, H = c->H;
-    real *gm2 = ralloc(2 * (size_t)N), *gcon = ralloc(3 * (size_t)N), *gop = ralloc(N), *gcol = ralloc(3 * (size_t)N);
-    const int ntile = c->gx * c->gy;
-    /* render backward: single thread, tile order then pixel order (deterministic; upstream uses float atomics) */
-    for (int tl = 0; tl < ntile; tl++) {
-        int tx0 = (tl % c->gx) * TILE, ty0 = (tl / c->gx) * TILE;
-        int64_t r0 = c->range[2 * tl], r1 = c->range[2 * tl + 1];
-        if (r1 <= r0) continue;
-        for (int ly = 0; ly < TILE; ly++)
-            for (int lx = 0; lx < TILE; lx++) {
-                int x = tx0 + lx, y = ty0 + ly;
-                if (x >= W || y >= H) continue;
-                size_t pix = (size_t)y * W + x;
-                const real Tfinal = c->finalT[pix];
-                real T = Tfinal;
-                const int last_contributor = c->ncontrib[pix];
-                real dpix[3] = {dL_dout[pix], dL_dout[(size_t)W * H + pix], dL_dout[2 * (size_t)W * H + pix]};
-                real accum[3] = {0, 0, 0}, last_color[3] = {0, 0, 0}, last_alpha = 0;
-                int contributor = (int)(r1 - r0);
-                for (int64_t k = r1 - 1; k >= r0; k--) {
-                    contributor--;
-                    if (contributor >= last_contributor) continue;
-                    int g = c->list[k];
-                    real dx = c->xy[2 * g] - (real)x, dy = c->xy[2 * g + 1] - (real)y;
-                    real cx = c->conic[3 * g], cy = c->conic[3 * g + 1], cz = c->conic[3 * g + 2], op = c->opac[g];
-                    real power = (real)-0.5 * (cx * dx * dx + cz * dy * dy) - cy * dx * dy;
-                    if (power > 0) continue;
-                    real G = (real)(sizeof(real) == 4 ? expf((float)power) : exp((double)power));
-                    real al = op * G; if (al > (real)0.99) al = (real)0.99;
-                    if (al < (real)(1.0 / 255.0)) continue;
-                    T = T / (1 - al);
-                    real dch = al * T, dL_dalpha = 0;
-                    for (int ch = 0; ch < 3; ch++) {
-                        real col = c->rgb[3 * (size_t)g + ch];
-                        accum[ch] = last_alpha * last_color[ch] + (1 - last_alpha) * accum[ch];
-                        last_color[ch] = col;
-                        dL_dalpha += (col - accum[ch]) * dpix[ch];
-                        gcol[3 * (size_t)g + ch] += dch * dpix[ch];
-                    }
-                    dL_dalpha *= T;
-                    last_alpha = al;
-                    real bgdot = c->bg[0] * dpix[0] + c->bg[1] * dpix[1] + c->bg[2] * dpix[2];
-                    dL_dalpha += (-Tfinal / (1 - al)) * bgdot;
-                    real dL_dG = op * dL_dalpha; /* quirk 1: 0.99 clamp not masked */
-                    real gdx = G * dx, gdy = G * dy;
-                    real dG_ddelx = -gdx * cx - gdy * cy, dG_ddely = -gdy * cz - gdx * cy;
-                    gm2[2 * g] += dL_dG * dG_ddelx * ((real)0.5 * W);
-                    gm2[2 * g + 1] += dL_dG * dG_ddely * ((real)0.5 * H);
-                    gcon[3 * g] += (real)-0.5 * gdx * dx * dL_dG;
-                    gcon[3 * g + 1] += (real)-0.5 * gdx * dy * dL_dG;
-                    gcon[3 * g + 2] += (real)-0.5 * gdy * dy * dL_dG;
-                    gop[g] += G * dL_dalpha;
-                }
-            }
+                         float *dL_drots /*N*4*/, float *dL_dconic_out /*N*3 (x,y,w) optional*/, int nthreads) {
+    const int N = c->N;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    bwd_acc_t acc[64];
+    for (int t = 0; t < nthreads; t++) {
+        acc[t].gm2 = ralloc(2 * (size_t)N); acc[t].gcon = ralloc(3 * (size_t)N); acc[t].gop = ralloc(N); acc[t].gcol = ralloc(3 * (size_t)N);
+    }
+    tile_job_t j; memset(&j, 0, sizeof(j)); j.c = (ctx_t *)c; j.backward = 1; j.dL_dout = dL_dout; j.acc = acc;
+    run_job(&j, nthreads);
+    real *gm2 = acc[0].gm2, *gcon = acc[0].gcon, *gop = acc[0].gop, *gcol = acc[0].gcol;
+    for (int t = 1; t < nthreads; t++) {
+        for (size_t i = 0; i < 2 * (size_t)N; i++) gm2[i] += acc[t].gm2[i];
+        for (size_t i = 0; i < 3 * (size_t)N; i++) { gcon[i] += acc[t].gcon[i]; gcol[i] += acc[t].gcol[i]; }
+        for (size_t i = 0; i < (size_t)N; i++) gop[i] += acc[t].gop[i];
+        free(acc[t].gm2); free(acc[t].gcon); free(acc[t].gop); free(acc[t].gcol);
     }
 
     const real *v = c->view, *p = c->proj;

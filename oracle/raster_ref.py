@@ -86,8 +86,13 @@ class RasterRef:
         st["point_list"] = st["point_list"][: m["D"]]
         return st
 
-    def backward(self, dL_dout):
-        """dL_dout: [3,H,W] -> dict of gradients shaped like upstream's return values."""
+    def set_tile_sampling(self, stride=1, offset=0):
+        """CPU-baseline timing only: blend (fwd and bwd) just the tiles with tile % stride == offset."""
+        self.lib.raster_ref_set_tile_sampling(C.c_int(stride), C.c_int(offset))
+
+    def backward(self, dL_dout, nthreads=1):
+        """dL_dout: [3,H,W] -> dict of gradients shaped like upstream's return values.
+        nthreads=1 is the deterministic checker; >1 only for CPU-baseline timing."""
         m = self.meta; N, M = m["N"], m["M"]
         g = _f(dL_dout)
         assert g.shape == (3, m["H"], m["W"])
@@ -96,7 +101,8 @@ class RasterRef:
                  scales=np.zeros((N, 3), np.float32), rotations=np.zeros((N, 4), np.float32), conic=np.zeros((N, 3), np.float32))
         self.lib.raster_ref_backward(C.c_void_p(self.ctx), _p(g), _p(m["shs"]), _p(m["scales"]), _p(m["rotations"]),
                                      _p(o["means2D"]), _p(o["colors"]), _p(o["opacity"]), _p(o["means3D"]), _p(o["cov3D"]),
-                                     _p(o["sh"]) if M else None, _p(o["scales"]), _p(o["rotations"]), _p(o["conic"]))
+                                     _p(o["sh"]) if M else None, _p(o["scales"]), _p(o["rotations"]), _p(o["conic"]),
+                                     C.c_int(nthreads))
         return o
 
     def mark_visible(self, means3D, viewmatrix, projmatrix):

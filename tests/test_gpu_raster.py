@@ -1,0 +1,266 @@
+"""Tile rasterizer forward + backward through the C ABI against the CPU oracle (oracle/raster_ref.c).
+
+Rules (see helpers.py): radii / num_rendered / per-tile instance order / n_contrib are integer work -> bit exact;
+image 1e-5 abs; gradients 1e-5 of each tensor's largest magnitude.  Pixels where the fp32 and fp64 oracles disagree
+by more than the tolerance (a hard gate flipped by rounding) are excluded from the image comparison and counted.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import IMG_ATOL, cam_args, fragile_pixels, grad_close, posed_scene, settings_from, zoom_camera
+from manus_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def gpu_forward(cam, bg, ps, debug=True, mode="precomp", extra=None, capacity=None):
+    from manus_b200.rasterizer import rasterize_forward
+
+    tg = lambda a: None if a is None else torch.tensor(np.ascontiguousarray(a), device=DEV)
+    st_args = dict(means3D=tg(ps["means3D"]), opacities=tg(ps["opacity"]).reshape(-1))
+    if mode == "precomp":
+        st_args.update(colors_precomp=tg(ps["colors"]), cov3D_precomp=tg(ps["cov3D"]))
+    else:
+        st_args.update(shs=tg(extra["shs"]), scales=tg(extra["scales"]), rotations=tg(extra["rotations"]))
+    settings = settings_from(cam, bg, DEV, debug=debug)
+    if extra and "scale_modifier" in extra:
+        settings = settings._replace(scale_modifier=extra["scale_modifier"])
+    color, radii, st = rasterize_forward(settings, capacity=capacity, **st_args)
+    torch.cuda.synchronize()
+    return color, radii, st
+
+
+def check_against_oracle(cam, bg, ps, raster_ref, raster_ref64, G=None, mode="precomp", extra=None, grad_rtol=1e-5):
+    from manus_b200.rasterizer import debug_views, rasterize_backward
+
+    kw = dict(colors_precomp=ps["colors"], cov3D_precomp=ps["cov3D"]) if mode == "precomp" else \
+        dict(shs=extra["shs"], sh_degree=3, scales=extra["scales"], rotations=extra["rotations"],
+             scale_modifier=extra.get("scale_modifier", 1.0))
+    ca = cam_args(cam, bg)
+    img32, radii32, D32 = raster_ref.forward(ps["means3D"], ps["opacity"], **kw, **ca)
+    img64, _, _ = raster_ref64.forward(ps["means3D"], ps["opacity"], **kw, **ca)
+    color, radii, st = gpu_forward(cam, bg, ps, mode=mode, extra=extra)
+    # ---- integer work: bit exact
+    np.testing.assert_array_equal(radii.cpu().numpy(), radii32)
+    assert st.resolve() == D32
+    ref_state = raster_ref.state()
+    dv = debug_views(st)
+    np.testing.assert_array_equal(dv["point_list"].cpu().numpy(), ref_state["point_list"])
+    np.testing.assert_array_equal(dv["ranges"].cpu().numpy().astype(np.int64), ref_state["ranges"])
+    # ---- image
+    got = color.cpu().numpy()
+    frag = fragile_pixels(img64, img32)
+    err = np.abs(got - img32).max(0)
+    assert frag.mean() <= 1e-3, f"too many gate-fragile pixels: {frag.sum()}"
+    assert err[~frag].max() <= IMG_ATOL, f"image max err {err[~frag].max()} ({(err > IMG_ATOL).sum()} px over, {frag.sum()} fragile)"
+    assert err.max() <= 2e-2
+    ok = ~frag
+    nc = dv["n_contrib"].cpu().numpy()
+    assert (nc[ok] == ref_state["n_contrib"][ok]).mean() > 0.9999
+    np.testing.assert_allclose(dv["final_T"].cpu().numpy()[ok], ref_state["final_T"][ok], atol=IMG_ATOL)
+    if G is None:
+        return st
+    # ---- gradients
+    g32 = raster_ref.backward(G)
+    grads = rasterize_backward(st, torch.tensor(G, device=DEV))
+    torch.cuda.synchronize()
+    names = ["means2D", "colors", "opacity", "means3D", "cov3D", "sh", "scales", "rotations"]
+    report = {}
+    for nm, g in zip(names, grads):
+        if g is None:
+            continue
+        ok_, e, s = grad_close(g.cpu().numpy().reshape(g32[nm].shape), g32[nm], grad_rtol)
+        report[nm] = (e, s)
+        assert ok_, f"grad {nm}: err {e} vs scale {s}"
+    return st
+
+
+def small_scene(seed, N=3000, W=160, H=120, zoom=1.6, scale_boost=0.3, opacity_boost=1.0):
+    sc = synth.make_hand(N, seed=seed)
+    cam = zoom_camera(seed * 7 % 51, W, H, zoom)
+    return sc, cam, posed_scene(sc, 3 * seed + 1, cam, scale_boost, opacity_boost)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_hand_scene_forward_backward(built_lib, raster_ref, raster_ref64, seed):
+    sc, cam, ps = small_scene(seed)
+    G = np.random.default_rng(7).uniform(0, 1, (3, cam.height, cam.width)).astype(np.float32)
+    check_against_oracle(cam, (1.0, 1.0, 1.0) if seed else (0.2, 0.4, 0.6), ps, raster_ref, raster_ref64, G)
+
+
+def test_ragged_image_size_and_deep_tiles(built_lib, raster_ref, raster_ref64):
+    """W, H not multiples of 16; few tiles holding thousands of instances each (several 256-record batches, early exit)."""
+    sc, cam, ps = small_scene(3, N=20000, W=75, H=53, zoom=0.9, scale_boost=0.0, opacity_boost=3.0)
+    G = np.random.default_rng(1).uniform(-1, 1, (3, cam.height, cam.width)).astype(np.float32)
+    st = check_against_oracle(cam, (0.0, 0.0, 0.0), ps, raster_ref, raster_ref64, G)
+    from manus_b200.rasterizer import debug_views
+    r = debug_views(st)["ranges"].cpu().numpy()
+    assert (r[:, 1] - r[:, 0]).max() > 600
+
+
+def test_composite_scene(built_lib, raster_ref, raster_ref64):
+    sc = synth.make_composite(8000, seed=5)
+    cam = zoom_camera(20, 240, 136, 1.2)
+    ps = posed_scene(sc, 9, cam, 0.2, 1.5)
+    G = np.random.default_rng(2).uniform(0, 1, (3, cam.height, cam.width)).astype(np.float32)
+    check_against_oracle(cam, (1.0, 1.0, 1.0), ps, raster_ref, raster_ref64, G)
+
+
+def test_sh_and_scale_rotation_modes(built_lib, raster_ref, raster_ref64):
+    sc, cam, ps = small_scene(4, N=2500)
+    rng = np.random.default_rng(0)
+    extra = dict(shs=np.concatenate([sc.f_dc, sc.f_rest * 3.0], 1).astype(np.float32),
+                 scales=np.exp(sc.log_scale + 0.3).astype(np.float32),
+                 rotations=(sc.quat / np.linalg.norm(sc.quat, axis=1, keepdims=True) * rng.uniform(0.9, 1.1, (sc.n, 1))).astype(np.float32),
+                 scale_modifier=1.1)
+    G = rng.uniform(0, 1, (3, cam.height, cam.width)).astype(np.float32)
+    check_against_oracle(cam, (0.1, 0.1, 0.1), ps, raster_ref, raster_ref64, G, mode="sh", extra=extra)
+
+
+def test_culled_and_offscreen_gaussians(built_lib, raster_ref, raster_ref64):
+    sc, cam, ps = small_scene(6, N=1500)
+    m = ps["means3D"].copy()
+    c = cam.camera_center
+    m[:200] = c + (m[:200] - c) * 0.05            # pulled to within 0.2 of the camera plane -> near cull
+    m[200:400] = c - (m[200:400] - c)             # behind the camera
+    m[400:500] += np.array([3.0, 0, 0], np.float32)   # far off-screen
+    ps["means3D"] = m.astype(np.float32)
+    G = np.ones((3, cam.height, cam.width), np.float32)
+    check_against_oracle(cam, (1.0, 1.0, 1.0), ps, raster_ref, raster_ref64, G)
+
+
+def test_all_culled_and_empty_inputs(built_lib):
+    from manus_b200.rasterizer import GaussianRasterizer
+
+    cam = zoom_camera(0, 64, 48)
+    bg = (0.25, 0.5, 0.75)
+    rs = settings_from(cam, bg, DEV)
+    r = GaussianRasterizer(rs)
+    z = lambda *s: torch.zeros(*s, device=DEV)
+    # N == 0
+    img, radii = r(z(0, 3), z(0, 3), z(0, 1), colors_precomp=z(0, 3), cov3D_precomp=z(0, 6))
+    assert img.shape == (3, 48, 64) and radii.numel() == 0
+    np.testing.assert_allclose(img.cpu().numpy(), np.broadcast_to(np.array(bg, np.float32)[:, None, None], (3, 48, 64)))
+    # everything behind the camera
+    m = torch.tensor(cam.camera_center, device=DEV)[None].repeat(50, 1)
+    m.requires_grad_(True)
+    s2d = z(50, 3).requires_grad_(True)
+    img, radii = r(m, s2d, torch.full((50, 1), 0.5, device=DEV), colors_precomp=z(50, 3) + 0.5, cov3D_precomp=z(50, 6) + 1e-4)
+    assert int(radii.abs().sum()) == 0
+    np.testing.assert_allclose(img.detach().cpu().numpy(), np.broadcast_to(np.array(bg, np.float32)[:, None, None], (3, 48, 64)))
+    img.sum().backward()
+    assert float(m.grad.abs().sum()) == 0 and float(s2d.grad.abs().sum()) == 0
+
+
+def test_module_interface_like_manus_calls_it(built_lib, raster_ref):
+    """The exact call pattern of render_gaussians (gaussian_utils.py:363-418): non-leaf means2D with retain_grad, [1,4,4]/[1,3]
+    camera tensors, [N,1] opacities, sliced (non-contiguous) means, permuted HWC loss."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "shims"))
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+
+    sc, cam, ps = small_scene(8, N=2000)
+    tg = lambda a: torch.tensor(a, device=DEV)
+    means_h = torch.cat([tg(ps["means3D"]), torch.ones(sc.n, 1, device=DEV)], 1).requires_grad_(True)
+    means = means_h[..., :3]                                     # non-contiguous view, like hand_dynamic.py:107
+    screenspace = torch.zeros_like(means, requires_grad=True) + 0
+    screenspace.retain_grad()
+    cov, col, op = tg(ps["cov3D"]).requires_grad_(True), tg(ps["colors"]).requires_grad_(True), tg(ps["opacity"]).requires_grad_(True)
+    rs = GaussianRasterizationSettings(image_height=cam.height, image_width=cam.width, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                                       bg=tg(np.ones(3, np.float32)), scale_modifier=1, viewmatrix=tg(cam.world_view_transform)[None],
+                                       projmatrix=tg(cam.full_proj_transform)[None], sh_degree=3, campos=tg(cam.camera_center)[None],
+                                       prefiltered=False, debug=False)
+    img, radii = GaussianRasterizer(raster_settings=rs)(means3D=means, means2D=screenspace, shs=None, colors_precomp=col, opacities=op,
+                                                        scales=None, rotations=None, cov3D_precomp=cov)
+    assert img.shape == (3, cam.height, cam.width) and radii.dtype == torch.int32 and radii.shape == (sc.n,)
+    hwc = torch.permute(img, (1, 2, 0))
+    Ghwc = torch.rand(cam.height, cam.width, 3, generator=torch.Generator().manual_seed(5)).to(DEV)
+    (hwc * Ghwc).sum().backward()
+    ref_img, ref_radii, _ = raster_ref.forward(ps["means3D"], ps["opacity"], colors_precomp=ps["colors"], cov3D_precomp=ps["cov3D"],
+                                               **cam_args(cam))
+    g = raster_ref.backward(Ghwc.permute(2, 0, 1).contiguous().cpu().numpy())
+    np.testing.assert_array_equal(radii.cpu().numpy(), ref_radii)
+    for got, nm in ((screenspace.grad, "means2D"), (means_h.grad[:, :3], "means3D"), (cov.grad, "cov3D"), (col.grad, "colors"),
+                    (op.grad, "opacity")):
+        ok_, e, s = grad_close(got.cpu().numpy(), g[nm])
+        assert ok_, (nm, e, s)
+    assert float(screenspace.grad[:, 2].abs().max()) == 0
+    assert float(means_h.grad[:, 3].abs().max()) == 0
+    vis = GaussianRasterizer(raster_settings=rs).markVisible(means)
+    np.testing.assert_array_equal(vis.cpu().numpy(), raster_ref.mark_visible(ps["means3D"], cam.world_view_transform, cam.full_proj_transform))
+
+
+def test_capacity_overflow_is_detected(built_lib):
+    from manus_b200 import _lib
+    from manus_b200.rasterizer import raster_query
+
+    sc, cam, ps = small_scene(9, N=2000)
+    color, radii, st = gpu_forward(cam, (1, 1, 1), ps, capacity=100)
+    nr, nv, ov = raster_query(st)
+    assert nr > 100 and ov == 1 and nv == int((radii > 0).sum())
+    with pytest.raises(_lib.ManusB200Error, match="capacity overflow"):
+        st.resolve()
+    color2, _, st2 = gpu_forward(cam, (1, 1, 1), ps, capacity=nr + 7)     # any capacity >= num_rendered gives the exact image
+    color3, _, st3 = gpu_forward(cam, (1, 1, 1), ps)
+    assert st2.resolve() == nr and torch.equal(color2, color3)
+
+
+def test_forward_is_deterministic_and_backward_noise_is_small(built_lib):
+    sc, cam, ps = small_scene(10, N=6000, W=256, H=144)
+    from manus_b200.rasterizer import rasterize_backward
+
+    G = torch.rand(3, cam.height, cam.width, device=DEV)
+    c1, r1, s1 = gpu_forward(cam, (1, 1, 1), ps, debug=False)
+    c2, r2, s2 = gpu_forward(cam, (1, 1, 1), ps, debug=False)
+    assert torch.equal(c1, c2) and torch.equal(r1, r2)
+    g1, g2 = rasterize_backward(s1, G), rasterize_backward(s2, G)
+    for a, b in zip(g1, g2):
+        if a is not None:
+            scale = max(1.0, float(a.abs().max()))
+            assert float((a - b).abs().max()) <= 2e-6 * scale      # float atomics: order noise only
+
+
+@pytest.mark.parametrize("n,W,H", [(300_000, 1920, 1080)])
+def test_full_size_properties(built_lib, n, W, H):
+    """BASELINE-size checks that need no oracle: blending is linear in colour, the colour gradient is exactly the blend weight
+    (so <grad, delta> equals the image change), radii > 0 <=> tiles touched, and num_rendered equals the sum of tile-rect areas."""
+    from manus_b200.rasterizer import debug_views, rasterize_backward
+
+    sc = synth.make_composite(n, seed=0)
+    cam = synth.camera(0, W, H)
+    ps = posed_scene(sc, 5, cam)
+    color, radii, st = gpu_forward(cam, (1, 1, 1), ps, debug=False)
+    dv = debug_views(st)
+    D = st.resolve()
+    assert D > n and int((radii > 0).sum()) > 0.9 * n
+    ranges = dv["ranges"].cpu().numpy().astype(np.int64)
+    lens = ranges[:, 1] - ranges[:, 0]
+    assert lens.min() >= 0 and lens.sum() == D
+    # per-tile depth order: instance depths are non-decreasing inside every tile range
+    # (depth = view-space z of the instance's Gaussian)
+    m = torch.tensor(ps["means3D"], device=DEV)
+    v = torch.tensor(cam.world_view_transform, device=DEV)
+    depth = m @ v[:3, 2] + v[3, 2]
+    pl = dv["point_list"].long()
+    dd = depth[pl]
+    tile_of = torch.repeat_interleave(torch.arange(lens.size, device=DEV), torch.tensor(lens, device=DEV))
+    same = tile_of[1:] == tile_of[:-1]
+    assert bool(((dd[1:] >= dd[:-1]) | ~same).all())
+    # linearity in colour
+    rng = np.random.default_rng(0)
+    delta = rng.uniform(-0.2, 0.2, ps["colors"].shape).astype(np.float32)
+    ps2 = dict(ps, colors=ps["colors"] + delta)
+    color2, _, _ = gpu_forward(cam, (1, 1, 1), ps2, debug=False)
+    G = torch.rand(3, H, W, device=DEV)
+    grads = rasterize_backward(st, G)
+    lhs = float((grads[1].double() * torch.tensor(delta, device=DEV).double()).sum())
+    rhs = float(((color2.double() - color.double()) * G.double()).sum())
+    assert abs(lhs - rhs) <= 2e-4 * max(1.0, abs(rhs)), (lhs, rhs)
+    # HWC-strided gradient input gives the same result as the contiguous one
+    Ghwc = G.permute(1, 2, 0).contiguous()
+    grads2 = rasterize_backward(st, Ghwc.permute(2, 0, 1))
+    for a, b in zip(grads, grads2):
+        if a is not None:
+            assert float((a - b).abs().max()) <= 2e-6 * max(1.0, float(a.abs().max()))
