@@ -261,7 +261,7 @@ def main():
     set_capacity_mode("exact")
     D_all, V_all = view_counts(r, staged, views)
     set_capacity_mode("reserve", margin=1.1)
-    _rz._Plan.high_water[(dev.index, scene.n, H, W)] = max(D_all)
+    _rz._Plan.high_water[(dev.index, scene.n, H, W)] = max(D_all.values())
 
     def timed(fn, steps, sampler=None):
         for it in range(WU):

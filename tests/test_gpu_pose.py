@@ -14,13 +14,13 @@ CASES = ["hand_voxel", "hand_points_iso", "object", "deg0", "deg1", "deg2"]
 # O(1e-5), gradients O(1..1e3)); fp32 round-off of the fused kernel vs the PyTorch op order is ~1e-6 in this norm.
 
 
-def close(got, ref, name, rtol=1e-5):
+def close(got, ref, name, rtol=1e-5, atol=1e-12):
     got, ref = got.detach().cpu().numpy(), np.asarray(ref)
     if ref.size == 0:
         return
     scale = float(np.abs(ref).max())
     err = float(np.abs(got.reshape(ref.shape) - ref).max())
-    assert err <= rtol * scale + 1e-12, (name, err, scale)
+    assert err <= rtol * scale + atol, (name, err, scale)
 
 
 def gpu_run(g, with_skin_grad=True):
@@ -58,7 +58,9 @@ def test_backward_matches_reference_goldens(built_lib, name):
     grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
     for k, gr in zip(names, grads):
         if g["g_" + k].size:
-            close(gr, g["g_" + k], "g_" + k)
+            # isotropic scaling: Sigma = s^2 I does not depend on the rotation, so the reference's g_quat is pure fp32
+            # cancellation noise (~1e-8); compare it on the absolute 1e-7 floor instead of relative to that noise.
+            close(gr, g["g_" + k], "g_" + k, atol=1e-7 if (k == "quat" and bool(g["isotropic"])) else 1e-12)
 
 
 def test_composite_scene_against_oracle(built_lib):

@@ -242,7 +242,8 @@ def test_full_size_properties(built_lib, n, W, H):
     # (depth = view-space z of the instance's Gaussian)
     m = torch.tensor(ps["means3D"], device=DEV)
     v = torch.tensor(cam.world_view_transform, device=DEV)
-    depth = m @ v[:3, 2] + v[3, 2]
+    # same operation order as the kernel (individually rounded, no FMA), so 1-ulp neighbours order identically
+    depth = ((m[:, 0] * v[0, 2] + m[:, 1] * v[1, 2]) + m[:, 2] * v[2, 2]) + v[3, 2]
     pl = dv["point_list"].long()
     dd = depth[pl]
     tile_of = torch.repeat_interleave(torch.arange(lens.size, device=DEV), torch.tensor(lens, device=DEV))
