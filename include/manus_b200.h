@@ -112,6 +112,13 @@ int mb_raster_backward(const mb_raster_inputs *in, const int32_t *radii, const v
                        float *dL_dsh /*[P,M,3]*/, float *dL_dscales /*[P,3]*/, float *dL_drotations /*[P,4]*/,
                        mb_stream_t stream);
 
+/* Diagnostics for tests: byte offsets of named arrays inside the opaque buffers of a forward with these sizes.
+ * out[0..3]: image buffer -> final_T f32[H*W], n_contrib u32[H*W], tile ranges u32[tiles][2], deepest last contributor u32[tiles];
+ * out[4..5]: binning buffer -> gaussian id per sorted instance u32[num_rendered], tile id per sorted instance u32[num_rendered];
+ * out[6..7]: geom buffer -> 48-B per-Gaussian blend records, counters u32[16]. */
+int mb_raster_state_layout(int32_t num_points, int64_t capacity, int32_t image_width, int32_t image_height, int64_t *out,
+                           int32_t n_out);
+
 /* markVisible: out[i] = 1 iff the point is in front of the near plane (view-space z > 0.2). */
 int mb_mark_visible(const float *means3D, int32_t num_points, const float *viewmatrix, const float *projmatrix,
                     uint8_t *out, mb_stream_t stream);

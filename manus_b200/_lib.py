@@ -55,6 +55,7 @@ SIGNATURES = {
     "mb_raster_backward_scratch_bytes": (C.c_size_t, [C.c_int32]),
     "mb_raster_backward": (C.c_int, [C.POINTER(RasterInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                      C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_size_t] + [C.c_void_p] * 8 + [C.c_void_p]),
+    "mb_raster_state_layout": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, i64p, C.c_int32]),
     "mb_mark_visible": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mb_pose_forward": (C.c_int, [C.POINTER(PoseInputs)] + [C.c_void_p] * 5 + [C.c_void_p]),
     "mb_pose_backward": (C.c_int, [C.POINTER(PoseInputs)] + [C.c_void_p] * 4 + [C.c_void_p] * 7 + [C.c_void_p]),

@@ -1,96 +1,208 @@
 // Per-tile alpha blending, forward and backward (A.4), plus the per-Gaussian backward of the
-// projection.  One CTA of 256 threads owns one 16x16 tile; its depth-sorted instance list is a contiguous run of 48-B
-// records that is streamed through shared memory by the TMA engine (cp.async.bulk + mbarrier, double buffered) while
-// the threads blend the previous batch.  A warp owns an 8x4 pixel block.  Arithmetic order per pixel is the reference
-// order (sequential front-to-back product), so results do not depend on the schedule.
+// projection.
+//
+// Work item = one 16x16 tile (kWarps = 8) or one 16x8 half tile (kWarps = 4); a warp owns an 8x4 pixel block.  The tile's
+// depth-sorted id list is staged into shared memory by the TMA engine (cp.async.bulk + mbarrier, 3-slot ring, two batches
+// ahead); every thread then gathers the 48-B record of one listed Gaussian with three 128-bit cp.async loads (records
+// are written once per Gaussian by the projection kernel and stay L2 resident), double buffered against the blending of
+// the previous batch.  Only the part of a list that is actually consumed is ever gathered: the forward stops a tile
+// when all its pixels are saturated, the backward starts at the tile's deepest last contributor.
+//
+// Per pixel the arithmetic is the reference's sequential front-to-back product, so results do not depend on the
+// schedule.  The inner loops are warp-convergent: a Gaussian whose power is above 0 or below its cut-off on all 32 pixels
+// of the warp costs ~14 instructions and no exponential (warp vote); the backward sums each of its nine per-Gaussian
+// partials over the warp with a 12-shuffle reduce-scatter and issues them as one vector of RED.ADD.F32 from nine lanes.
+#include <stdlib.h>
+
 #include "raster_state.cuh"
 
 namespace mb {
 
-constexpr int kBatch = 256;                 // records per pipeline stage (12 KB)
 constexpr int kAccStride = 12;              // floats per Gaussian in the gradient accumulator
 // accumulator slots: 0,1 mean2D.xy | 2,3,4 conic (x,y,w) | 5 opacity | 6,7,8 colour
 
 int build_instances(const mb_raster_inputs *in, const RasterDims &d, const GeomState &g, const BinningState &b,
                     const ImageState &im, int64_t capacity, cudaStream_t s);
 
-__device__ __forceinline__ void pixel_of_thread(int tile, int gx, int tid, int &px, int &py) {
-    const int warp = tid >> 5, lane = tid & 31;
-    px = (tile % gx) * kTile + (warp & 1) * 8 + (lane & 7);
-    py = (tile / gx) * kTile + (warp >> 1) * 4 + (lane >> 3);
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
+template <int kWarps>
+struct StageSmem {
+    static constexpr int B = kWarps * 32;       // list entries per batch = threads per CTA
+    Record rec[2][B];                           // gathered records, double buffered
+    uint32_t ids[3][B + 4];                     // TMA-staged slices of the id list (16-B aligned source => up to 3 ids of slack)
+    uint64_t bar[3];
+    uint32_t red;                               // per-CTA scratch (max last contributor)
+};
+
+// Streams a tile's id list through shared memory: sequence step i handles batch i (forward) or nb-1-i (backward).
+template <int kWarps>
+struct ListStager {
+    static constexpr int B = kWarps * 32;
+    StageSmem<kWarps> &sm;
+    const uint32_t *list;      // sorted id list (whole frame)
+    const Record *rec;         // per-Gaussian records
+    uint32_t first;            // index of the tile's first instance in `list`
+    int len, nb;
+    bool reverse;
+
+    __device__ __forceinline__ int batch_of(int i) const { return reverse ? nb - 1 - i : i; }
+
+    __device__ __forceinline__ void issue_ids(int i) {   // one elected thread
+        const int b = batch_of(i), cnt = min(B, len - b * B);
+        const uint32_t start = first + (uint32_t)(b * B), o = start & 3u;
+        const uint32_t bytes = ((o + (uint32_t)cnt) * 4u + 15u) & ~15u;
+        const int slot = i % 3;
+        mbar_expect_tx(&sm.bar[slot], bytes);
+        bulk_g2s(&sm.ids[slot][0], list + (start - o), bytes, &sm.bar[slot]);
+    }
+    __device__ __forceinline__ void gather(int i) {      // all threads; one commit group per call
+        const int b = batch_of(i), cnt = min(B, len - b * B);
+        const uint32_t o = (first + (uint32_t)(b * B)) & 3u;
+        const int slot = i % 3;
+        mbar_wait(&sm.bar[slot], (uint32_t)((i / 3) & 1));
+        if ((int)threadIdx.x < cnt) {
+            const char *src = reinterpret_cast<const char *>(rec + sm.ids[slot][o + threadIdx.x]);
+            char *dst = reinterpret_cast<char *>(&sm.rec[i & 1][threadIdx.x]);
+            cp_async16(dst, src);
+            cp_async16(dst + 16, src + 16);
+            cp_async16(dst + 32, src + 32);
+        }
+        cp_async_commit();
+    }
+    __device__ __forceinline__ void prologue() {
+        if (threadIdx.x == 0) {
+            mbar_init(&sm.bar[0], 1);
+            mbar_init(&sm.bar[1], 1);
+            mbar_init(&sm.bar[2], 1);
+            mbar_fence_init();
+            sm.red = 0;
+        }
+        __syncthreads();
+        if (nb > 0) {
+            if (threadIdx.x == 0) {
+                issue_ids(0);
+                if (nb > 1) issue_ids(1);
+            }
+            gather(0);
+        }
+    }
+    // top of sequence step i: keep the pipeline full, then make batch i visible to every thread
+    __device__ __forceinline__ void advance(int i) {
+        if (threadIdx.x == 0 && i + 2 < nb) issue_ids(i + 2);
+        if (i + 1 < nb) gather(i + 1);
+        else cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+    }
+    // leaving after step i with copies possibly in flight: nothing may land in shared memory after the CTA is gone
+    __device__ __forceinline__ void drain(int i) {
+        cp_async_wait<0>();
+        if (threadIdx.x == 0 && i + 2 < nb) mbar_wait(&sm.bar[(i + 2) % 3], (uint32_t)(((i + 2) / 3) & 1));
+    }
+    __device__ __forceinline__ int count(int i) const { return min(B, len - batch_of(i) * B); }
+    __device__ __forceinline__ const float4 *records(int i) const { return reinterpret_cast<const float4 *>(&sm.rec[i & 1][0]); }
+};
+
+// pixel of a thread: the work item covers 8/kWarps... see kernel comments; vw = virtual warp index inside the 16x16 tile
+__device__ __forceinline__ void pixel_of_thread(int tile, int gx, int vw, int lane, int &px, int &py) {
+    px = (tile % gx) * kTile + (vw & 1) * 8 + (lane & 7);
+    py = (tile / gx) * kTile + (vw >> 1) * 4 + (lane >> 3);
 }
 
-__global__ void __launch_bounds__(256) blend_forward_kernel(const Record *__restrict__ records,
-                                                            const uint2 *__restrict__ ranges, int W, int H, int gx,
-                                                            const float *__restrict__ bg, float *__restrict__ out_color,
-                                                            float *__restrict__ final_T, uint32_t *__restrict__ n_contrib) {
-    __shared__ __align__(128) Record stage[2][kBatch];
-    __shared__ __align__(8) uint64_t bar[2];
-    const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 24 / kWarps) blend_forward_kernel(
+    const Record *__restrict__ recs, const uint32_t *__restrict__ list, const uint2 *__restrict__ ranges,
+    const uint32_t *__restrict__ order, int W, int H, int gx, const float *__restrict__ bg, float *__restrict__ out_color,
+    float *__restrict__ final_T, uint32_t *__restrict__ n_contrib, uint32_t *__restrict__ tile_maxlast) {
+    constexpr int kSplit = 8 / kWarps;
+    __shared__ __align__(128) StageSmem<kWarps> sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int item = blockIdx.x / kSplit, sub = blockIdx.x % kSplit;
+    const int tile = order ? (int)order[item] : item;
     const uint2 range = ranges[tile];
-    const int len = (int)(range.y - range.x);
-    const int nb = (len + kBatch - 1) / kBatch;
     int px, py;
-    pixel_of_thread(tile, gx, tid, px, py);
+    pixel_of_thread(tile, gx, sub * kWarps + warp, lane, px, py);
     const bool inside = px < W && py < H;
     const float fx = (float)px, fy = (float)py;
 
-    if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    const Record *src = records + range.x;
-    if (tid == 0 && nb > 0) {
-        const uint32_t bytes = (uint32_t)min(kBatch, len) * (uint32_t)sizeof(Record);
-        mbar_expect_tx(&bar[0], bytes);
-        bulk_g2s(&stage[0][0], src, bytes, &bar[0]);
-    }
+    ListStager<kWarps> st{sm, list, recs, range.x, (int)(range.y - range.x), 0, false};
+    st.nb = (st.len + st.B - 1) / st.B;
+    st.prologue();
 
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    uint32_t contributor = 0, last = 0;
+    uint32_t last = 0;
     bool done = !inside;
-    for (int b = 0; b < nb; ++b) {
-        const int cur = b & 1;
-        if (tid == 0 && b + 1 < nb) {   // prefetch the next batch into the buffer released at the end of iteration b-1
-            const uint32_t bytes = (uint32_t)min(kBatch, len - (b + 1) * kBatch) * (uint32_t)sizeof(Record);
-            mbar_expect_tx(&bar[cur ^ 1], bytes);
-            bulk_g2s(&stage[cur ^ 1][0], src + (size_t)(b + 1) * kBatch, bytes, &bar[cur ^ 1]);
-        }
-        mbar_wait(&bar[cur], (uint32_t)((b >> 1) & 1));
-        const int cnt = min(kBatch, len - b * kBatch);
-        if (!done) {
-            const float4 *st = reinterpret_cast<const float4 *>(&stage[cur][0]);
-            for (int j = 0; j < cnt; ++j) {
-                const float4 ra = st[3 * j], rb = st[3 * j + 1];
-                ++contributor;
-                const float dx = ra.x - fx, dy = ra.y - fy;
-                const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
-                if (power > 0.0f) continue;
-                const float alpha = fminf(kAlphaMax, rb.y * expf(power));
-                if (alpha < kAlphaMin) continue;
-                const float test_T = T * (1.0f - alpha);
-                if (test_T < kTMin) {
-                    done = true;
-                    break;
-                }
+    bool wdone = __all_sync(0xffffffffu, done);
+    for (int i = 0; i < st.nb; ++i) {
+        st.advance(i);
+        const int cnt = st.count(i);
+        const float4 *r = st.records(i);
+        const uint32_t base = (uint32_t)(i * st.B);
+        // one list entry: exact reference arithmetic, executed only when some pixel of the warp may be touched
+        auto blend = [&](const float4 &ra, const float4 &rb, float blue, float power, bool cand, uint32_t pos1) {
+            const float alpha = fminf(kAlphaMax, rb.y * expf(power));
+            const bool ok = cand && !done && alpha >= kAlphaMin;
+            const float test_T = T * (1.0f - alpha);
+            const bool stop = ok && test_T < kTMin;
+            if (ok && !stop) {
                 const float w = alpha * T;
                 C0 += rb.z * w;
                 C1 += rb.w * w;
-                C2 += st[3 * j + 2].x * w;
+                C2 += blue * w;
                 T = test_T;
-                last = contributor;
+                last = pos1;
             }
+            done = done || stop;
+            if (__any_sync(0xffffffffu, stop)) wdone = __all_sync(0xffffffffu, done);
+        };
+        int j = 0;
+        if (!wdone) {
+            for (; j + 4 <= cnt; j += 4) {
+                float4 ra[4], rb[4];
+                float2 rc[4];
+                float power[4];
+                bool cand[4], any = false;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    ra[k] = r[3 * (j + k)];
+                    rb[k] = r[3 * (j + k) + 1];
+                    rc[k] = *reinterpret_cast<const float2 *>(&r[3 * (j + k) + 2]);
+                    const float dx = ra[k].x - fx, dy = ra[k].y - fy;
+                    power[k] = -0.5f * (ra[k].z * dx * dx + rb[k].x * dy * dy) - ra[k].w * dx * dy;
+                    cand[k] = !done && power[k] <= 0.0f && !(power[k] < rc[k].y);
+                    any = any || cand[k];
+                }
+                if (!__any_sync(0xffffffffu, any)) continue;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (__any_sync(0xffffffffu, cand[k])) blend(ra[k], rb[k], rc[k].x, power[k], cand[k], base + (uint32_t)(j + k) + 1u);
+                if (wdone) break;
+            }
+            if (!wdone)
+                for (; j < cnt; ++j) {
+                    const float4 ra = r[3 * j], rb = r[3 * j + 1];
+                    const float2 rc = *reinterpret_cast<const float2 *>(&r[3 * j + 2]);
+                    const float dx = ra.x - fx, dy = ra.y - fy;
+                    const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
+                    const bool cand = !done && power <= 0.0f && !(power < rc.y);
+                    if (__any_sync(0xffffffffu, cand)) blend(ra, rb, rc.x, power, cand, base + (uint32_t)j + 1u);
+                }
         }
-        // all reads of stage[cur] are complete after this barrier; it also counts finished pixels (early exit)
+        // all reads of this batch are complete after the barrier; it also counts finished pixels (early exit)
         const int ndone = __syncthreads_count(done);
-        if (ndone == 256) {
-            if (tid == 0 && b + 1 < nb) mbar_wait(&bar[cur ^ 1], (uint32_t)(((b + 1) >> 1) & 1));   // drain in-flight copy
+        if (ndone == st.B) {
+            st.drain(i);
             break;
         }
     }
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, last);
+    if (lane == 0 && wmax) atomicMax(&sm.red, wmax);
     if (inside) {
         const size_t pix = (size_t)py * W + px, plane = (size_t)W * H;
         final_T[pix] = T;
@@ -99,23 +211,65 @@ __global__ void __launch_bounds__(256) blend_forward_kernel(const Record *__rest
         out_color[plane + pix] = C1 + T * bg[1];
         out_color[2 * plane + pix] = C2 + T * bg[2];
     }
+    __syncthreads();
+    if (tid == 0 && sm.red) atomicMax(&tile_maxlast[tile], sm.red);
 }
 
-__global__ void __launch_bounds__(256) blend_backward_kernel(const Record *__restrict__ records,
-                                                             const uint2 *__restrict__ ranges, int W, int H, int gx,
-                                                             const float *__restrict__ bg, const float *__restrict__ final_T,
-                                                             const uint32_t *__restrict__ n_contrib,
-                                                             const float *__restrict__ dL_dout, int64_t sc, int64_t sy,
-                                                             int64_t sx, float *__restrict__ acc) {
-    __shared__ __align__(128) Record stage[2][kBatch];
-    __shared__ __align__(8) uint64_t bar[2];
-    __shared__ uint32_t warp_max[8];
+// lane -> which of the 9 reduced values it owns after the reduce-scatter (or -1)
+__device__ __forceinline__ int reduce_slot(int lane) {
+    const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
+    const int k2 = 2 * b2 + b1;        // index into the 3-array
+    const int k3 = 3 * b3 + k2;        // index into the 5-array
+    const int k4 = 5 * b4 + k3;        // index into the 9-array
+    const bool valid = (lane & 1) == 0 && k2 < 3 && k3 < 5 && k4 < 9 && !(b2 && b1) && !(b3 && k2 >= 2) && !(b4 && k3 >= 4);
+    return valid ? k4 : -1;
+}
+
+// Sum each of v[0..8] over the 32 lanes: 5+3+2+1+1 = 12 shuffles.  Afterwards the lane with reduce_slot(lane) == k
+// holds the total of v[k] in the return value.
+__device__ __forceinline__ float reduce_scatter9(const float (&v)[9], int lane) {
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4, h1 = lane & 2;
+    float a[5], b[3], c[2];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {   // keep v[0..4] (low half) or v[5..8] (high half)
+        const float lo = v[k], hi = k < 4 ? v[5 + k] : 0.f;
+        const float recv = __shfl_xor_sync(0xffffffffu, h4 ? lo : hi, 16);
+        a[k] = (h4 ? hi : lo) + recv;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {   // keep a[0..2] or a[3..4]
+        const float lo = a[k], hi = k < 2 ? a[3 + k] : 0.f;
+        const float recv = __shfl_xor_sync(0xffffffffu, h3 ? lo : hi, 8);
+        b[k] = (h3 ? hi : lo) + recv;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {   // keep b[0..1] or b[2]
+        const float lo = b[k], hi = k < 1 ? b[2 + k] : 0.f;
+        const float recv = __shfl_xor_sync(0xffffffffu, h2 ? lo : hi, 4);
+        c[k] = (h2 ? hi : lo) + recv;
+    }
+    const float recv = __shfl_xor_sync(0xffffffffu, h1 ? c[0] : c[1], 2);
+    float d = (h1 ? c[1] : c[0]) + recv;
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
+}
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 16 / kWarps) blend_backward_kernel(
+    const Record *__restrict__ recs, const uint32_t *__restrict__ list, const uint2 *__restrict__ ranges,
+    const uint32_t *__restrict__ order, const uint32_t *__restrict__ tile_maxlast, int W, int H, int gx,
+    const float *__restrict__ bg, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
+    const float *__restrict__ dL_dout, int64_t sc, int64_t sy, int64_t sx, float *__restrict__ acc) {
+    constexpr int kSplit = 8 / kWarps;
+    __shared__ __align__(128) StageSmem<kWarps> sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x;
+    const int item = blockIdx.x / kSplit, sub = blockIdx.x % kSplit;
+    const int tile = order ? (int)order[item] : item;
+    const int len = (int)tile_maxlast[tile];      // list positions [0, len) can matter, walked back to front
+    if (len == 0) return;
     const uint2 range = ranges[tile];
-    if (range.y <= range.x) return;
     int px, py;
-    pixel_of_thread(tile, gx, tid, px, py);
+    pixel_of_thread(tile, gx, sub * kWarps + warp, lane, px, py);
     const bool inside = px < W && py < H;
     const float fx = (float)px, fy = (float)py;
     const size_t pix = (size_t)py * W + px;
@@ -129,60 +283,46 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const Record *__res
         dp2 = gp[2 * sc];
     }
     const float bg_dot = bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2;
+    const int slot = reduce_slot(lane);
 
-    // only instances in front of the deepest last-contributor of the tile can matter
-    uint32_t m = __reduce_max_sync(0xffffffffu, last);
-    if (lane == 0) warp_max[warp] = m;
-    if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    m = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) m = max(m, warp_max[w]);
-    const int len = (int)m;                       // process list positions [0, len) back to front
-    const int nb = (len + kBatch - 1) / kBatch;
-    if (nb == 0) return;
-    const Record *src = records + range.x;
-    auto issue = [&](int b, int buf) {
-        const uint32_t bytes = (uint32_t)min(kBatch, len - b * kBatch) * (uint32_t)sizeof(Record);
-        mbar_expect_tx(&bar[buf], bytes);
-        bulk_g2s(&stage[buf][0], src + (size_t)b * kBatch, bytes, &bar[buf]);
-    };
-    if (tid == 0) issue(nb - 1, 0);
+    ListStager<kWarps> st{sm, list, recs, range.x, len, 0, true};
+    st.nb = (len + st.B - 1) / st.B;
+    st.prologue();
 
+    // nothing to do for this warp's pixels behind their deepest last contributor
+    const uint32_t wlast = __reduce_max_sync(0xffffffffu, last);
     float T = T_final, a0 = 0.f, a1 = 0.f, a2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
-    int it = 0;
-    for (int b = nb - 1; b >= 0; --b, ++it) {
-        const int cur = it & 1;
-        if (tid == 0 && b > 0) issue(b - 1, cur ^ 1);
-        mbar_wait(&bar[cur], (uint32_t)((it >> 1) & 1));
-        const int cnt = min(kBatch, len - b * kBatch);
-        const float4 *st = reinterpret_cast<const float4 *>(&stage[cur][0]);
-        for (int j = cnt - 1; j >= 0; --j) {
-            const uint32_t pos = (uint32_t)(b * kBatch + j);
-            const float4 ra = st[3 * j], rb = st[3 * j + 1];
+    for (int i = 0; i < st.nb; ++i) {
+        st.advance(i);
+        const int cnt = st.count(i);
+        const float4 *r = st.records(i);
+        const int b = st.batch_of(i);
+        const uint32_t *ids = &sm.ids[i % 3][(range.x + (uint32_t)(b * st.B)) & 3u];
+        int j = cnt - 1;
+        if ((uint32_t)(b * st.B) + (uint32_t)cnt > wlast) j = (int)wlast - b * st.B - 1;   // may be negative: whole batch skipped
+        for (; j >= 0; --j) {
+            const uint32_t pos = (uint32_t)(b * st.B + j);
+            const float4 ra = r[3 * j], rb = r[3 * j + 1];
+            const float2 rc = *reinterpret_cast<const float2 *>(&r[3 * j + 2]);
             const float dx = ra.x - fx, dy = ra.y - fy;
             const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
+            const bool cand = (pos < last) && (power <= 0.0f) && !(power < rc.y);
+            if (!__any_sync(0xffffffffu, cand)) continue;
             const float G = expf(power);
             const float alpha = fminf(kAlphaMax, rb.y * G);
-            const bool active = (pos < last) && (power <= 0.0f) && (alpha >= kAlphaMin);
+            const bool active = cand && (alpha >= kAlphaMin);
             if (!__any_sync(0xffffffffu, active)) continue;
-            const float4 rc = st[3 * j + 2];
-            float g_m2x = 0.f, g_m2y = 0.f, g_cx = 0.f, g_cy = 0.f, g_cw = 0.f, g_op = 0.f, g_c0 = 0.f, g_c1 = 0.f, g_c2 = 0.f;
+            float v[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (active) {
                 T = T / (1.0f - alpha);
                 const float dch = alpha * T;
-                float dL_dalpha;
                 a0 = last_alpha * lc0 + (1.f - last_alpha) * a0;
                 a1 = last_alpha * lc1 + (1.f - last_alpha) * a1;
                 a2 = last_alpha * lc2 + (1.f - last_alpha) * a2;
                 lc0 = rb.z; lc1 = rb.w; lc2 = rc.x;
-                dL_dalpha = (lc0 - a0) * dp0 + (lc1 - a1) * dp1 + (lc2 - a2) * dp2;
-                g_c0 = dch * dp0; g_c1 = dch * dp1; g_c2 = dch * dp2;
+                float dL_dalpha = (lc0 - a0) * dp0 + (lc1 - a1) * dp1 + (lc2 - a2) * dp2;
+                v[6] = dch * dp0; v[7] = dch * dp1; v[8] = dch * dp2;
                 dL_dalpha *= T;
                 last_alpha = alpha;
                 dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
@@ -190,26 +330,17 @@ __global__ void __launch_bounds__(256) blend_backward_kernel(const Record *__res
                 const float gdx = G * dx, gdy = G * dy;
                 const float dG_ddelx = -gdx * ra.z - gdy * ra.w;
                 const float dG_ddely = -gdy * rb.x - gdx * ra.w;
-                g_m2x = dL_dG * dG_ddelx * ddelx_dx;
-                g_m2y = dL_dG * dG_ddely * ddely_dy;
-                g_cx = -0.5f * gdx * dx * dL_dG;
-                g_cy = -0.5f * gdx * dy * dL_dG;
-                g_cw = -0.5f * gdy * dy * dL_dG;
-                g_op = G * dL_dalpha;
+                v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                v[1] = dL_dG * dG_ddely * ddely_dy;
+                v[2] = -0.5f * gdx * dx * dL_dG;
+                v[3] = -0.5f * gdx * dy * dL_dG;
+                v[4] = -0.5f * gdy * dy * dL_dG;
+                v[5] = G * dL_dalpha;
             }
-            g_m2x = warp_sum(g_m2x); g_m2y = warp_sum(g_m2y);
-            g_cx = warp_sum(g_cx); g_cy = warp_sum(g_cy); g_cw = warp_sum(g_cw);
-            g_op = warp_sum(g_op);
-            g_c0 = warp_sum(g_c0); g_c1 = warp_sum(g_c1); g_c2 = warp_sum(g_c2);
-            if (lane == 0) {
-                float *dst = acc + (size_t)__float_as_uint(rc.y) * kAccStride;
-                red_add(dst + 0, g_m2x); red_add(dst + 1, g_m2y);
-                red_add(dst + 2, g_cx); red_add(dst + 3, g_cy); red_add(dst + 4, g_cw);
-                red_add(dst + 5, g_op);
-                red_add(dst + 6, g_c0); red_add(dst + 7, g_c1); red_add(dst + 8, g_c2);
-            }
+            const float total = reduce_scatter9(v, lane);
+            if (slot >= 0) red_add(acc + (size_t)ids[j] * kAccStride + slot, total);
         }
-        __syncthreads();   // stage[cur] may be overwritten by the copy issued in the next iteration
+        __syncthreads();   // this batch's buffers may be overwritten by the copies issued in the next step
     }
 }
 
@@ -386,9 +517,35 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBwdArgs a) 
     for (int k = 0; k < 6; ++k) a.dL_dcov3D[6 * (size_t)i + k] = gcov[k];
 }
 
+// work-item shape of the tile kernels: 8 warps = one 16x16 tile per CTA, 4 warps = one 16x8 half tile per CTA
+static int blend_warps() {
+    static int cached = 0;
+    if (!cached) {
+        const char *e = getenv("MB_BLEND_WARPS");
+        cached = (e && atoi(e) == 4) ? 4 : 8;
+    }
+    return cached;
+}
+
 }  // namespace mb
 
 using namespace mb;
+
+extern "C" int mb_raster_state_layout(int32_t num_points, int64_t capacity, int32_t w, int32_t h, int64_t *out, int32_t n_out) {
+    MB_REQUIRE(out != nullptr && n_out >= 8, "mb_raster_state_layout: need room for 8 offsets");
+    GeomState g = GeomState::carve(nullptr, num_points);
+    BinningState b = BinningState::carve(nullptr, capacity);
+    ImageState im = ImageState::carve(nullptr, w, h);
+    out[0] = (int64_t)((char *)im.final_T - (char *)nullptr);
+    out[1] = (int64_t)((char *)im.n_contrib - (char *)nullptr);
+    out[2] = (int64_t)((char *)im.ranges - (char *)nullptr);
+    out[3] = (int64_t)((char *)im.tile_maxlast - (char *)nullptr);
+    out[4] = (int64_t)((char *)b.gid_b - (char *)nullptr);
+    out[5] = (int64_t)((char *)b.tile_b - (char *)nullptr);
+    out[6] = (int64_t)((char *)g.rec - (char *)nullptr);
+    out[7] = (int64_t)((char *)g.counters - (char *)nullptr);
+    return MB_OK;
+}
 
 extern "C" int mb_raster_forward_render(const mb_raster_inputs *in, void *geom, void *binning, size_t binning_bytes,
                                         int64_t capacity, void *image_buf, size_t image_bytes, float *out_color,
@@ -407,18 +564,26 @@ extern "C" int mb_raster_forward_render(const mb_raster_inputs *in, void *geom, 
                   image_bytes, im.bytes);
         return MB_ERR_WORKSPACE;
     }
+    MB_CUDA(cudaMemsetAsync(im.ranges, 0, (size_t)((char *)im.order_fwd - (char *)im.ranges), s));   // ranges + tile_maxlast
+    const bool dbg = in->debug != 0;
+    const uint32_t *order = nullptr;
     if (d.P > 0 && capacity > 0) {
         rc = build_instances(in, d, g, b, im, capacity, s);
         if (rc) return rc;
-    } else {
-        MB_CUDA(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)d.tiles, s));
+        rc = tile_order(nullptr, im.ranges, d.tiles, im.order_fwd, s, dbg);
+        if (rc) return rc;
+        order = im.order_fwd;
     }
     {
         KernelTimer kt("blend_forward", s);
-        blend_forward_kernel<<<d.tiles, 256, 0, s>>>(b.records, im.ranges, d.W, d.H, d.gx, in->background, out_color, im.final_T,
-                                                     im.n_contrib);
+        if (blend_warps() == 4)
+            blend_forward_kernel<4><<<d.tiles * 2, 128, 0, s>>>(g.rec, b.gid_b, im.ranges, order, d.W, d.H, d.gx, in->background,
+                                                                out_color, im.final_T, im.n_contrib, im.tile_maxlast);
+        else
+            blend_forward_kernel<8><<<d.tiles, 256, 0, s>>>(g.rec, b.gid_b, im.ranges, order, d.W, d.H, d.gx, in->background,
+                                                            out_color, im.final_T, im.n_contrib, im.tile_maxlast);
     }
-    return check_launch("blend_forward", in->debug != 0, s);
+    return check_launch("blend_forward", dbg, s);
 }
 
 extern "C" size_t mb_raster_backward_scratch_bytes(int32_t num_points) {
@@ -451,10 +616,18 @@ extern "C" int mb_raster_backward(const mb_raster_inputs *in, const int32_t *rad
     float *acc = reinterpret_cast<float *>(grad_scratch);
     MB_CUDA(cudaMemsetAsync(acc, 0, (size_t)d.P * kAccStride * sizeof(float), s));
     if (capacity > 0) {
+        rc = tile_order(im.tile_maxlast, nullptr, d.tiles, im.order_bwd, s, dbg);
+        if (rc) return rc;
         {
             KernelTimer kt("blend_backward", s);
-            blend_backward_kernel<<<d.tiles, 256, 0, s>>>(b.records, im.ranges, d.W, d.H, d.gx, in->background, im.final_T,
-                                                          im.n_contrib, dL_dout, stride_c, stride_y, stride_x, acc);
+            if (blend_warps() == 4)
+                blend_backward_kernel<4><<<d.tiles * 2, 128, 0, s>>>(g.rec, b.gid_b, im.ranges, im.order_bwd, im.tile_maxlast, d.W, d.H,
+                                                                     d.gx, in->background, im.final_T, im.n_contrib, dL_dout,
+                                                                     stride_c, stride_y, stride_x, acc);
+            else
+                blend_backward_kernel<8><<<d.tiles, 256, 0, s>>>(g.rec, b.gid_b, im.ranges, im.order_bwd, im.tile_maxlast, d.W, d.H,
+                                                                 d.gx, in->background, im.final_T, im.n_contrib, dL_dout, stride_c,
+                                                                 stride_y, stride_x, acc);
         }
         rc = check_launch("blend_backward", dbg, s);
         if (rc) return rc;

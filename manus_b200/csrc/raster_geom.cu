@@ -13,7 +13,7 @@ namespace mb {
 struct PreArgs {
     int P, W, H, gx, gy, deg, M;
     float tanx, tany, focx, focy, scale_mod;
-    const float *means3D, *opac, *cov3D_precomp, *scales, *rots, *shs, *view, *proj, *campos;
+    const float *means3D, *opac, *colors, *cov3D_precomp, *scales, *rots, *shs, *view, *proj, *campos;
     GeomState g;
     int32_t *radii;
 };
@@ -123,9 +123,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
                     tiles = (uint32_t)area;
                     key = __float_as_uint(tz);
                     a.g.rect[i] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
-                    a.g.xy[i] = make_float2(px, py);
-                    a.g.depth[i] = tz;
-                    a.g.conic_opacity[i] = make_float4(cc * di, -cb * di, ca * di, a.opac[i]);
+                    float rgb[3];
                     if (kSH) {   // step 10: colour from SH in the world-space view direction
                         float dx = mx - cam[32], dy = my - cam[33], dz = mz - cam[34];
                         const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
@@ -141,10 +139,21 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
                             for (int k = 0; k < nb; ++k) r += basis[k] * sh[3 * k + ch];
                             r += 0.5f;
                             if (r < 0.f) { mask |= 1u << ch; r = 0.f; }
-                            a.g.rgb[3 * (size_t)i + ch] = r;
+                            rgb[ch] = r;
                         }
                         a.g.clamped[i] = mask;
+                    } else {
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) rgb[ch] = a.colors[3 * (size_t)i + ch];
                     }
+                    const float op = a.opac[i];
+                    // below this power, op * exp(power) < 1/255 with a wide margin (NaN for op < 0: never skips)
+                    const float cut = -logf(255.0f * op) - 1e-4f;
+                    Record r;
+                    r.a = make_float4(px, py, cc * di, -cb * di);
+                    r.b = make_float4(ca * di, op, rgb[0], rgb[1]);
+                    r.c = make_float4(rgb[2], cut, 0.f, 0.f);
+                    a.g.rec[i] = r;
                 }
             }
         }
@@ -157,7 +166,9 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
     if ((tid & 31) == 0 && vis) atomicAdd(&a.g.counters[kCntVisible], (uint32_t)__popc(vis));
 }
 
-// one thread per depth-sorted Gaussian: writes its (tile id, gaussian id) run at its exclusive offset
+// Instance emission, warp-cooperative: a warp owns 32 consecutive depth-sorted Gaussians; their (tile id, gaussian id)
+// runs are contiguous in the instance list, so the lanes walk the warp's slots in order (coalesced 128-B stores) and
+// find the owning Gaussian of each slot by a shuffle binary search over the warp's inclusive tile counts.
 __global__ void __launch_bounds__(256) emit_instances_kernel(int P, int gx, const uint32_t *__restrict__ sorted_idx,
                                                              const uint32_t *__restrict__ offsets,
                                                              const uint32_t *__restrict__ tiles_touched,
@@ -165,42 +176,96 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, int gx, cons
                                                              uint32_t *__restrict__ counters, int64_t capacity,
                                                              uint32_t *__restrict__ tile_out, uint32_t *__restrict__ gid_out) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && (int64_t)counters[kCntRendered] > capacity) counters[kCntOverflow] = 1;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) {
-        const uint32_t g = sorted_idx[i];
-        if (tiles_touched[g] == 0) continue;
-        const ushort4 r = rect[g];
-        int64_t pos = offsets[i];
-        for (int y = r.y; y < r.w; ++y)
-            for (int x = r.x; x < r.z; ++x, ++pos)
-                if (pos < capacity) {
-                    tile_out[pos] = (uint32_t)(y * gx + x);
-                    gid_out[pos] = g;
-                }
+    const int lane = threadIdx.x & 31;
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (int i0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; i0 < P; i0 += warps_total * 32) {
+        const int i = i0 + lane;
+        uint32_t g = 0, cnt = 0, off = 0;
+        ushort4 r = make_ushort4(0, 0, 1, 1);
+        if (i < P) {
+            g = sorted_idx[i];
+            cnt = tiles_touched[g];
+            off = offsets[i];
+            if (cnt) r = rect[g];
+        }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const int64_t base = (int64_t)__shfl_sync(0xffffffffu, off, 0);
+        const uint32_t width = (uint32_t)(r.z - r.x);
+        for (uint32_t s0 = 0; s0 < total; s0 += 32) {
+            const uint32_t sl = s0 + lane;
+            int lo = 0, hi = 31;   // first lane whose inclusive count exceeds sl
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const int mid = (lo + hi) >> 1;
+                const uint32_t v = __shfl_sync(0xffffffffu, incl, mid);
+                if (v > sl) hi = mid; else lo = mid + 1;
+            }
+            const uint32_t o_incl = __shfl_sync(0xffffffffu, incl, lo), o_cnt = __shfl_sync(0xffffffffu, cnt, lo);
+            const uint32_t o_g = __shfl_sync(0xffffffffu, g, lo), o_w = __shfl_sync(0xffffffffu, width, lo);
+            const uint32_t o_x0 = __shfl_sync(0xffffffffu, (uint32_t)r.x, lo), o_y0 = __shfl_sync(0xffffffffu, (uint32_t)r.y, lo);
+            const int64_t pos = base + sl;
+            if (sl < total && pos < capacity) {
+                const uint32_t local = sl - (o_incl - o_cnt);
+                const uint32_t ty = local / o_w, tx = local - ty * o_w;
+                tile_out[pos] = (o_y0 + ty) * (uint32_t)gx + o_x0 + tx;
+                gid_out[pos] = o_g;
+            }
+        }
     }
 }
 
-// tile ranges + 48-B blend records, one thread per sorted instance
-__global__ void __launch_bounds__(256) finalize_instances_kernel(const uint32_t *__restrict__ counters, int64_t capacity,
-                                                                 const uint32_t *__restrict__ tile_sorted,
-                                                                 const uint32_t *__restrict__ gid_sorted,
-                                                                 const float2 *__restrict__ xy,
-                                                                 const float4 *__restrict__ conic_opacity,
-                                                                 const float *__restrict__ rgb, uint2 *__restrict__ ranges,
-                                                                 Record *__restrict__ records) {
+// tile ranges from the tile-sorted instance list, one thread per instance
+__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t *__restrict__ counters, int64_t capacity,
+                                                          const uint32_t *__restrict__ tile_sorted, uint2 *__restrict__ ranges) {
     int64_t n = counters[kCntRendered];
     if (n > capacity) n = capacity;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t t = tile_sorted[i], g = gid_sorted[i];
+        const uint32_t t = tile_sorted[i];
         if (i == 0 || tile_sorted[i - 1] != t) ranges[t].x = (uint32_t)i;
         if (i == n - 1 || tile_sorted[i + 1] != t) ranges[t].y = (uint32_t)(i + 1);
-        const float2 c = xy[g];
-        const float4 co = conic_opacity[g];
-        Record r;
-        r.a = make_float4(c.x, c.y, co.x, co.y);
-        r.b = make_float4(co.z, co.w, rgb[3 * (size_t)g], rgb[3 * (size_t)g + 1]);
-        r.c = make_float4(rgb[3 * (size_t)g + 2], __uint_as_float(g), 0.f, 0.f);
-        records[i] = r;
     }
+}
+
+// Work order of the tile kernels: tiles by descending weight (list length for the forward, deepest last-contributor for
+// the backward) so that the longest lists start first.  Counting sort over 129 quarter-octave buckets, single CTA.
+__device__ __forceinline__ int weight_bucket(uint32_t w) {
+    if (w == 0) return 0;
+    const int e = 31 - __clz(w);
+    const int m = e >= 2 ? (int)((w >> (e - 2)) & 3u) : (int)((w << (2 - e)) & 3u);
+    return 1 + 4 * e + m;
+}
+
+__global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t *__restrict__ weight, const uint2 *__restrict__ ranges,
+                                                          int tiles, uint32_t *__restrict__ order) {
+    __shared__ uint32_t hist[132], base[132];
+    for (int b = threadIdx.x; b < 132; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+        const uint32_t w = weight ? weight[t] : ranges[t].y - ranges[t].x;
+        atomicAdd(&hist[weight_bucket(w)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int b = 131; b >= 0; --b) { base[b] = run; run += hist[b]; }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+        const uint32_t w = weight ? weight[t] : ranges[t].y - ranges[t].x;
+        order[atomicAdd(&base[weight_bucket(w)], 1u)] = (uint32_t)t;
+    }
+}
+
+int tile_order(const uint32_t *weight_or_null, const uint2 *ranges_or_null, int tiles, uint32_t *order, cudaStream_t s, bool debug) {
+    KernelTimer kt("tile_order", s);
+    tile_order_kernel<<<1, 1024, 0, s>>>(weight_or_null, ranges_or_null, tiles, order);
+    return check_launch("tile_order", debug, s);
 }
 
 int validate_raster_inputs(const mb_raster_inputs *in, const char *who) {
@@ -230,7 +295,7 @@ static int tile_bits(int tiles) {
     return b < 1 ? 1 : b;
 }
 
-// emission + per-tile ordering + ranges + records; shared with the render entry point (raster_blend.cu)
+// emission + per-tile ordering + ranges; shared with the render entry point (raster_blend.cu)
 int build_instances(const mb_raster_inputs *in, const RasterDims &d, const GeomState &g, const BinningState &b,
                     const ImageState &im, int64_t capacity, cudaStream_t s) {
     const bool dbg = in->debug != 0;
@@ -249,11 +314,10 @@ int build_instances(const mb_raster_inputs *in, const RasterDims &d, const GeomS
     if (rc) return rc;
     const int grid_d = (int)max((int64_t)1, min((capacity + 255) / 256, (int64_t)sm_count() * 16));
     {
-    KernelTimer kt("finalize_instances", s);
-    finalize_instances_kernel<<<grid_d, 256, 0, s>>>(g.counters, capacity, b.tile_b, b.gid_b, g.xy, g.conic_opacity,
-                                                     in->shs ? g.rgb : in->colors_precomp, im.ranges, b.records);
+    KernelTimer kt("tile_ranges", s);
+    tile_ranges_kernel<<<grid_d, 256, 0, s>>>(g.counters, capacity, b.tile_b, im.ranges);
     }
-    return check_launch("finalize_instances", dbg, s);
+    return check_launch("tile_ranges", dbg, s);
 }
 
 }  // namespace mb
@@ -287,7 +351,7 @@ extern "C" int mb_raster_forward_geom(const mb_raster_inputs *in, void *geom, si
         a.P = d.P; a.W = d.W; a.H = d.H; a.gx = d.gx; a.gy = d.gy; a.deg = in->sh_degree; a.M = in->sh_coeffs;
         a.tanx = in->tanfovx; a.tany = in->tanfovy; a.focx = d.focx; a.focy = d.focy; a.scale_mod = in->scale_modifier;
         a.means3D = in->means3D; a.opac = in->opacities; a.cov3D_precomp = in->cov3D_precomp; a.scales = in->scales;
-        a.rots = in->rotations; a.shs = in->shs; a.view = in->viewmatrix; a.proj = in->projmatrix; a.campos = in->campos;
+        a.rots = in->rotations; a.shs = in->shs; a.colors = in->colors_precomp; a.view = in->viewmatrix; a.proj = in->projmatrix; a.campos = in->campos;
         a.g = g; a.radii = radii;
         const int grid = (d.P + 255) / 256;
         {

@@ -1,13 +1,18 @@
 // Layout of the three opaque rasterizer buffers (geom / binning / image) -- shared by forward and backward.
 //
 // HBM layout (all arrays 256-B aligned inside their buffer):
-//   geom    (per Gaussian, P rows)  : xy f32x2 | depth f32 | conic+opacity f32x4 | rgb f32x3 | cov3D f32x6 | tiles u32 | tile rect u16x4 |
-//                                     clamp mask u32 | depth key u32 | identity idx u32 | depth-sorted key/idx u32 |
+//   geom    (per Gaussian, P rows)  : 48-B blend record | cov3D f32x6 (scale/rotation mode only) | tiles u32 | tile rect u16x4 |
+//                                     SH clamp mask u32 | depth key u32 | identity idx u32 | depth-sorted key/idx u32 |
 //                                     instance offsets (depth order) u32 | scan partials | sort workspace | counters
-//   binning (per instance, D rows)  : tile id u32 x2 (ping-pong) | gaussian id u32 x2 | 48-B blend record | sort workspace
-//   image   (per pixel / per tile)  : final_T f32 | n_contrib u32 | tile range u32x2 | tile work order u32
-// The 48-B record is what the tile kernels stream through shared memory with bulk (TMA) copies:
-//   { x, y, conic.x, conic.y | conic.z, opacity, r, g | b, gaussian id (bits), 0, 0 }
+//   binning (per instance, D rows)  : tile id u32 x2 (ping-pong) | gaussian id u32 x2 (ping-pong; the sorted one is the per-tile
+//                                     depth-ordered list the tile kernels walk) | sort workspace
+//   image   (per pixel / per tile)  : final_T f32 | n_contrib u32 | tile range u32x2 | deepest last-contributor per tile u32 |
+//                                     tile work order (forward, backward) u32
+// The 48-B record is written ONCE per Gaussian by the projection kernel (24 MB at 500k Gaussians: L2 resident) and is
+// what the tile kernels gather into shared memory with 128-bit loads, driven by the TMA-staged id list:
+//   { x, y, conic.x, conic.y | conic.z, opacity, r, g | b, power cut-off, 0, 0 }
+// power cut-off = -ln(255 * opacity) - 1e-4: below it opacity*exp(power) < 1/255 holds with a wide fp32 margin, so the
+// exponential need not be evaluated (the exact test alpha < 1/255 still decides everything above the cut-off).
 #pragma once
 #include "common.cuh"
 #include "sort_scan.cuh"
@@ -19,16 +24,13 @@ enum Counter { kCntRendered = 0, kCntVisible = 1, kCntOverflow = 2, kCntTileCurs
 struct Record {   // 48 bytes, 16-B aligned
     float4 a;     // x, y, conic.x, conic.y
     float4 b;     // conic.z, opacity, r, g
-    float4 c;     // b, id-as-float-bits, 0, 0
+    float4 c;     // b, power cut-off, 0, 0
 };
 static_assert(sizeof(Record) == 48, "record must be 48 bytes");
 
 struct GeomState {
     uint32_t *counters;
-    float2 *xy;
-    float *depth;
-    float4 *conic_opacity;
-    float *rgb;        // [P*3]
+    Record *rec;       // [P]
     float *cov3D;      // [P*6]
     uint32_t *tiles_touched;
     ushort4 *rect;     // tile rectangle (x0, y0, x1, y1), exclusive upper bounds
@@ -42,10 +44,7 @@ struct GeomState {
         GeomState g;
         const size_t n = (size_t)(P > 0 ? P : 1);
         g.counters = c.take<uint32_t>(kNumCounters);
-        g.xy = c.take<float2>(n);
-        g.depth = c.take<float>(n);
-        g.conic_opacity = c.take<float4>(n);
-        g.rgb = c.take<float>(3 * n);
+        g.rec = c.take<Record>(n);
         g.cov3D = c.take<float>(6 * n);
         g.tiles_touched = c.take<uint32_t>(n);
         g.rect = c.take<ushort4>(n);
@@ -62,22 +61,22 @@ struct GeomState {
     }
 };
 
+constexpr int kListPad = 8;   // slack after the id list: 16-B aligned bulk copies may read up to 3 ids past a tile's range
+
 struct BinningState {
     uint32_t *tile_a, *tile_b;   // tile id per instance (ping-pong)
-    uint32_t *gid_a, *gid_b;     // gaussian id per instance
-    Record *records;             // sorted by (tile, depth)
+    uint32_t *gid_a, *gid_b;     // gaussian id per instance; gid_b = sorted by (tile, depth)
     void *sort_ws;
     size_t bytes;
 
     static BinningState carve(void *p, int64_t capacity) {
         Carver c(p);
         BinningState b;
-        const size_t n = (size_t)(capacity > 0 ? capacity : 1);
+        const size_t n = (size_t)(capacity > 0 ? capacity : 1) + kListPad;
         b.tile_a = c.take<uint32_t>(n);
         b.tile_b = c.take<uint32_t>(n);
         b.gid_a = c.take<uint32_t>(n);
         b.gid_b = c.take<uint32_t>(n);
-        b.records = c.take<Record>(n + 1);
         b.sort_ws = c.take<char>(sort_workspace_bytes((int64_t)n));
         b.bytes = c.off;
         return b;
@@ -85,11 +84,12 @@ struct BinningState {
 };
 
 struct ImageState {
-    float *final_T;        // [H*W]
-    uint32_t *n_contrib;   // [H*W]
-    uint2 *ranges;         // [tiles] (start, end) into records
-    uint32_t *tile_order;  // [tiles] tiles sorted by descending length (work queue)
-    uint32_t *tile_len;    // [tiles]
+    float *final_T;          // [H*W]
+    uint32_t *n_contrib;     // [H*W]
+    uint2 *ranges;           // [tiles] (start, end) into the sorted id list
+    uint32_t *tile_maxlast;  // [tiles] max over the tile's pixels of n_contrib (how far the backward has to walk)
+    uint32_t *order_fwd;     // [tiles] tiles by descending list length
+    uint32_t *order_bwd;     // [tiles] tiles by descending tile_maxlast
     size_t bytes;
 
     static ImageState carve(void *p, int W, int H) {
@@ -100,8 +100,9 @@ struct ImageState {
         s.final_T = c.take<float>(px ? px : 1);
         s.n_contrib = c.take<uint32_t>(px ? px : 1);
         s.ranges = c.take<uint2>(tiles ? tiles : 1);
-        s.tile_order = c.take<uint32_t>(tiles ? tiles : 1);
-        s.tile_len = c.take<uint32_t>(tiles ? tiles : 1);
+        s.tile_maxlast = c.take<uint32_t>(tiles ? tiles : 1);
+        s.order_fwd = c.take<uint32_t>(tiles ? tiles : 1);
+        s.order_bwd = c.take<uint32_t>(tiles ? tiles : 1);
         s.bytes = c.off;
         return s;
     }
@@ -127,5 +128,8 @@ inline RasterDims raster_dims(const mb_raster_inputs *in) {
 }
 
 int validate_raster_inputs(const mb_raster_inputs *in, const char *who);
+
+// order[i] = tile with the i-th largest weight (approximately: descending power-of-two-ish buckets); single CTA
+int tile_order(const uint32_t *weight_or_null, const uint2 *ranges_or_null, int tiles, uint32_t *order, cudaStream_t s, bool debug);
 
 }  // namespace mb

@@ -244,22 +244,21 @@ class GaussianRasterizer(nn.Module):
 
 
 def debug_views(st: RasterState):
-    """Typed views into the opaque buffers of a finished forward (layout: manus_b200/csrc/raster_state.cuh).
-    For tests and diagnostics only: {'final_T' [H,W], 'n_contrib' [H,W], 'ranges' [tiles,2], 'records' [cap,12],
-    'point_list' [num_rendered] (gaussian id per sorted instance)}."""
-    al = lambda n: (n + 255) // 256 * 256
-    H, W = st.inputs.image_height, st.inputs.image_width
+    """Typed views into the opaque buffers of a finished forward (offsets from mb_raster_state_layout).
+    For tests and diagnostics only: {'final_T' [H,W], 'n_contrib' [H,W], 'ranges' [tiles,2], 'tile_maxlast' [tiles],
+    'point_list' [num_rendered] (gaussian id per sorted instance), 'records' [N,12]}."""
+    L = _lib.lib()
+    H, W, N = st.inputs.image_height, st.inputs.image_width, st.inputs.num_points
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     px = H * W
+    off = (C.c_int64 * 8)()
+    _lib.check(L.mb_raster_state_layout(N, st.capacity, W, H, off, 8), "mb_raster_state_layout")
     img = st.image
-    o1 = al(px * 4)
-    o2 = o1 + al(px * 4)
-    final_T = img[: px * 4].view(torch.float32).reshape(H, W)
-    n_contrib = img[o1: o1 + px * 4].view(torch.int32).reshape(H, W)
-    ranges = img[o2: o2 + tiles * 8].view(torch.int32).reshape(tiles, 2)
-    cap = max(st.capacity, 1)
-    ro = 4 * al(cap * 4)
-    records = st.binning[ro: ro + cap * 48].view(torch.float32).reshape(cap, 12)
+    final_T = img[off[0]: off[0] + px * 4].view(torch.float32).reshape(H, W)
+    n_contrib = img[off[1]: off[1] + px * 4].view(torch.int32).reshape(H, W)
+    ranges = img[off[2]: off[2] + tiles * 8].view(torch.int32).reshape(tiles, 2)
+    maxlast = img[off[3]: off[3] + tiles * 4].view(torch.int32)
     n = st.resolve()
-    point_list = records[: min(n, cap), 9].contiguous().view(torch.int32)
-    return dict(final_T=final_T, n_contrib=n_contrib, ranges=ranges, records=records, point_list=point_list)
+    point_list = st.binning[off[4]: off[4] + min(n, st.capacity) * 4].view(torch.int32)
+    records = st.geom[off[6]: off[6] + N * 48].view(torch.float32).reshape(N, 12)
+    return dict(final_T=final_T, n_contrib=n_contrib, ranges=ranges, tile_maxlast=maxlast, point_list=point_list, records=records)
