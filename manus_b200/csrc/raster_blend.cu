@@ -9,9 +9,10 @@
 // when all its pixels are saturated, the backward starts at the tile's deepest last contributor.
 //
 // Per pixel the arithmetic is the reference's sequential front-to-back product, so results do not depend on the
-// schedule.  The inner loops are warp-convergent: a Gaussian whose power is above 0 or below its cut-off on all 32 pixels
-// of the warp costs ~14 instructions and no exponential (warp vote); the backward sums each of its nine per-Gaussian
-// partials over the warp with a 12-shuffle reduce-scatter and issues them as one vector of RED.ADD.F32 from nine lanes.
+// schedule.  The inner loops are warp-convergent: per round, the 32 lanes box-test 32 list entries against the warp's
+// pixel block (one ballot), and only the survivors are evaluated per pixel; a survivor whose power is below its cut-off
+// on all 32 pixels costs no exponential (warp vote).  The backward sums each of its nine per-Gaussian partials over the
+// warp with a 12-shuffle reduce-scatter and issues them as one vector of RED.ADD.F32 from nine lanes.
 #include <stdlib.h>
 
 #include "raster_state.cuh"
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(kWarps * 32, 24 / kWarps) blend_forward_kernel
     pixel_of_thread(tile, gx, sub * kWarps + warp, lane, px, py);
     const bool inside = px < W && py < H;
     const float fx = (float)px, fy = (float)py;
+    const float bcx = (float)(px - (lane & 7)) + 3.5f, bcy = (float)(py - (lane >> 3)) + 1.5f;   // centre of the warp's pixel block
 
     ListStager<kWarps> st{sm, list, recs, range.x, (int)(range.y - range.x), 0, false};
     st.nb = (st.len + st.B - 1) / st.B;
@@ -144,55 +146,42 @@ __global__ void __launch_bounds__(kWarps * 32, 24 / kWarps) blend_forward_kernel
         const int cnt = st.count(i);
         const float4 *r = st.records(i);
         const uint32_t base = (uint32_t)(i * st.B);
-        // one list entry: exact reference arithmetic, executed only when some pixel of the warp may be touched
-        auto blend = [&](const float4 &ra, const float4 &rb, float blue, float power, bool cand, uint32_t pos1) {
-            const float alpha = fminf(kAlphaMax, rb.y * expf(power));
-            const bool ok = cand && !done && alpha >= kAlphaMin;
-            const float test_T = T * (1.0f - alpha);
-            const bool stop = ok && test_T < kTMin;
-            if (ok && !stop) {
-                const float w = alpha * T;
-                C0 += rb.z * w;
-                C1 += rb.w * w;
-                C2 += blue * w;
-                T = test_T;
-                last = pos1;
+        // 32 list entries per round: lane k box-tests entry j0+k against the warp's 8x4 pixel block, the survivors are
+        // blended in list order with the exact reference arithmetic
+        for (int j0 = 0; j0 < cnt && !wdone; j0 += 32) {
+            bool hit = false;
+            if (j0 + lane < cnt) {
+                const float4 ra = r[3 * (j0 + lane)], rc = r[3 * (j0 + lane) + 2];
+                hit = fabsf(ra.x - bcx) <= rc.z + 3.5f && fabsf(ra.y - bcy) <= rc.w + 1.5f;
             }
-            done = done || stop;
-            if (__any_sync(0xffffffffu, stop)) wdone = __all_sync(0xffffffffu, done);
-        };
-        int j = 0;
-        if (!wdone) {
-            for (; j + 4 <= cnt; j += 4) {
-                float4 ra[4], rb[4];
-                float2 rc[4];
-                float power[4];
-                bool cand[4], any = false;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    ra[k] = r[3 * (j + k)];
-                    rb[k] = r[3 * (j + k) + 1];
-                    rc[k] = *reinterpret_cast<const float2 *>(&r[3 * (j + k) + 2]);
-                    const float dx = ra[k].x - fx, dy = ra[k].y - fy;
-                    power[k] = -0.5f * (ra[k].z * dx * dx + rb[k].x * dy * dy) - ra[k].w * dx * dy;
-                    cand[k] = !done && power[k] <= 0.0f && !(power[k] < rc[k].y);
-                    any = any || cand[k];
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                const int j = j0 + __ffs(m) - 1;
+                m &= m - 1;
+                const float4 ra = r[3 * j], rb = r[3 * j + 1];
+                const float2 rc = *reinterpret_cast<const float2 *>(&r[3 * j + 2]);
+                const float dx = ra.x - fx, dy = ra.y - fy;
+                const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
+                const bool cand = !done && power <= 0.0f && !(power < rc.y);
+                if (!__any_sync(0xffffffffu, cand)) continue;
+                const float alpha = fminf(kAlphaMax, rb.y * expf(power));
+                const bool ok = cand && alpha >= kAlphaMin;
+                const float test_T = T * (1.0f - alpha);
+                const bool stop = ok && test_T < kTMin;
+                if (ok && !stop) {
+                    const float w = alpha * T;
+                    C0 += rb.z * w;
+                    C1 += rb.w * w;
+                    C2 += rc.x * w;
+                    T = test_T;
+                    last = base + (uint32_t)j + 1u;
                 }
-                if (!__any_sync(0xffffffffu, any)) continue;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (__any_sync(0xffffffffu, cand[k])) blend(ra[k], rb[k], rc[k].x, power[k], cand[k], base + (uint32_t)(j + k) + 1u);
-                if (wdone) break;
+                done = done || stop;
+                if (__any_sync(0xffffffffu, stop)) {
+                    wdone = __all_sync(0xffffffffu, done);
+                    if (wdone) break;
+                }
             }
-            if (!wdone)
-                for (; j < cnt; ++j) {
-                    const float4 ra = r[3 * j], rb = r[3 * j + 1];
-                    const float2 rc = *reinterpret_cast<const float2 *>(&r[3 * j + 2]);
-                    const float dx = ra.x - fx, dy = ra.y - fy;
-                    const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
-                    const bool cand = !done && power <= 0.0f && !(power < rc.y);
-                    if (__any_sync(0xffffffffu, cand)) blend(ra, rb, rc.x, power, cand, base + (uint32_t)j + 1u);
-                }
         }
         // all reads of this batch are complete after the barrier; it also counts finished pixels (early exit)
         const int ndone = __syncthreads_count(done);
@@ -284,6 +273,7 @@ __global__ void __launch_bounds__(kWarps * 32, 16 / kWarps) blend_backward_kerne
     }
     const float bg_dot = bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2;
     const int slot = reduce_slot(lane);
+    const float bcx = (float)(px - (lane & 7)) + 3.5f, bcy = (float)(py - (lane >> 3)) + 1.5f;   // centre of the warp's pixel block
 
     ListStager<kWarps> st{sm, list, recs, range.x, len, 0, true};
     st.nb = (len + st.B - 1) / st.B;
@@ -299,46 +289,57 @@ __global__ void __launch_bounds__(kWarps * 32, 16 / kWarps) blend_backward_kerne
         const float4 *r = st.records(i);
         const int b = st.batch_of(i);
         const uint32_t *ids = &sm.ids[i % 3][(range.x + (uint32_t)(b * st.B)) & 3u];
-        int j = cnt - 1;
-        if ((uint32_t)(b * st.B) + (uint32_t)cnt > wlast) j = (int)wlast - b * st.B - 1;   // may be negative: whole batch skipped
-        for (; j >= 0; --j) {
-            const uint32_t pos = (uint32_t)(b * st.B + j);
-            const float4 ra = r[3 * j], rb = r[3 * j + 1];
-            const float2 rc = *reinterpret_cast<const float2 *>(&r[3 * j + 2]);
-            const float dx = ra.x - fx, dy = ra.y - fy;
-            const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
-            const bool cand = (pos < last) && (power <= 0.0f) && !(power < rc.y);
-            if (!__any_sync(0xffffffffu, cand)) continue;
-            const float G = expf(power);
-            const float alpha = fminf(kAlphaMax, rb.y * G);
-            const bool active = cand && (alpha >= kAlphaMin);
-            if (!__any_sync(0xffffffffu, active)) continue;
-            float v[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (active) {
-                T = T / (1.0f - alpha);
-                const float dch = alpha * T;
-                a0 = last_alpha * lc0 + (1.f - last_alpha) * a0;
-                a1 = last_alpha * lc1 + (1.f - last_alpha) * a1;
-                a2 = last_alpha * lc2 + (1.f - last_alpha) * a2;
-                lc0 = rb.z; lc1 = rb.w; lc2 = rc.x;
-                float dL_dalpha = (lc0 - a0) * dp0 + (lc1 - a1) * dp1 + (lc2 - a2) * dp2;
-                v[6] = dch * dp0; v[7] = dch * dp1; v[8] = dch * dp2;
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                const float dL_dG = rb.y * dL_dalpha;   // the 0.99 clamp is not masked (upstream behaviour)
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * ra.z - gdy * ra.w;
-                const float dG_ddely = -gdy * rb.x - gdx * ra.w;
-                v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                v[1] = dL_dG * dG_ddely * ddely_dy;
-                v[2] = -0.5f * gdx * dx * dL_dG;
-                v[3] = -0.5f * gdx * dy * dL_dG;
-                v[4] = -0.5f * gdy * dy * dL_dG;
-                v[5] = G * dL_dalpha;
+        int jend = cnt;   // entries at or behind the warp's deepest last contributor cannot matter
+        if ((uint32_t)(b * st.B) + (uint32_t)cnt > wlast) jend = (int)wlast - b * st.B;
+        for (int j0 = ((jend - 1) >> 5) << 5; j0 >= 0; j0 -= 32) {
+            bool hit = false;
+            if (j0 + lane < jend) {
+                const float4 ra = r[3 * (j0 + lane)], rc = r[3 * (j0 + lane) + 2];
+                hit = fabsf(ra.x - bcx) <= rc.z + 3.5f && fabsf(ra.y - bcy) <= rc.w + 1.5f;
             }
-            const float total = reduce_scatter9(v, lane);
-            if (slot >= 0) red_add(acc + (size_t)ids[j] * kAccStride + slot, total);
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {   // survivors back to front
+                const int k = 31 - __clz(m);
+                m &= ~(1u << k);
+                const int j = j0 + k;
+                const uint32_t pos = (uint32_t)(b * st.B + j);
+                const float4 ra = r[3 * j], rb = r[3 * j + 1];
+                const float2 rc = *reinterpret_cast<const float2 *>(&r[3 * j + 2]);
+                const float dx = ra.x - fx, dy = ra.y - fy;
+                const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
+                const bool cand = (pos < last) && (power <= 0.0f) && !(power < rc.y);
+                if (!__any_sync(0xffffffffu, cand)) continue;
+                const float G = expf(power);
+                const float alpha = fminf(kAlphaMax, rb.y * G);
+                const bool active = cand && (alpha >= kAlphaMin);
+                if (!__any_sync(0xffffffffu, active)) continue;
+                float v[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (active) {
+                    T = T / (1.0f - alpha);
+                    const float dch = alpha * T;
+                    a0 = last_alpha * lc0 + (1.f - last_alpha) * a0;
+                    a1 = last_alpha * lc1 + (1.f - last_alpha) * a1;
+                    a2 = last_alpha * lc2 + (1.f - last_alpha) * a2;
+                    lc0 = rb.z; lc1 = rb.w; lc2 = rc.x;
+                    float dL_dalpha = (lc0 - a0) * dp0 + (lc1 - a1) * dp1 + (lc2 - a2) * dp2;
+                    v[6] = dch * dp0; v[7] = dch * dp1; v[8] = dch * dp2;
+                    dL_dalpha *= T;
+                    last_alpha = alpha;
+                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                    const float dL_dG = rb.y * dL_dalpha;   // the 0.99 clamp is not masked (upstream behaviour)
+                    const float gdx = G * dx, gdy = G * dy;
+                    const float dG_ddelx = -gdx * ra.z - gdy * ra.w;
+                    const float dG_ddely = -gdy * rb.x - gdx * ra.w;
+                    v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                    v[1] = dL_dG * dG_ddely * ddely_dy;
+                    v[2] = -0.5f * gdx * dx * dL_dG;
+                    v[3] = -0.5f * gdx * dy * dL_dG;
+                    v[4] = -0.5f * gdy * dy * dL_dG;
+                    v[5] = G * dL_dalpha;
+                }
+                const float total = reduce_scatter9(v, lane);
+                if (slot >= 0) red_add(acc + (size_t)ids[j] * kAccStride + slot, total);
+            }
         }
         __syncthreads();   // this batch's buffers may be overwritten by the copies issued in the next step
     }

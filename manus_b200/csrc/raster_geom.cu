@@ -149,10 +149,13 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
                     const float op = a.opac[i];
                     // below this power, op * exp(power) < 1/255 with a wide margin (NaN for op < 0: never skips)
                     const float cut = -logf(255.0f * op) - 1e-4f;
+                    // half extents of the bounding box of { power >= cut }: dx^2 <= 2|cut| cov2D.xx, dy^2 <= 2|cut| cov2D.yy
+                    // (NaN when no pixel can pass the alpha gate: such a record never survives the tile kernels' box test)
+                    const float ex = sqrtf(-2.0f * cut * ca) * 1.0001f + 0.01f, ey = sqrtf(-2.0f * cut * cc) * 1.0001f + 0.01f;
                     Record r;
                     r.a = make_float4(px, py, cc * di, -cb * di);
                     r.b = make_float4(ca * di, op, rgb[0], rgb[1]);
-                    r.c = make_float4(rgb[2], cut, 0.f, 0.f);
+                    r.c = make_float4(rgb[2], cut, ex, ey);
                     a.g.rec[i] = r;
                 }
             }

@@ -10,9 +10,11 @@
 //                                     tile work order (forward, backward) u32
 // The 48-B record is written ONCE per Gaussian by the projection kernel (24 MB at 500k Gaussians: L2 resident) and is
 // what the tile kernels gather into shared memory with 128-bit loads, driven by the TMA-staged id list:
-//   { x, y, conic.x, conic.y | conic.z, opacity, r, g | b, power cut-off, 0, 0 }
+//   { x, y, conic.x, conic.y | conic.z, opacity, r, g | b, power cut-off, box half-extent x, y }
 // power cut-off = -ln(255 * opacity) - 1e-4: below it opacity*exp(power) < 1/255 holds with a wide fp32 margin, so the
 // exponential need not be evaluated (the exact test alpha < 1/255 still decides everything above the cut-off).
+// box half-extents = bounding box of the ellipse { power >= cut-off } (+ margin): a warp skips, 32 list entries per vote,
+// every Gaussian whose box misses its 8x4 pixel block.
 #pragma once
 #include "common.cuh"
 #include "sort_scan.cuh"
@@ -24,7 +26,7 @@ enum Counter { kCntRendered = 0, kCntVisible = 1, kCntOverflow = 2, kCntTileCurs
 struct Record {   // 48 bytes, 16-B aligned
     float4 a;     // x, y, conic.x, conic.y
     float4 b;     // conic.z, opacity, r, g
-    float4 c;     // b, power cut-off, 0, 0
+    float4 c;     // b, power cut-off, box half-extent x, box half-extent y
 };
 static_assert(sizeof(Record) == 48, "record must be 48 bytes");
 

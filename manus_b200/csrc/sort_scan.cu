@@ -35,53 +35,29 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t
     }
 }
 
-// in-place exclusive scan of the dense [256 * nchunks] array, single CTA of 1024 threads
-__global__ void __launch_bounds__(1024) radix_offsets_kernel(uint32_t *__restrict__ counts, int64_t n_host,
-                                                             const uint32_t *__restrict__ n_dev, int64_t max_n) {
+// One warp per digit: in-place exclusive scan of counts[digit][0..nchunks) and the digit's total.  The prefix over the
+// 256 digit totals is taken by every scatter CTA itself (256 values, one block scan), so no single-CTA pass remains.
+__global__ void __launch_bounds__(256) radix_offsets_kernel(uint32_t *__restrict__ counts, uint32_t *__restrict__ totals,
+                                                            int64_t n_host, const uint32_t *__restrict__ n_dev, int64_t max_n) {
     const int64_t n = resolve_n(n_host, n_dev, max_n);
     const int64_t nchunks = (n + kSortChunk - 1) / kSortChunk;
-    const int64_t total = 256 * nchunks;
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    for (int64_t base = 0; base < total; base += 4096) {
-        const int64_t i0 = base + 4 * tid;
-        uint32_t v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (i0 + k < total) ? counts[i0 + k] : 0u;
-        const uint32_t mine = v[0] + v[1] + v[2] + v[3];
-        uint32_t incl = mine;
+    const int lane = threadIdx.x & 31;
+    const int digit = blockIdx.x * 8 + (threadIdx.x >> 5);
+    uint32_t *row = counts + (int64_t)digit * nchunks;
+    uint32_t carry = 0;
+    for (int64_t base = 0; base < nchunks; base += 32) {
+        const int64_t c = base + lane;
+        const uint32_t v = c < nchunks ? row[c] : 0u;
+        uint32_t incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        if (lane == 31) warp_sums[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = warp_sums[lane];
-            uint32_t wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += t;
-            }
-            warp_sums[lane] = wi - w;  // exclusive
-        }
-        __syncthreads();
-        const uint32_t carry = carry_s;
-        uint32_t run = carry + warp_sums[warp] + incl - mine;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i0 + k < total) counts[i0 + k] = run;
-            run += v[k];
-        }
-        __syncthreads();
-        if (tid == 1023) carry_s = run;  // run == carry + sum of this 4096-block
-        __syncthreads();
+        if (c < nchunks) row[c] = carry + incl - v;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
+    if (lane == 0) totals[digit] = carry;
 }
 
 __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint32_t *__restrict__ keys_in,
@@ -89,12 +65,31 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint3
                                                                      uint32_t *__restrict__ keys_out,
                                                                      uint32_t *__restrict__ vals_out, int64_t n_host,
                                                                      const uint32_t *__restrict__ n_dev, int64_t max_n,
-                                                                     int shift, const uint32_t *__restrict__ offsets) {
+                                                                     int shift, const uint32_t *__restrict__ offsets,
+                                                                     const uint32_t *__restrict__ totals) {
     const int64_t n = resolve_n(n_host, n_dev, max_n);
     const int64_t nchunks = (n + kSortChunk - 1) / kSortChunk;
     __shared__ uint32_t warp_cnt[kSortWarps][256];
+    __shared__ uint32_t digit_warp_sum[kSortWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = lanemask_lt();
+    // first global position of digit `tid` = exclusive prefix of the digit totals
+    uint32_t digit_base;
+    {
+        const uint32_t v = totals[tid];
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) digit_warp_sum[warp] = incl;
+        __syncthreads();
+        uint32_t wp = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) wp += (w < warp) ? digit_warp_sum[w] : 0u;
+        digit_base = wp + incl - v;
+    }
     for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w) warp_cnt[w][tid] = 0;
@@ -121,7 +116,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint3
         }
         __syncthreads();
         {   // thread `tid` owns digit `tid`: exclusive prefix over warps + global base of (digit, chunk)
-            uint32_t run = offsets[(int64_t)tid * nchunks + chunk];
+            uint32_t run = digit_base + offsets[(int64_t)tid * nchunks + chunk];
 #pragma unroll
             for (int w = 0; w < kSortWarps; ++w) {
                 const uint32_t t = warp_cnt[w][tid];
@@ -183,12 +178,12 @@ int radix_sort_pairs(uint32_t *keys_in, uint32_t *vals_in, uint32_t *keys_out, u
         }
         {
             KernelTimer kt("radix_offsets", stream);
-            radix_offsets_kernel<<<1, 1024, 0, stream>>>(ws.counts, n_host, n_dev, max_n);
+            radix_offsets_kernel<<<32, 256, 0, stream>>>(ws.counts, ws.totals, n_host, n_dev, max_n);
         }
         {
             KernelTimer kt("radix_scatter", stream);
             radix_scatter_kernel<<<grid, kSortThreads, 0, stream>>>(src_k, src_v, dst_k, dst_v, n_host, n_dev, max_n, shift,
-                                                                   ws.counts);
+                                                                   ws.counts, ws.totals);
         }
         int rc = check_launch("radix pass", debug, stream);
         if (rc) return rc;

@@ -3,7 +3,7 @@
 //
 // One pass over an 8-bit digit is three launches:
 //   radix_hist    : per-chunk digit histogram  -> counts[digit][chunk]           (chunk = 4096 consecutive elements)
-//   radix_offsets : exclusive scan of counts in (digit, chunk) order, in place   (single CTA)
+//   radix_offsets : per digit, exclusive scan of counts over the chunks, in place, + digit totals (one warp per digit)
 //   radix_scatter : stable rank inside the chunk (warp match + per-warp counters) and scatter
 // Everything the sorts of one frame touch is L2-resident on B200 (126 MB), so the passes are L2-bound, not HBM-bound.
 #pragma once
@@ -20,13 +20,14 @@ inline int64_t sort_chunks(int64_t n) { return (n + kSortChunk - 1) / kSortChunk
 
 struct SortWorkspace {
     uint32_t *counts;   // [256][max_chunks]
+    uint32_t *totals;   // [256] keys per digit of the current pass
     uint32_t *keys_tmp, *vals_tmp;
     int64_t max_chunks;
 };
 
 inline size_t sort_workspace_bytes(int64_t max_n) {
     int64_t ch = sort_chunks(max_n) + 1;
-    return align_up(256 * ch * sizeof(uint32_t)) + 2 * align_up((size_t)(max_n + 1) * sizeof(uint32_t));
+    return align_up(256 * ch * sizeof(uint32_t)) + align_up(256 * sizeof(uint32_t)) + 2 * align_up((size_t)(max_n + 1) * sizeof(uint32_t));
 }
 
 inline SortWorkspace carve_sort_workspace(void *p, int64_t max_n) {
@@ -34,6 +35,7 @@ inline SortWorkspace carve_sort_workspace(void *p, int64_t max_n) {
     SortWorkspace w;
     w.max_chunks = sort_chunks(max_n) + 1;
     w.counts = c.take<uint32_t>(256 * w.max_chunks);
+    w.totals = c.take<uint32_t>(256);
     w.keys_tmp = c.take<uint32_t>(max_n + 1);
     w.vals_tmp = c.take<uint32_t>(max_n + 1);
     return w;

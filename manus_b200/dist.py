@@ -144,6 +144,8 @@ class SceneRenderer:
         self.n_hand = scene.n_hand
         self.skin = None if scene.skin_wts is None else torch.as_tensor(scene.skin_wts).to(device)
         self.bones_rest = None if scene.bones_rest is None else torch.as_tensor(scene.bones_rest).to(device)
+        self.rest_inv = None if self.bones_rest is None else torch.linalg.inv(self.bones_rest)   # constant per scene
+        self._eye = torch.eye(4, dtype=torch.float32, device=device)[None]
         self.bg = torch.tensor(bg, dtype=torch.float32, device=device)
         self._synth = synth
         self._cams = {}
@@ -172,6 +174,6 @@ class SceneRenderer:
         dcam = Camera(cam.width, cam.height, cam.fovx, cam.fovy, cam_dev[0:16].view(4, 4), cam_dev[16:32].view(4, 4), cam_dev[32:35], None)
         bone_tf = None
         if self.n_hand > 0:
-            bone_tf = bone_transforms(bones_dev.view(-1, 4, 4), self.bones_rest, True)
+            bone_tf = torch.cat([torch.bmm(bones_dev.view(-1, 4, 4), self.rest_inv), self._eye], dim=0)   # = bone_transforms(...)
         return render_fused(self.flat.leaves(), self.skin, bone_tf, dcam, self.bg, self.sh_degree, self.flat.isotropic,
                             self.n_hand, grad_sink=sink)

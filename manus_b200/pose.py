@@ -19,9 +19,14 @@ from . import _lib
 from ._lib import ptr
 
 
-def bone_transforms(bones_posed: torch.Tensor, bones_rest: torch.Tensor, append_identity: bool = True) -> torch.Tensor:
-    """T_b = posed_b . inv(rest_b) (+ identity background bone): hand_dynamic.py:93-102.  20 tiny matrices: plumbing."""
-    tfs = torch.einsum("nij,njk->nik", bones_posed, torch.linalg.inv(bones_rest))
+def bone_transforms(bones_posed: torch.Tensor, bones_rest: torch.Tensor, append_identity: bool = True,
+                    rest_inv: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """T_b = posed_b . inv(rest_b) (+ identity background bone): hand_dynamic.py:93-102.  20 tiny matrices: plumbing.
+    The rest pose is constant for a scene, so callers that render many frames pass ``rest_inv = torch.linalg.inv(bones_rest)``
+    computed once (same values; saves the batched LU kernels of every frame)."""
+    if rest_inv is None:
+        rest_inv = torch.linalg.inv(bones_rest)
+    tfs = torch.einsum("nij,njk->nik", bones_posed, rest_inv)
     if append_identity:
         tfs = torch.cat([tfs, torch.eye(4, dtype=tfs.dtype, device=tfs.device)[None]], dim=0)
     return tfs
