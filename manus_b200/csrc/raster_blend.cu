@@ -523,7 +523,7 @@ static int blend_warps() {
     static int cached = 0;
     if (!cached) {
         const char *e = getenv("MB_BLEND_WARPS");
-        cached = (e && atoi(e) == 4) ? 4 : 8;
+        cached = (e && atoi(e) == 8) ? 8 : 4;
     }
     return cached;
 }

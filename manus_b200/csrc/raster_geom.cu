@@ -171,13 +171,18 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
 
 // Instance emission, warp-cooperative: a warp owns 32 consecutive depth-sorted Gaussians; their (tile id, gaussian id)
 // runs are contiguous in the instance list, so the lanes walk the warp's slots in order (coalesced 128-B stores) and
-// find the owning Gaussian of each slot by a shuffle binary search over the warp's inclusive tile counts.
+// find the owning Gaussian of each slot by a shuffle binary search over the warp's inclusive tile counts.  The few
+// Gaussians that cover more than kBigTiles tiles (up to the whole screen) are queued and written by whole CTAs in
+// emit_big_kernel, so that no warp is left with thousands of slots.
+constexpr uint32_t kBigTiles = 64;
+
 __global__ void __launch_bounds__(256) emit_instances_kernel(int P, int gx, const uint32_t *__restrict__ sorted_idx,
                                                              const uint32_t *__restrict__ offsets,
                                                              const uint32_t *__restrict__ tiles_touched,
                                                              const ushort4 *__restrict__ rect,
                                                              uint32_t *__restrict__ counters, int64_t capacity,
-                                                             uint32_t *__restrict__ tile_out, uint32_t *__restrict__ gid_out) {
+                                                             uint32_t *__restrict__ tile_out, uint32_t *__restrict__ gid_out,
+                                                             uint32_t *__restrict__ big_list) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && (int64_t)counters[kCntRendered] > capacity) counters[kCntOverflow] = 1;
     const int lane = threadIdx.x & 31;
     const int warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -190,6 +195,10 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, int gx, cons
             cnt = tiles_touched[g];
             off = offsets[i];
             if (cnt) r = rect[g];
+            if (cnt > kBigTiles) {
+                big_list[atomicAdd(&counters[kCntBig], 1u)] = (uint32_t)i;
+                cnt = 0;
+            }
         }
         uint32_t incl = cnt;
 #pragma unroll
@@ -198,7 +207,6 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, int gx, cons
             if (lane >= o) incl += t;
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        const int64_t base = (int64_t)__shfl_sync(0xffffffffu, off, 0);
         const uint32_t width = (uint32_t)(r.z - r.x);
         for (uint32_t s0 = 0; s0 < total; s0 += 32) {
             const uint32_t sl = s0 + lane;
@@ -212,12 +220,37 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, int gx, cons
             const uint32_t o_incl = __shfl_sync(0xffffffffu, incl, lo), o_cnt = __shfl_sync(0xffffffffu, cnt, lo);
             const uint32_t o_g = __shfl_sync(0xffffffffu, g, lo), o_w = __shfl_sync(0xffffffffu, width, lo);
             const uint32_t o_x0 = __shfl_sync(0xffffffffu, (uint32_t)r.x, lo), o_y0 = __shfl_sync(0xffffffffu, (uint32_t)r.y, lo);
-            const int64_t pos = base + sl;
+            const uint32_t o_off = __shfl_sync(0xffffffffu, off, lo);
+            const uint32_t local = sl - (o_incl - o_cnt);
+            const int64_t pos = (int64_t)o_off + local;
             if (sl < total && pos < capacity) {
-                const uint32_t local = sl - (o_incl - o_cnt);
                 const uint32_t ty = local / o_w, tx = local - ty * o_w;
                 tile_out[pos] = (o_y0 + ty) * (uint32_t)gx + o_x0 + tx;
                 gid_out[pos] = o_g;
+            }
+        }
+    }
+}
+
+// one CTA per queued big Gaussian (grid-stride)
+__global__ void __launch_bounds__(256) emit_big_kernel(int gx, const uint32_t *__restrict__ sorted_idx,
+                                                       const uint32_t *__restrict__ offsets,
+                                                       const uint32_t *__restrict__ tiles_touched,
+                                                       const ushort4 *__restrict__ rect, const uint32_t *__restrict__ counters,
+                                                       int64_t capacity, const uint32_t *__restrict__ big_list,
+                                                       uint32_t *__restrict__ tile_out, uint32_t *__restrict__ gid_out) {
+    const uint32_t nbig = counters[kCntBig];
+    for (uint32_t e = blockIdx.x; e < nbig; e += gridDim.x) {
+        const uint32_t i = big_list[e], g = sorted_idx[i], cnt = tiles_touched[g];
+        const ushort4 r = rect[g];
+        const uint32_t w = (uint32_t)(r.z - r.x);
+        const int64_t off = offsets[i];
+        for (uint32_t local = threadIdx.x; local < cnt; local += blockDim.x) {
+            const int64_t pos = off + local;
+            if (pos < capacity) {
+                const uint32_t ty = local / w, tx = local - ty * w;
+                tile_out[pos] = ((uint32_t)r.y + ty) * (uint32_t)gx + (uint32_t)r.x + tx;
+                gid_out[pos] = g;
             }
         }
     }
@@ -307,9 +340,16 @@ int build_instances(const mb_raster_inputs *in, const RasterDims &d, const GeomS
     {
     KernelTimer kt("emit_instances", s);
     emit_instances_kernel<<<grid_p, 256, 0, s>>>(d.P, d.gx, g.sorted_idx, g.offsets, g.tiles_touched, g.rect, g.counters,
-                                                 capacity, b.tile_a, b.gid_a);
+                                                 capacity, b.tile_a, b.gid_a, g.big_list);
     }
     int rc = check_launch("emit_instances", dbg, s);
+    if (rc) return rc;
+    {
+    KernelTimer kt("emit_big", s);
+    emit_big_kernel<<<sm_count() * 2, 256, 0, s>>>(d.gx, g.sorted_idx, g.offsets, g.tiles_touched, g.rect, g.counters, capacity,
+                                                  g.big_list, b.tile_a, b.gid_a);
+    }
+    rc = check_launch("emit_big", dbg, s);
     if (rc) return rc;
     SortWorkspace ws = carve_sort_workspace(b.sort_ws, capacity > 0 ? capacity : 1);
     rc = radix_sort_pairs(b.tile_a, b.gid_a, b.tile_b, b.gid_b, -1, g.counters + kCntRendered, capacity, 0, tile_bits(d.tiles),

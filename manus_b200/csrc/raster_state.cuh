@@ -21,7 +21,7 @@
 
 namespace mb {
 
-enum Counter { kCntRendered = 0, kCntVisible = 1, kCntOverflow = 2, kCntTileCursor = 3, kCntBwdCursor = 4, kNumCounters = 16 };
+enum Counter { kCntRendered = 0, kCntVisible = 1, kCntOverflow = 2, kCntTileCursor = 3, kCntBwdCursor = 4, kCntBig = 5, kNumCounters = 16 };
 
 struct Record {   // 48 bytes, 16-B aligned
     float4 a;     // x, y, conic.x, conic.y
@@ -38,6 +38,7 @@ struct GeomState {
     ushort4 *rect;     // tile rectangle (x0, y0, x1, y1), exclusive upper bounds
     uint32_t *clamped;
     uint32_t *depth_key, *ident, *sorted_key, *sorted_idx, *offsets, *scan_partials;
+    uint32_t *big_list;   // depth-order indices of the Gaussians that cover more than kBigTiles tiles
     void *sort_ws;
     size_t bytes;
 
@@ -57,6 +58,7 @@ struct GeomState {
         g.sorted_idx = c.take<uint32_t>(n);
         g.offsets = c.take<uint32_t>(n);
         g.scan_partials = c.take<uint32_t>((size_t)scan_blocks((int64_t)n) + 1);
+        g.big_list = c.take<uint32_t>(n);
         g.sort_ws = c.take<char>(sort_workspace_bytes((int64_t)n));
         g.bytes = c.off;
         return g;

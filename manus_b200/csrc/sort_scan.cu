@@ -9,133 +9,139 @@ __device__ __forceinline__ int64_t resolve_n(int64_t n_host, const uint32_t *n_d
     return n < max_n ? n : max_n;
 }
 
-// counts[digit * nchunks + chunk] = number of keys of `chunk` whose digit is `digit`
+// hist[pass][digit] += number of keys whose digit of that pass is `digit`; one read of the keys for all passes
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t n_host,
                                                                   const uint32_t *__restrict__ n_dev, int64_t max_n,
-                                                                  int shift, uint32_t *__restrict__ counts) {
+                                                                  int begin_bit, int passes, uint32_t *__restrict__ hist) {
     const int64_t n = resolve_n(n_host, n_dev, max_n);
-    const int64_t nchunks = (n + kSortChunk - 1) / kSortChunk;
-    __shared__ uint32_t hist[256];
-    const int tid = threadIdx.x, lane = tid & 31;
-    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-        hist[tid] = 0;
-        __syncthreads();
-        const int64_t base = chunk * kSortChunk;
-#pragma unroll 4
-        for (int r = 0; r < kSortItems; ++r) {
-            const int64_t idx = base + r * kSortThreads + tid;
-            const bool valid = idx < n;
-            const uint32_t digit = valid ? ((keys[idx] >> shift) & 255u) : 256u;
-            const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-            if (valid && (__ffs(peers) - 1) == lane) atomicAdd(&hist[digit], __popc(peers));
-        }
-        __syncthreads();
-        counts[(int64_t)tid * nchunks + chunk] = hist[tid];
-        __syncthreads();
-    }
-}
-
-// One warp per digit: in-place exclusive scan of counts[digit][0..nchunks) and the digit's total.  The prefix over the
-// 256 digit totals is taken by every scatter CTA itself (256 values, one block scan), so no single-CTA pass remains.
-__global__ void __launch_bounds__(256) radix_offsets_kernel(uint32_t *__restrict__ counts, uint32_t *__restrict__ totals,
-                                                            int64_t n_host, const uint32_t *__restrict__ n_dev, int64_t max_n) {
-    const int64_t n = resolve_n(n_host, n_dev, max_n);
-    const int64_t nchunks = (n + kSortChunk - 1) / kSortChunk;
-    const int lane = threadIdx.x & 31;
-    const int digit = blockIdx.x * 8 + (threadIdx.x >> 5);
-    uint32_t *row = counts + (int64_t)digit * nchunks;
-    uint32_t carry = 0;
-    for (int64_t base = 0; base < nchunks; base += 32) {
-        const int64_t c = base + lane;
-        const uint32_t v = c < nchunks ? row[c] : 0u;
-        uint32_t incl = v;
+    __shared__ uint32_t h[kSortMaxPasses][256];
+    const int tid = threadIdx.x;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+    for (int p = 0; p < kSortMaxPasses; ++p) h[p][tid] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * kSortThreads * 4;
+    const bool vec = (reinterpret_cast<uintptr_t>(keys) & 15u) == 0;
+    for (int64_t i = ((int64_t)blockIdx.x * kSortThreads + tid) * 4; i < n; i += stride) {
+        uint32_t k[4];
+        int cnt = 4;
+        if (vec && i + 4 <= n) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(keys + i);
+            k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+        } else {
+            cnt = (int)(n - i < 4 ? n - i : 4);
+            for (int e = 0; e < cnt; ++e) k[e] = keys[i + e];
         }
-        if (c < nchunks) row[c] = carry + incl - v;
-        carry += __shfl_sync(0xffffffffu, incl, 31);
+        for (int p = 0; p < passes; ++p) {
+            const int shift = begin_bit + 8 * p;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (e < cnt) atomicAdd(&h[p][(k[e] >> shift) & 255u], 1u);
+        }
     }
-    if (lane == 0) totals[digit] = carry;
+    __syncthreads();
+    for (int p = 0; p < passes; ++p)
+        if (h[p][tid]) atomicAdd(&hist[p * 256 + tid], h[p][tid]);
 }
 
-__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(const uint32_t *__restrict__ keys_in,
-                                                                     const uint32_t *__restrict__ vals_in,
-                                                                     uint32_t *__restrict__ keys_out,
-                                                                     uint32_t *__restrict__ vals_out, int64_t n_host,
-                                                                     const uint32_t *__restrict__ n_dev, int64_t max_n,
-                                                                     int shift, const uint32_t *__restrict__ offsets,
-                                                                     const uint32_t *__restrict__ totals) {
+constexpr uint32_t kFlagAggregate = 1u << 30, kFlagPrefix = 2u << 30, kCountMask = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(kSortThreads) radix_pass_kernel(const uint32_t *__restrict__ keys_in,
+                                                                  const uint32_t *__restrict__ vals_in,
+                                                                  uint32_t *__restrict__ keys_out,
+                                                                  uint32_t *__restrict__ vals_out, int64_t n_host,
+                                                                  const uint32_t *__restrict__ n_dev, int64_t max_n,
+                                                                  int shift, const uint32_t *__restrict__ hist,
+                                                                  volatile uint32_t *status, uint32_t *cursor) {
     const int64_t n = resolve_n(n_host, n_dev, max_n);
     const int64_t nchunks = (n + kSortChunk - 1) / kSortChunk;
     __shared__ uint32_t warp_cnt[kSortWarps][256];
-    __shared__ uint32_t digit_warp_sum[kSortWarps];
+    __shared__ uint32_t base_s[256];
+    __shared__ uint32_t scan_s[kSortWarps];
+    __shared__ uint32_t chunk_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = lanemask_lt();
-    // first global position of digit `tid` = exclusive prefix of the digit totals
+    if (tid == 0) chunk_s = atomicAdd(cursor, 1u);
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) warp_cnt[w][tid] = 0;
+    __syncthreads();
+    const int64_t chunk = chunk_s;
+    if (chunk >= nchunks) return;
+    // stable rank of every key among the keys of its warp's 512-element slice with the same digit
+    const int64_t base = chunk * kSortChunk + (int64_t)warp * (32 * kSortItems);
+    uint32_t key[kSortItems], rank[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const int64_t idx = base + r * 32 + lane;
+        key[r] = idx < n ? keys_in[idx] : 0xffffffffu;
+    }
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const int64_t idx = base + r * 32 + lane;
+        const bool valid = idx < n;
+        const uint32_t digit = valid ? ((key[r] >> shift) & 255u) : 256u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) {
+            old = warp_cnt[warp][digit];
+            warp_cnt[warp][digit] = old + __popc(peers);
+        }
+        __syncwarp();
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[r] = old + __popc(peers & lt);
+    }
+    __syncthreads();
+    // thread `tid` owns digit `tid`
+    uint32_t mine = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+        const uint32_t t = warp_cnt[w][tid];
+        warp_cnt[w][tid] = mine;     // exclusive prefix over the warps of this chunk
+        mine += t;
+    }
+    status[chunk * 256 + tid] = (chunk == 0 ? kFlagPrefix : kFlagAggregate) | mine;
+    // first global position of the digit = exclusive prefix of the digit histogram (block scan of 256 values)
     uint32_t digit_base;
     {
-        const uint32_t v = totals[tid];
+        const uint32_t v = hist[tid];
         uint32_t incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
         }
-        if (lane == 31) digit_warp_sum[warp] = incl;
+        if (lane == 31) scan_s[warp] = incl;
         __syncthreads();
         uint32_t wp = 0;
 #pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) wp += (w < warp) ? digit_warp_sum[w] : 0u;
+        for (int w = 0; w < kSortWarps; ++w) wp += (w < warp) ? scan_s[w] : 0u;
         digit_base = wp + incl - v;
     }
-    for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-#pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) warp_cnt[w][tid] = 0;
-        __syncthreads();
-        const int64_t base = chunk * kSortChunk + (int64_t)warp * (32 * kSortItems);
-        uint32_t key[kSortItems];
-        uint32_t rank[kSortItems];
-#pragma unroll
-        for (int r = 0; r < kSortItems; ++r) {
-            const int64_t idx = base + r * 32 + lane;
-            const bool valid = idx < n;
-            key[r] = valid ? keys_in[idx] : 0xffffffffu;
-            const uint32_t digit = valid ? ((key[r] >> shift) & 255u) : 256u;
-            const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-            const int leader = __ffs(peers) - 1;
-            uint32_t old = 0;
-            if (valid && lane == leader) {
-                old = warp_cnt[warp][digit];
-                warp_cnt[warp][digit] = old + __popc(peers);
-            }
-            __syncwarp();
-            old = __shfl_sync(0xffffffffu, old, leader);
-            rank[r] = old + __popc(peers & lt);
+    // decoupled look-back: keys with this digit in all earlier chunks
+    uint32_t before = 0;
+    if (chunk > 0) {
+        int64_t p = chunk - 1;
+        while (true) {
+            const uint32_t v = status[p * 256 + tid];
+            const uint32_t f = v & ~kCountMask;
+            if (f == 0) continue;   // predecessor has not published yet (it is running: chunk ids are handed out in start order)
+            before += v & kCountMask;
+            if (f == kFlagPrefix) break;
+            --p;
         }
-        __syncthreads();
-        {   // thread `tid` owns digit `tid`: exclusive prefix over warps + global base of (digit, chunk)
-            uint32_t run = digit_base + offsets[(int64_t)tid * nchunks + chunk];
+        status[chunk * 256 + tid] = kFlagPrefix | (before + mine);
+    }
+    base_s[tid] = digit_base + before;
+    __syncthreads();
 #pragma unroll
-            for (int w = 0; w < kSortWarps; ++w) {
-                const uint32_t t = warp_cnt[w][tid];
-                warp_cnt[w][tid] = run;
-                run += t;
-            }
+    for (int r = 0; r < kSortItems; ++r) {
+        const int64_t idx = base + r * 32 + lane;
+        if (idx < n) {
+            const uint32_t digit = (key[r] >> shift) & 255u;
+            const uint32_t pos = base_s[digit] + warp_cnt[warp][digit] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = vals_in[idx];
         }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < kSortItems; ++r) {
-            const int64_t idx = base + r * 32 + lane;
-            if (idx < n) {
-                const uint32_t digit = (key[r] >> shift) & 255u;
-                const uint32_t pos = warp_cnt[warp][digit] + rank[r];
-                keys_out[pos] = key[r];
-                vals_out[pos] = vals_in[idx];
-            }
-        }
-        __syncthreads();
     }
 }
 
@@ -155,37 +161,39 @@ int radix_sort_pairs(uint32_t *keys_in, uint32_t *vals_in, uint32_t *keys_out, u
     const int64_t bound = n_host >= 0 ? n_host : max_n;
     if (bound <= 0) return MB_OK;
     const int passes = (end_bit - begin_bit + 7) / 8;
-    int64_t chunks = sort_chunks(bound);
-    if (chunks > ws.max_chunks) {
-        set_error("radix_sort_pairs: workspace too small (%lld chunks > %lld)", (long long)chunks, (long long)ws.max_chunks);
+    const int64_t chunks = sort_chunks(bound);
+    if (chunks > ws.max_chunks || passes > kSortMaxPasses) {
+        set_error("radix_sort_pairs: workspace too small (%lld chunks > %lld) or too many passes (%d)", (long long)chunks,
+                  (long long)ws.max_chunks, passes);
         return MB_ERR_WORKSPACE;
     }
-    const int grid = (int)(chunks < (int64_t)sm_count() * 8 ? chunks : (int64_t)sm_count() * 8);
     if (passes == 0) {
+        const int grid = (int)(chunks < (int64_t)sm_count() * 8 ? chunks : (int64_t)sm_count() * 8);
         copy_pairs_kernel<<<grid, 256, 0, stream>>>(keys_in, vals_in, keys_out, vals_out, n_host, n_dev, max_n);
         return check_launch("copy_pairs", debug, stream);
     }
+    MB_CUDA(cudaMemsetAsync(ws.zeroed, 0, ws.zeroed_bytes, stream));
+    {
+        KernelTimer kt("radix_hist", stream);
+        const int64_t want = (bound + kSortThreads * 16 - 1) / (kSortThreads * 16);
+        const int grid = (int)(want < (int64_t)sm_count() * 4 ? want : (int64_t)sm_count() * 4);
+        radix_hist_kernel<<<grid, kSortThreads, 0, stream>>>(keys_in, n_host, n_dev, max_n, begin_bit, passes, ws.hist);
+    }
+    int rc = check_launch("radix_hist", debug, stream);
+    if (rc) return rc;
     // ping-pong so that the last pass lands in keys_out / vals_out
     uint32_t *src_k = keys_in, *src_v = vals_in;
     for (int p = 0; p < passes; ++p) {
         const bool to_out = ((passes - 1 - p) % 2) == 0;
         uint32_t *dst_k = to_out ? keys_out : ws.keys_tmp;
         uint32_t *dst_v = to_out ? vals_out : ws.vals_tmp;
-        const int shift = begin_bit + 8 * p;
         {
-            KernelTimer kt("radix_hist", stream);
-            radix_hist_kernel<<<grid, kSortThreads, 0, stream>>>(src_k, n_host, n_dev, max_n, shift, ws.counts);
+            KernelTimer kt("radix_pass", stream);
+            radix_pass_kernel<<<(int)chunks, kSortThreads, 0, stream>>>(src_k, src_v, dst_k, dst_v, n_host, n_dev, max_n,
+                                                                      begin_bit + 8 * p, ws.hist + p * 256,
+                                                                      ws.status + (size_t)p * ws.max_chunks * 256, ws.cursor + p);
         }
-        {
-            KernelTimer kt("radix_offsets", stream);
-            radix_offsets_kernel<<<32, 256, 0, stream>>>(ws.counts, ws.totals, n_host, n_dev, max_n);
-        }
-        {
-            KernelTimer kt("radix_scatter", stream);
-            radix_scatter_kernel<<<grid, kSortThreads, 0, stream>>>(src_k, src_v, dst_k, dst_v, n_host, n_dev, max_n, shift,
-                                                                   ws.counts, ws.totals);
-        }
-        int rc = check_launch("radix pass", debug, stream);
+        rc = check_launch("radix pass", debug, stream);
         if (rc) return rc;
         src_k = dst_k;
         src_v = dst_v;

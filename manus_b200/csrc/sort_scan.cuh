@@ -1,11 +1,12 @@
 // Stable LSD radix sort of (u32 key, u32 value) pairs and an exclusive scan, with the element count optionally
 // read from device memory so that the whole frame can be enqueued without a host round trip.
 //
-// One pass over an 8-bit digit is three launches:
-//   radix_hist    : per-chunk digit histogram  -> counts[digit][chunk]           (chunk = 4096 consecutive elements)
-//   radix_offsets : per digit, exclusive scan of counts over the chunks, in place, + digit totals (one warp per digit)
-//   radix_scatter : stable rank inside the chunk (warp match + per-warp counters) and scatter
-// Everything the sorts of one frame touch is L2-resident on B200 (126 MB), so the passes are L2-bound, not HBM-bound.
+// Onesweep scheme: ONE histogram kernel reads the keys once and counts the 8-bit digits of every pass (digit counts do
+// not depend on the order of the keys), then each pass is a single kernel: a CTA takes the next chunk of 4096 keys
+// (dynamic chunk id, so that every predecessor is already running), ranks its keys stably (warp match + per-warp
+// counters), publishes its per-digit counts, obtains the counts of all earlier chunks by decoupled look-back over
+// [chunk][digit] status words (2 flag bits + 30-bit count) and scatters.  A sort of k passes is k + 2 launches
+// (memset, histogram, k passes).  Everything the sorts of one frame touch is L2-resident on B200 (126 MB).
 #pragma once
 #include "common.cuh"
 
@@ -15,27 +16,35 @@ constexpr int kSortThreads = 256;
 constexpr int kSortItems = 16;                           // per thread
 constexpr int kSortChunk = kSortThreads * kSortItems;    // 4096
 constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortMaxPasses = 4;
 
 inline int64_t sort_chunks(int64_t n) { return (n + kSortChunk - 1) / kSortChunk; }
 
 struct SortWorkspace {
-    uint32_t *counts;   // [256][max_chunks]
-    uint32_t *totals;   // [256] keys per digit of the current pass
+    uint32_t *zeroed;        // start of the region cleared by one memset per sort: hist | cursors | status
+    size_t zeroed_bytes;
+    uint32_t *hist;          // [kSortMaxPasses][256] digit counts of each pass
+    uint32_t *cursor;        // [kSortMaxPasses] next chunk id of each pass
+    uint32_t *status;        // [kSortMaxPasses][max_chunks][256] look-back words
     uint32_t *keys_tmp, *vals_tmp;
     int64_t max_chunks;
 };
 
 inline size_t sort_workspace_bytes(int64_t max_n) {
-    int64_t ch = sort_chunks(max_n) + 1;
-    return align_up(256 * ch * sizeof(uint32_t)) + align_up(256 * sizeof(uint32_t)) + 2 * align_up((size_t)(max_n + 1) * sizeof(uint32_t));
+    const int64_t ch = sort_chunks(max_n) + 1;
+    return align_up(kSortMaxPasses * 256 * sizeof(uint32_t)) + align_up(64 * sizeof(uint32_t)) +
+           align_up((size_t)kSortMaxPasses * ch * 256 * sizeof(uint32_t)) + 2 * align_up((size_t)(max_n + 1) * sizeof(uint32_t));
 }
 
 inline SortWorkspace carve_sort_workspace(void *p, int64_t max_n) {
     Carver c(p);
     SortWorkspace w;
     w.max_chunks = sort_chunks(max_n) + 1;
-    w.counts = c.take<uint32_t>(256 * w.max_chunks);
-    w.totals = c.take<uint32_t>(256);
+    w.hist = c.take<uint32_t>(kSortMaxPasses * 256);
+    w.cursor = c.take<uint32_t>(64);
+    w.status = c.take<uint32_t>((size_t)kSortMaxPasses * w.max_chunks * 256);
+    w.zeroed = w.hist;
+    w.zeroed_bytes = (size_t)((char *)(w.status + (size_t)kSortMaxPasses * w.max_chunks * 256) - (char *)w.hist);
     w.keys_tmp = c.take<uint32_t>(max_n + 1);
     w.vals_tmp = c.take<uint32_t>(max_n + 1);
     return w;
