@@ -4,9 +4,13 @@
 // Replaces ~100 small PyTorch kernels per frame of the reference (src/modules/hand_dynamic.py:86-137,
 // src/models/gaussian.py:48-93, src/utils/gaussian_utils.py:248-314,431-449, src/utils/sh_utils.py:57-120): the per-Gaussian
 // 4x4 transform is never written to HBM and its inverse (torch.linalg.inv on N 4x4 matrices in the reference) is the
-// closed-form affine inverse.  One thread per Gaussian, 128 Gaussians per CTA; the wide rows (SH coefficients, skin
-// weights) move through shared memory so that every HBM access is a coalesced run; strides are padded to odd word
-// counts so the per-thread row reads are bank-conflict free.
+// closed-form affine inverse.
+//
+// Persistent CTAs walk tiles of 128 Gaussians (one thread per Gaussian).  Every per-Gaussian array of a tile is one
+// dense run in HBM (f_rest 23 KB, skin weights 10.5 KB, xyz / scales / quaternions / ... 0.5-2 KB), so a tile is fetched by
+// a handful of 1-D bulk TMA copies (cp.async.bulk + mbarrier) into the shared-memory stage that is not being computed
+// on, results are written over the thread's own input rows and leave the same way (cp.async.bulk shared -> global).
+// Two stages per CTA and two CTAs per SM keep ~80 KB of loads in flight per SM while the ALUs work on the other stage.
 //
 // HBM bytes per Gaussian (fp32, K=16, B bones): forward 236 + 4B read, 52 written; backward re-reads the parameters
 // and the 52 B of upstream gradients and writes 236 B of parameter gradients.
@@ -14,8 +18,9 @@
 
 namespace mb {
 
-constexpr int kPoseThreads = 128;
+constexpr int kPoseThreads = 128;   // Gaussians per tile = threads per CTA
 constexpr int kMaxBones = 64;
+constexpr int kMaxArrays = 12;
 
 struct PoseArgs {
     int N, n_skinned, B, deg, K, iso;
@@ -27,29 +32,57 @@ struct PoseArgs {
     float *g_xyz, *g_log_scale, *g_quat, *g_opacity_logit, *g_f_dc, *g_f_rest, *g_skin;
 };
 
-__host__ __device__ inline int odd_stride(int n) { return n | 1; }
+// Shared-memory image of one tile of kPoseThreads Gaussians (offsets in floats, every array 16-B aligned).  Rows are
+// dense: the wide rows have odd word counts in the shipped configurations (45 = 15 SH coefficients x 3, 21 bones), so
+// the per-thread row reads are bank-conflict free without padding.
+struct TileLayout {
+    int fr, sk, xyz, ls, quat, opac, fdc, cov, gpx, gcov, gcol, gop, floats;
+};
 
-inline size_t pose_smem_bytes(int B, int K) {
-    const int rs = (K - 1) * 3;
-    return sizeof(float) * ((size_t)B * 13 + 4 + (size_t)kPoseThreads * (rs > 0 ? odd_stride(rs) : 0) +
-                            (size_t)kPoseThreads * (B > 0 ? odd_stride(B) : 0));
+__host__ __device__ inline TileLayout tile_layout(int K, int B, int iso, bool backward) {
+    TileLayout L;
+    const int T = kPoseThreads;
+    int o = 0;
+    L.fr = o; o += T * (K - 1) * 3;
+    L.sk = o; o += T * B;
+    L.xyz = o; o += T * 3;
+    L.ls = o; o += T * (iso ? 1 : 3);
+    L.quat = o; o += T * 4;
+    L.opac = o; o += T;
+    L.fdc = o; o += T * 3;
+    L.cov = o; o += backward ? 0 : T * 6;
+    L.gpx = o; o += backward ? T * 3 : 0;
+    L.gcov = o; o += backward ? T * 6 : 0;
+    L.gcol = o; o += backward ? T * 3 : 0;
+    L.gop = o; o += backward ? T : 0;
+    L.floats = o;
+    return L;
 }
 
-// coalesced copy of `rows` rows of `width` floats (dense in global memory) into padded shared rows
-__device__ __forceinline__ void stage_rows_in(float *dst, int dst_stride, const float *__restrict__ src, int rows, int width) {
-    const int total = rows * width;
-    for (int j = threadIdx.x; j < total; j += kPoseThreads) {
-        const int r = j / width, c = j - r * width;
-        dst[r * dst_stride + c] = src[j];
-    }
+inline size_t pose_smem_bytes(int B, int K, int iso, bool backward) {
+    // bones (13 floats each) + camera + 2 mbarriers, then two tile stages
+    return sizeof(float) * ((size_t)kMaxBones * 13 + 8) + 2 * sizeof(float) * (size_t)tile_layout(K, B, iso, backward).floats;
 }
-__device__ __forceinline__ void stage_rows_out(float *__restrict__ dst, const float *src, int src_stride, int rows, int width) {
-    const int total = rows * width;
-    for (int j = threadIdx.x; j < total; j += kPoseThreads) {
-        const int r = j / width, c = j - r * width;
-        dst[j] = src[r * src_stride + c];
-    }
+
+struct Transfer {   // one dense array of a tile: global <-> shared
+    const float *g;
+    int s;          // offset in the stage (floats)
+    uint32_t bytes;
+};
+
+__device__ __forceinline__ bool bulk_ok(const Transfer &t) {
+    return t.bytes && ((reinterpret_cast<uintptr_t>(t.g) | t.bytes) & 15u) == 0;
 }
+
+// 1-D bulk asynchronous copy shared -> global (TMA engine); completion tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct PoseLocal {
     float A[9], t[3], s;     // blended transform (identity for static Gaussians)
@@ -76,17 +109,18 @@ __device__ __forceinline__ float mat3_inverse(const float *a, float *inv) {
     return det;
 }
 
-// everything both directions need: blended transform, rotation, scales
-__device__ __forceinline__ void pose_common(const PoseArgs &a, int i, int row, const float *bones_s, const float *w_s, int ws,
-                                            PoseLocal &p) {
-    p.x[0] = a.xyz[3 * (size_t)i]; p.x[1] = a.xyz[3 * (size_t)i + 1]; p.x[2] = a.xyz[3 * (size_t)i + 2];
+// everything both directions need: blended transform, rotation, scales.  `st` = the tile's stage, `row` = thread's row.
+__device__ __forceinline__ void pose_common(const PoseArgs &a, const TileLayout &L, const float *st, int i, int row,
+                                            const float *bones_s, PoseLocal &p) {
+    p.x[0] = st[L.xyz + 3 * row]; p.x[1] = st[L.xyz + 3 * row + 1]; p.x[2] = st[L.xyz + 3 * row + 2];
     p.skinned = i < a.n_skinned;
     if (p.skinned) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) p.A[k] = 0.f;
         p.t[0] = p.t[1] = p.t[2] = 0.f; p.s = 0.f;
+        const float *w_row = st + L.sk + row * a.B;
         for (int b = 0; b < a.B; ++b) {
-            const float w = w_s[row * ws + b];
+            const float w = w_row[b];
             if (w == 0.f) continue;
             const float *T = bones_s + 13 * b;
             p.A[0] += w * T[0]; p.A[1] += w * T[1]; p.A[2] += w * T[2]; p.t[0] += w * T[3];
@@ -99,14 +133,14 @@ __device__ __forceinline__ void pose_common(const PoseArgs &a, int i, int row, c
         p.A[1] = p.A[2] = p.A[3] = p.A[5] = p.A[6] = p.A[7] = 0.f;
         p.t[0] = p.t[1] = p.t[2] = 0.f; p.s = 1.f;
     }
-    const float q0 = a.quat[4 * (size_t)i], q1 = a.quat[4 * (size_t)i + 1], q2 = a.quat[4 * (size_t)i + 2], q3 = a.quat[4 * (size_t)i + 3];
-    p.qnorm = sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
-    p.qn[0] = q0 / p.qnorm; p.qn[1] = q1 / p.qnorm; p.qn[2] = q2 / p.qnorm; p.qn[3] = q3 / p.qnorm;
+    const float4 q = *reinterpret_cast<const float4 *>(st + L.quat + 4 * row);
+    p.qnorm = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    p.qn[0] = q.x / p.qnorm; p.qn[1] = q.y / p.qnorm; p.qn[2] = q.z / p.qnorm; p.qn[3] = q.w / p.qnorm;
     quat_to_rot(p.qn[0], p.qn[1], p.qn[2], p.qn[3], p.R);
     if (a.iso) {
-        p.S[0] = p.S[1] = p.S[2] = expf(a.log_scale[i]);
+        p.S[0] = p.S[1] = p.S[2] = expf(st[L.ls + row]);
     } else {
-        p.S[0] = expf(a.log_scale[3 * (size_t)i]); p.S[1] = expf(a.log_scale[3 * (size_t)i + 1]); p.S[2] = expf(a.log_scale[3 * (size_t)i + 2]);
+        p.S[0] = expf(st[L.ls + 3 * row]); p.S[1] = expf(st[L.ls + 3 * row + 1]); p.S[2] = expf(st[L.ls + 3 * row + 2]);
     }
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -131,102 +165,225 @@ __device__ __forceinline__ float view_dir(const PoseLocal &p, const float *cam, 
     return n;
 }
 
-__device__ __forceinline__ void load_block_inputs(const PoseArgs &a, int base, int cnt, float *bones_s, float *cam_s, float *fr_s,
-                                                  int frs, float *w_s, int ws) {
+// Persistent tile pipeline shared by both directions.  Every array of a tile is one dense run in global memory, so a
+// tile is brought in by a handful of 1-D bulk (TMA) copies into the stage that is not being computed on, and written
+// back the same way; runs that are not 16-B sized / aligned (last tile, skinned/static boundary, odd tensor offsets) take
+// a cooperative load / store path through the same shared-memory image.
+template <bool kBackward>
+struct TilePipe {
+    const PoseArgs &a;
+    TileLayout L;
+    float *stage0;
+    uint64_t *bar;
+
+    __device__ __forceinline__ float *stage(int k) const { return stage0 + (k & 1) * L.floats; }
+
+    __device__ __forceinline__ int inputs(int tile, Transfer *t) const {
+        const int base = tile * kPoseThreads, cnt = min(kPoseThreads, a.N - base);
+        const int nsk = max(0, min(cnt, a.n_skinned - base));
+        const int rs = (a.K - 1) * 3, lsw = a.iso ? 1 : 3;
+        int n = 0;
+        t[n++] = {a.f_rest ? a.f_rest + (size_t)base * rs : nullptr, L.fr, (uint32_t)(rs > 0 ? cnt * rs * 4 : 0)};
+        t[n++] = {a.skin ? a.skin + (size_t)base * a.B : nullptr, L.sk, (uint32_t)(nsk * a.B * 4)};
+        t[n++] = {a.xyz + (size_t)base * 3, L.xyz, (uint32_t)(cnt * 12)};
+        t[n++] = {a.log_scale + (size_t)base * lsw, L.ls, (uint32_t)(cnt * lsw * 4)};
+        t[n++] = {a.quat + (size_t)base * 4, L.quat, (uint32_t)(cnt * 16)};
+        t[n++] = {a.opacity_logit + base, L.opac, (uint32_t)(cnt * 4)};
+        t[n++] = {a.f_dc + (size_t)base * 3, L.fdc, (uint32_t)(cnt * 12)};
+        if (kBackward) {
+            t[n++] = {a.g_posed_xyz + (size_t)base * 3, L.gpx, (uint32_t)(cnt * 12)};
+            t[n++] = {a.g_cov6 + (size_t)base * 6, L.gcov, (uint32_t)(cnt * 24)};
+            t[n++] = {a.g_colors + (size_t)base * 3, L.gcol, (uint32_t)(cnt * 12)};
+            t[n++] = {a.g_opacity + base, L.gop, (uint32_t)(cnt * 4)};
+        }
+        return n;
+    }
+    __device__ __forceinline__ int outputs(int tile, Transfer *t) const {
+        const int base = tile * kPoseThreads, cnt = min(kPoseThreads, a.N - base);
+        const int nsk = max(0, min(cnt, a.n_skinned - base));
+        const int rs = (a.K - 1) * 3, lsw = a.iso ? 1 : 3;
+        int n = 0;
+        if (!kBackward) {
+            t[n++] = {a.posed_xyz + (size_t)base * 3, L.xyz, (uint32_t)(cnt * 12)};
+            t[n++] = {a.cov6 + (size_t)base * 6, L.cov, (uint32_t)(cnt * 24)};
+            t[n++] = {a.colors + (size_t)base * 3, L.fdc, (uint32_t)(cnt * 12)};
+            t[n++] = {a.opacity + base, L.opac, (uint32_t)(cnt * 4)};
+        } else {
+            t[n++] = {a.g_f_rest ? a.g_f_rest + (size_t)base * rs : nullptr, L.fr, (uint32_t)(rs > 0 ? cnt * rs * 4 : 0)};
+            t[n++] = {a.g_skin ? a.g_skin + (size_t)base * a.B : nullptr, L.sk, (uint32_t)(a.g_skin ? nsk * a.B * 4 : 0)};
+            t[n++] = {a.g_xyz + (size_t)base * 3, L.gpx, (uint32_t)(cnt * 12)};
+            t[n++] = {a.g_log_scale + (size_t)base * lsw, L.ls, (uint32_t)(cnt * lsw * 4)};
+            t[n++] = {a.g_quat + (size_t)base * 4, L.quat, (uint32_t)(cnt * 16)};
+            t[n++] = {a.g_opacity_logit + base, L.gop, (uint32_t)(cnt * 4)};
+            t[n++] = {a.g_f_dc + (size_t)base * 3, L.gcol, (uint32_t)(cnt * 12)};
+        }
+        return n;
+    }
+    // elected thread: start the bulk copies of `tile` into stage k
+    __device__ __forceinline__ void prefetch(int tile, int k) const {
+        Transfer t[kMaxArrays];
+        const int n = inputs(tile, t);
+        uint32_t total = 0;
+        for (int j = 0; j < n; ++j)
+            if (bulk_ok(t[j])) total += t[j].bytes;
+        if (total == 0) return;
+        mbar_expect_tx(&bar[k & 1], total);
+        for (int j = 0; j < n; ++j)
+            if (bulk_ok(t[j])) bulk_g2s(stage(k) + t[j].s, t[j].g, t[j].bytes, &bar[k & 1]);
+    }
+    // all threads: the tile's inputs are complete in stage k after this returns (phase = per-stage mbarrier parity bits)
+    __device__ __forceinline__ void acquire(int tile, int k, uint32_t &phase) const {
+        Transfer t[kMaxArrays];
+        const int n = inputs(tile, t);
+        bool any_bulk = false, any_plain = false;
+        for (int j = 0; j < n; ++j) {
+            if (bulk_ok(t[j])) any_bulk = true;
+            else if (t[j].bytes) {
+                any_plain = true;
+                float *dst = stage(k) + t[j].s;
+                const int words = (int)(t[j].bytes >> 2);
+                for (int e = threadIdx.x; e < words; e += kPoseThreads) dst[e] = t[j].g[e];
+            }
+        }
+        if (any_bulk) {
+            mbar_wait(&bar[k & 1], (phase >> (k & 1)) & 1u);
+            phase ^= 1u << (k & 1);
+        }
+        if (any_plain) __syncthreads();
+    }
+    // all threads, after the results have been written into stage k
+    __device__ __forceinline__ void release(int tile, int k) const {
+        fence_proxy_async();
+        __syncthreads();
+        Transfer t[kMaxArrays];
+        const int n = outputs(tile, t);
+        for (int j = 0; j < n; ++j) {
+            if (!t[j].bytes) continue;
+            float *dst = const_cast<float *>(t[j].g);
+            const float *src = stage(k) + t[j].s;
+            if (bulk_ok(t[j])) {
+                if (threadIdx.x == 0) bulk_s2g(dst, src, t[j].bytes);
+            } else {
+                const int words = (int)(t[j].bytes >> 2);
+                for (int e = threadIdx.x; e < words; e += kPoseThreads) dst[e] = src[e];
+            }
+        }
+        if (threadIdx.x == 0) bulk_commit();
+    }
+};
+
+template <bool kBackward, typename Body>
+__device__ __forceinline__ void run_tiles(const PoseArgs &a, float *smem, Body body) {
+    float *bones_s = smem, *cam_s = bones_s + kMaxBones * 13;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(cam_s + 4);
+    TilePipe<kBackward> pipe{a, tile_layout(a.K, a.B, a.iso, kBackward), cam_s + 8, bar};
     for (int j = threadIdx.x; j < a.B * 13; j += kPoseThreads) {
         const int b = j / 13, e = j - 13 * b;
         bones_s[j] = a.bone_tf[16 * b + (e < 12 ? e : 15)];
     }
     if (threadIdx.x < 3) cam_s[threadIdx.x] = a.campos[threadIdx.x];
-    const int rs = (a.K - 1) * 3;
-    if (rs > 0) stage_rows_in(fr_s, frs, a.f_rest + (size_t)base * rs, cnt, rs);
-    const int nsk = min(cnt, a.n_skinned - base);
-    if (nsk > 0) stage_rows_in(w_s, ws, a.skin + (size_t)base * a.B, nsk, a.B);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
     __syncthreads();
-}
-
-__global__ void __launch_bounds__(kPoseThreads) pose_forward_kernel(PoseArgs a) {
-    extern __shared__ float smem[];
-    const int rs = (a.K - 1) * 3, frs = rs > 0 ? odd_stride(rs) : 0, ws = a.B > 0 ? odd_stride(a.B) : 0;
-    float *bones_s = smem, *cam_s = bones_s + a.B * 13, *fr_s = cam_s + 4, *w_s = fr_s + kPoseThreads * frs;
-    const int base = blockIdx.x * kPoseThreads;
-    const int cnt = min(kPoseThreads, a.N - base);
-    load_block_inputs(a, base, cnt, bones_s, cam_s, fr_s, frs, w_s, ws);
-    const int row = threadIdx.x, i = base + row;
-    if (row >= cnt) return;
-    PoseLocal p;
-    pose_common(a, i, row, bones_s, w_s, ws, p);
-    // mean
-    float px[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) px[r] = p.A[3 * r] * p.x[0] + p.A[3 * r + 1] * p.x[1] + p.A[3 * r + 2] * p.x[2] + p.t[r];
-    // covariance: Sigma' = (A L)(A L)^T
-    float Bm[9];
-    if (p.skinned) mat3_mul(p.A, p.L, Bm);
-    else {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) Bm[k] = p.L[k];
-    }
-    float c6[6];
-    c6[0] = Bm[0] * Bm[0] + Bm[1] * Bm[1] + Bm[2] * Bm[2];
-    c6[1] = Bm[0] * Bm[3] + Bm[1] * Bm[4] + Bm[2] * Bm[5];
-    c6[2] = Bm[0] * Bm[6] + Bm[1] * Bm[7] + Bm[2] * Bm[8];
-    c6[3] = Bm[3] * Bm[3] + Bm[4] * Bm[4] + Bm[5] * Bm[5];
-    c6[4] = Bm[3] * Bm[6] + Bm[4] * Bm[7] + Bm[5] * Bm[8];
-    c6[5] = Bm[6] * Bm[6] + Bm[7] * Bm[7] + Bm[8] * Bm[8];
-    // colour
-    float Ainv[9], ci[3], dir[3], basis[16];
-    if (p.skinned) mat3_inverse(p.A, Ainv);
-    view_dir(p, cam_s, Ainv, ci, dir);
-    sh_basis(a.deg, dir[0], dir[1], dir[2], basis);
-    const int nb = (a.deg + 1) * (a.deg + 1);
-    float rgb[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float v = basis[0] * a.f_dc[3 * (size_t)i + c];
-        for (int k = 1; k < nb; ++k) v += basis[k] * fr_s[row * frs + 3 * (k - 1) + c];
-        rgb[c] = fmaxf(v + 0.5f, 0.f);
-    }
-    const float ol = a.opacity_logit[i];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        a.posed_xyz[3 * (size_t)i + r] = px[r];
-        a.colors[3 * (size_t)i + r] = rgb[r];
-    }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) a.cov6[6 * (size_t)i + k] = c6[k];
-    a.opacity[i] = 1.0f / (1.0f + expf(-ol));
-    if (a.tf_out && p.skinned) {
-        float *o = a.tf_out + 16 * (size_t)i;
-        o[0] = p.A[0]; o[1] = p.A[1]; o[2] = p.A[2]; o[3] = p.t[0];
-        o[4] = p.A[3]; o[5] = p.A[4]; o[6] = p.A[5]; o[7] = p.t[1];
-        o[8] = p.A[6]; o[9] = p.A[7]; o[10] = p.A[8]; o[11] = p.t[2];
-        // bottom row = sum_b w_b T_b[3,:]
-        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-        for (int b = 0; b < a.B; ++b) {
-            const float w = w_s[row * ws + b];
-            b0 += w * a.bone_tf[16 * b + 12]; b1 += w * a.bone_tf[16 * b + 13]; b2 += w * a.bone_tf[16 * b + 14];
+    const int ntiles = (a.N + kPoseThreads - 1) / kPoseThreads;
+    if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) pipe.prefetch(blockIdx.x, 0);
+    int k = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+        const int next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < ntiles) {
+            bulk_wait_read_all();   // the stores of two tiles ago have finished reading the stage that is refilled now
+            pipe.prefetch(next, k + 1);
         }
-        o[12] = b0; o[13] = b1; o[14] = b2; o[15] = p.s;
+        pipe.acquire(tile, k, phase);
+        const int row = threadIdx.x, i = tile * kPoseThreads + row;
+        if (i < a.N) body(pipe.L, pipe.stage(k), i, row, bones_s, cam_s);
+        pipe.release(tile, k);
+        __syncthreads();   // plain-path stores have read the stage before it is refilled
     }
+    if (threadIdx.x == 0) bulk_wait_all();
 }
 
-__global__ void __launch_bounds__(kPoseThreads) pose_backward_kernel(PoseArgs a) {
-    extern __shared__ float smem[];
-    const int rs = (a.K - 1) * 3, frs = rs > 0 ? odd_stride(rs) : 0, ws = a.B > 0 ? odd_stride(a.B) : 0;
-    float *bones_s = smem, *cam_s = bones_s + a.B * 13, *fr_s = cam_s + 4, *w_s = fr_s + kPoseThreads * frs;
-    const int base = blockIdx.x * kPoseThreads;
-    const int cnt = min(kPoseThreads, a.N - base);
-    load_block_inputs(a, base, cnt, bones_s, cam_s, fr_s, frs, w_s, ws);
-    const int row = threadIdx.x, i = base + row;
-    if (row < cnt) {
+template <int DEG>
+__global__ void __launch_bounds__(kPoseThreads) pose_forward_kernel(PoseArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    constexpr int nb = (DEG + 1) * (DEG + 1);
+    run_tiles<false>(a, smem, [&](const TileLayout &L, float *st, int i, int row, const float *bones_s, const float *cam_s) {
         PoseLocal p;
-        pose_common(a, i, row, bones_s, w_s, ws, p);
+        pose_common(a, L, st, i, row, bones_s, p);
+        // mean
+        float px[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) px[r] = p.A[3 * r] * p.x[0] + p.A[3 * r + 1] * p.x[1] + p.A[3 * r + 2] * p.x[2] + p.t[r];
+        // covariance: Sigma' = (A L)(A L)^T
+        float Bm[9];
+        if (p.skinned) mat3_mul(p.A, p.L, Bm);
+        else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) Bm[k] = p.L[k];
+        }
+        float c6[6];
+        c6[0] = Bm[0] * Bm[0] + Bm[1] * Bm[1] + Bm[2] * Bm[2];
+        c6[1] = Bm[0] * Bm[3] + Bm[1] * Bm[4] + Bm[2] * Bm[5];
+        c6[2] = Bm[0] * Bm[6] + Bm[1] * Bm[7] + Bm[2] * Bm[8];
+        c6[3] = Bm[3] * Bm[3] + Bm[4] * Bm[4] + Bm[5] * Bm[5];
+        c6[4] = Bm[3] * Bm[6] + Bm[4] * Bm[7] + Bm[5] * Bm[8];
+        c6[5] = Bm[6] * Bm[6] + Bm[7] * Bm[7] + Bm[8] * Bm[8];
+        // colour
+        float Ainv[9], ci[3], dir[3], basis[16];
+        if (p.skinned) mat3_inverse(p.A, Ainv);
+        view_dir(p, cam_s, Ainv, ci, dir);
+        sh_basis(DEG, dir[0], dir[1], dir[2], basis);
+        const float *fr = st + L.fr + row * (a.K - 1) * 3;
+        float rgb[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = basis[0] * st[L.fdc + 3 * row + c];
+#pragma unroll
+            for (int k = 1; k < nb; ++k) v += basis[k] * fr[3 * (k - 1) + c];
+            rgb[c] = fmaxf(v + 0.5f, 0.f);
+        }
+        const float ol = st[L.opac + row];
+        if (a.tf_out && p.skinned) {
+            float *o = a.tf_out + 16 * (size_t)i;
+            o[0] = p.A[0]; o[1] = p.A[1]; o[2] = p.A[2]; o[3] = p.t[0];
+            o[4] = p.A[3]; o[5] = p.A[4]; o[6] = p.A[5]; o[7] = p.t[1];
+            o[8] = p.A[6]; o[9] = p.A[7]; o[10] = p.A[8]; o[11] = p.t[2];
+            // bottom row = sum_b w_b T_b[3,:]
+            float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+            for (int b = 0; b < a.B; ++b) {
+                const float w = st[L.sk + row * a.B + b];
+                b0 += w * a.bone_tf[16 * b + 12]; b1 += w * a.bone_tf[16 * b + 13]; b2 += w * a.bone_tf[16 * b + 14];
+            }
+            o[12] = b0; o[13] = b1; o[14] = b2; o[15] = p.s;
+        }
+        // results over the thread's own input rows (xyz -> posed xyz, f_dc -> colour, logit -> opacity)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            st[L.xyz + 3 * row + r] = px[r];
+            st[L.fdc + 3 * row + r] = rgb[r];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) st[L.cov + 6 * row + k] = c6[k];
+        st[L.opac + row] = 1.0f / (1.0f + expf(-ol));
+    });
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(kPoseThreads) pose_backward_kernel(PoseArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    constexpr int nb = (DEG + 1) * (DEG + 1);
+    run_tiles<true>(a, smem, [&](const TileLayout &L, float *st, int i, int row, const float *bones_s, const float *cam_s) {
+        PoseLocal p;
+        pose_common(a, L, st, i, row, bones_s, p);
         float gx[3] = {0.f, 0.f, 0.f}, dA[9], dt[3] = {0.f, 0.f, 0.f}, ds = 0.f;
 #pragma unroll
         for (int k = 0; k < 9; ++k) dA[k] = 0.f;
         // ---- mean: x' = A x + t
-        const float gp[3] = {a.g_posed_xyz[3 * (size_t)i], a.g_posed_xyz[3 * (size_t)i + 1], a.g_posed_xyz[3 * (size_t)i + 2]};
+        const float gp[3] = {st[L.gpx + 3 * row], st[L.gpx + 3 * row + 1], st[L.gpx + 3 * row + 2]};
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             gx[r] = p.A[r] * gp[0] + p.A[3 + r] * gp[1] + p.A[6 + r] * gp[2];
@@ -235,7 +392,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_backward_kernel(PoseArgs a)
             for (int c = 0; c < 3; ++c) dA[3 * r + c] = gp[r] * p.x[c];
         }
         // ---- covariance: Sigma' = Bm Bm^T, Bm = A L ; Gs = symmetrised dL/dSigma'
-        const float *g6 = a.g_cov6 + 6 * (size_t)i;
+        const float *g6 = st + L.gcov + 6 * row;
         const float Gs[9] = {g6[0], 0.5f * g6[1], 0.5f * g6[2], 0.5f * g6[1], g6[3], 0.5f * g6[4], 0.5f * g6[2], 0.5f * g6[4], g6[5]};
         float Bm[9], dB[9], dL[9];
         if (p.skinned) mat3_mul(p.A, p.L, Bm);
@@ -268,39 +425,43 @@ __global__ void __launch_bounds__(kPoseThreads) pose_backward_kernel(PoseArgs a)
         }
         quat_to_rot_bwd(p.qn[0], p.qn[1], p.qn[2], p.qn[3], dR, dqn);
         const float qd = p.qn[0] * dqn[0] + p.qn[1] * dqn[1] + p.qn[2] * dqn[2] + p.qn[3] * dqn[3];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) a.g_quat[4 * (size_t)i + k] = (dqn[k] - p.qn[k] * qd) / p.qnorm;
-        if (a.iso) a.g_log_scale[i] = dS[0] * p.S[0] + dS[1] * p.S[1] + dS[2] * p.S[2];
+        float4 gq;
+        gq.x = (dqn[0] - p.qn[0] * qd) / p.qnorm; gq.y = (dqn[1] - p.qn[1] * qd) / p.qnorm;
+        gq.z = (dqn[2] - p.qn[2] * qd) / p.qnorm; gq.w = (dqn[3] - p.qn[3] * qd) / p.qnorm;
+        *reinterpret_cast<float4 *>(st + L.quat + 4 * row) = gq;
+        if (a.iso) st[L.ls + row] = dS[0] * p.S[0] + dS[1] * p.S[1] + dS[2] * p.S[2];
         else {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) a.g_log_scale[3 * (size_t)i + k] = dS[k] * p.S[k];
+            for (int k = 0; k < 3; ++k) st[L.ls + 3 * row + k] = dS[k] * p.S[k];
         }
         // ---- colour
         float Ainv[9], ci[3], dir[3], basis[16], bxg[16], byg[16], bzg[16];
         if (p.skinned) mat3_inverse(p.A, Ainv);
         const float dn = view_dir(p, cam_s, Ainv, ci, dir);
-        sh_basis(a.deg, dir[0], dir[1], dir[2], basis);
-        sh_basis_grad(a.deg, dir[0], dir[1], dir[2], bxg, byg, bzg);
-        const int nb = (a.deg + 1) * (a.deg + 1);
+        sh_basis(DEG, dir[0], dir[1], dir[2], basis);
+        sh_basis_grad(DEG, dir[0], dir[1], dir[2], bxg, byg, bzg);
+        float *fr = st + L.fr + row * (a.K - 1) * 3;
         float go[3], gd[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float f0 = a.f_dc[3 * (size_t)i + c];
-            float v = basis[0] * f0;
-            for (int k = 1; k < nb; ++k) v += basis[k] * fr_s[row * frs + 3 * (k - 1) + c];
-            go[c] = (v + 0.5f >= 0.f) ? a.g_colors[3 * (size_t)i + c] : 0.f;
-            a.g_f_dc[3 * (size_t)i + c] = basis[0] * go[c];
+            float v = basis[0] * st[L.fdc + 3 * row + c];
+#pragma unroll
+            for (int k = 1; k < nb; ++k) v += basis[k] * fr[3 * (k - 1) + c];
+            go[c] = (v + 0.5f >= 0.f) ? st[L.gcol + 3 * row + c] : 0.f;
         }
-        for (int k = 1; k < a.K; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) st[L.gcol + 3 * row + c] = basis[0] * go[c];   // g_f_dc
+#pragma unroll
+        for (int k = 1; k < nb; ++k)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                float *slot = fr_s + row * frs + 3 * (k - 1) + c;
-                if (k < nb) {
-                    const float s = *slot * go[c];
-                    gd[0] += bxg[k] * s; gd[1] += byg[k] * s; gd[2] += bzg[k] * s;
-                    *slot = basis[k] * go[c];
-                } else *slot = 0.f;
+                const float sv = fr[3 * (k - 1) + c] * go[c];
+                gd[0] += bxg[k] * sv; gd[1] += byg[k] * sv; gd[2] += bzg[k] * sv;
+                fr[3 * (k - 1) + c] = basis[k] * go[c];
             }
+        for (int k = nb; k < a.K; ++k)   // coefficients above the active degree get no gradient
+#pragma unroll
+            for (int c = 0; c < 3; ++c) fr[3 * (k - 1) + c] = 0.f;
         const float dot = dir[0] * gd[0] + dir[1] * gd[1] + dir[2] * gd[2];
         const float gdd[3] = {(gd[0] - dir[0] * dot) / dn, (gd[1] - dir[1] * dot) / dn, (gd[2] - dir[2] * dot) / dn};
 #pragma unroll
@@ -320,22 +481,19 @@ __global__ void __launch_bounds__(kPoseThreads) pose_backward_kernel(PoseArgs a)
             ds += (p.t[0] * du[0] + p.t[1] * du[1] + p.t[2] * du[2]) * is * is;
         }
 #pragma unroll
-        for (int r = 0; r < 3; ++r) a.g_xyz[3 * (size_t)i + r] = gx[r];
-        const float sg = 1.0f / (1.0f + expf(-a.opacity_logit[i]));
-        a.g_opacity_logit[i] = a.g_opacity[i] * sg * (1.0f - sg);
+        for (int r = 0; r < 3; ++r) st[L.gpx + 3 * row + r] = gx[r];   // g_xyz
+        const float sg = 1.0f / (1.0f + expf(-st[L.opac + row]));
+        st[L.gop + row] = st[L.gop + row] * sg * (1.0f - sg);          // g_opacity_logit
         if (a.g_skin && p.skinned) {
+            float *w_row = st + L.sk + row * a.B;
             for (int b = 0; b < a.B; ++b) {
                 const float *T = bones_s + 13 * b;
-                w_s[row * ws + b] = dA[0] * T[0] + dA[1] * T[1] + dA[2] * T[2] + dt[0] * T[3] + dA[3] * T[4] + dA[4] * T[5] +
-                                    dA[5] * T[6] + dt[1] * T[7] + dA[6] * T[8] + dA[7] * T[9] + dA[8] * T[10] + dt[2] * T[11] +
-                                    ds * T[12];
+                w_row[b] = dA[0] * T[0] + dA[1] * T[1] + dA[2] * T[2] + dt[0] * T[3] + dA[3] * T[4] + dA[4] * T[5] +
+                           dA[5] * T[6] + dt[1] * T[7] + dA[6] * T[8] + dA[7] * T[9] + dA[8] * T[10] + dt[2] * T[11] +
+                           ds * T[12];
             }
         }
-    }
-    __syncthreads();
-    if (rs > 0) stage_rows_out(a.g_f_rest + (size_t)base * rs, fr_s, frs, cnt, rs);
-    const int nsk = min(cnt, a.n_skinned - base);
-    if (a.g_skin && nsk > 0) stage_rows_out(a.g_skin + (size_t)base * a.B, w_s, ws, nsk, a.B);
+    });
 }
 
 static int validate_pose(const mb_pose_inputs *in, const char *who) {
@@ -365,6 +523,39 @@ static PoseArgs pose_args(const mb_pose_inputs *in) {
     return a;
 }
 
+template <int DEG>
+static int launch_pose(const PoseArgs &a, bool backward, cudaStream_t s) {
+    const size_t smem = pose_smem_bytes(a.B, a.K, a.iso, backward);
+    const int ntiles = (a.N + kPoseThreads - 1) / kPoseThreads;
+    int per_sm = (int)((size_t)(220 * 1024) / smem);
+    if (per_sm < 1) {
+        set_error("pose kernel: a tile of %d Gaussians with %d SH coefficients and %d bones needs %zu bytes of shared memory", kPoseThreads,
+                  a.K, a.B, smem);
+        return MB_ERR_INVALID;
+    }
+    if (per_sm > 8) per_sm = 8;
+    const int grid = min(ntiles, sm_count() * per_sm);
+    if (backward) {
+        MB_CUDA(cudaFuncSetAttribute(pose_backward_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KernelTimer kt("pose_backward", s);
+        pose_backward_kernel<DEG><<<grid, kPoseThreads, smem, s>>>(a);
+    } else {
+        MB_CUDA(cudaFuncSetAttribute(pose_forward_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KernelTimer kt("pose_forward", s);
+        pose_forward_kernel<DEG><<<grid, kPoseThreads, smem, s>>>(a);
+    }
+    return check_launch(backward ? "pose_backward" : "pose_forward", false, s);
+}
+
+static int launch_pose_deg(const PoseArgs &a, bool backward, cudaStream_t s) {
+    switch (a.deg) {
+        case 0: return launch_pose<0>(a, backward, s);
+        case 1: return launch_pose<1>(a, backward, s);
+        case 2: return launch_pose<2>(a, backward, s);
+        default: return launch_pose<3>(a, backward, s);
+    }
+}
+
 }  // namespace mb
 
 using namespace mb;
@@ -377,13 +568,7 @@ extern "C" int mb_pose_forward(const mb_pose_inputs *in, float *posed_xyz, float
     MB_REQUIRE(posed_xyz && posed_cov6 && colors && opacity, "mb_pose_forward: null output");
     PoseArgs a = pose_args(in);
     a.posed_xyz = posed_xyz; a.cov6 = posed_cov6; a.colors = colors; a.opacity = opacity; a.tf_out = tf_out;
-    const size_t smem = pose_smem_bytes(a.B, a.K);
-    MB_CUDA(cudaFuncSetAttribute(pose_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
-        KernelTimer kt("pose_forward", (cudaStream_t)stream);
-        pose_forward_kernel<<<(a.N + kPoseThreads - 1) / kPoseThreads, kPoseThreads, smem, (cudaStream_t)stream>>>(a);
-    }
-    return check_launch("pose_forward", false, (cudaStream_t)stream);
+    return launch_pose_deg(a, false, (cudaStream_t)stream);
 }
 
 extern "C" int mb_pose_backward(const mb_pose_inputs *in, const float *g_posed_xyz, const float *g_posed_cov6,
@@ -399,11 +584,5 @@ extern "C" int mb_pose_backward(const mb_pose_inputs *in, const float *g_posed_x
     a.g_posed_xyz = g_posed_xyz; a.g_cov6 = g_posed_cov6; a.g_colors = g_colors; a.g_opacity = g_opacity;
     a.g_xyz = g_xyz; a.g_log_scale = g_log_scale; a.g_quat = g_quat; a.g_opacity_logit = g_opacity_logit;
     a.g_f_dc = g_f_dc; a.g_f_rest = g_f_rest; a.g_skin = g_skin_wts;
-    const size_t smem = pose_smem_bytes(a.B, a.K);
-    MB_CUDA(cudaFuncSetAttribute(pose_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
-        KernelTimer kt("pose_backward", (cudaStream_t)stream);
-        pose_backward_kernel<<<(a.N + kPoseThreads - 1) / kPoseThreads, kPoseThreads, smem, (cudaStream_t)stream>>>(a);
-    }
-    return check_launch("pose_backward", false, (cudaStream_t)stream);
+    return launch_pose_deg(a, true, (cudaStream_t)stream);
 }
