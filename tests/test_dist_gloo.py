@@ -1,0 +1,95 @@
+"""Host logic of the view-sharded data-parallel step on CPU with gloo, world_size 2:
+R ranks x (views / R) views + ONE all-reduce of the flat gradient buffer == one process accumulating the same views
+(the reference's ``final_loss / accum_iter``, /root/reference/src/modules/hand_dynamic.py:248,259-277).
+No kernel runs here: ``render_backward`` is a deterministic stand-in that fills the sink like the pose backward does."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from manus_b200.dist import PARAM_ORDER, FlatGaussians, allreduce_gradients, shard_views, sharded_step
+
+N, VIEWS = 257, [3, 8, 11, 20, 21, 34, 40]
+
+
+def fake_render_backward(flat, view, sink):
+    """Overwrites every sink tensor with a view-dependent pattern (what one view's backward would write) and returns a loss."""
+    for j, name in enumerate(PARAM_ORDER):
+        g = sink[name]
+        base = torch.arange(g.numel(), dtype=torch.float32).reshape(g.shape)
+        g.copy_(torch.sin(base * 0.01 + view) * (j + 1) + flat.params[name] * 0.5)
+    return torch.tensor(float(view) * 0.25)
+
+
+def make_flat():
+    flat = FlatGaussians(N, "cpu")
+    gen = torch.Generator().manual_seed(0)
+    flat.data.copy_(torch.randn(flat.data.shape, generator=gen))
+    return flat
+
+
+def single_process_reference(views):
+    flat = make_flat()
+    loss = sharded_step(flat, views, fake_render_backward)
+    return flat.grad.clone(), float(loss)
+
+
+def _worker(rank, world, port, views, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        flat = make_flat()
+        mine = shard_views(views, rank, world)
+        loss = sharded_step(flat, mine, fake_render_backward, global_views=len(views))
+        np.save(os.path.join(out_dir, f"grad_{rank}.npy"), flat.grad.numpy())
+        np.save(os.path.join(out_dir, f"loss_{rank}.npy"), np.array([float(loss)]))
+        # the plain collective helper: SUM then average over ranks
+        t = torch.full((5,), float(rank + 1))
+        allreduce_gradients(t)
+        np.save(os.path.join(out_dir, f"avg_{rank}.npy"), t.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_shard_views_round_robin():
+    assert shard_views(VIEWS, 0, 2) == [3, 11, 21, 40]
+    assert shard_views(VIEWS, 1, 2) == [8, 20, 34]
+    assert sorted(sum((shard_views(list(range(50)), r, 8) for r in range(8)), [])) == list(range(50))
+    assert [len(shard_views(list(range(50)), r, 8)) for r in range(8)] == [7, 7, 6, 6, 6, 6, 6, 6]
+
+
+def test_flat_buffer_layout():
+    flat = FlatGaussians(10, "cpu")
+    assert flat.floats_per_gaussian == 59 and flat.allreduce_bytes() == 10 * 59 * 4
+    # views alias the flat buffers, segment per parameter in PARAM_ORDER
+    off = 0
+    for name in PARAM_ORDER:
+        g = flat.grads[name]
+        assert g.data_ptr() == flat.grad.data_ptr() + 4 * off and g.is_contiguous()
+        off += g.numel()
+    assert off == flat.grad.numel()
+    iso = FlatGaussians(10, "cpu", sh_coeffs=4, isotropic=True)
+    assert iso.floats_per_gaussian == 3 + 3 + 9 + 1 + 1 + 4
+
+
+@pytest.mark.parametrize("views", [VIEWS, VIEWS[:2], VIEWS[:1]])
+def test_two_ranks_equal_gradient_accumulation(tmp_path, views):
+    ref_grad, ref_loss = single_process_reference(views)
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, views, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        got = np.load(tmp_path / f"grad_{r}.npy")
+        np.testing.assert_allclose(got, ref_grad.numpy(), rtol=2e-6, atol=2e-6)       # fp32 sum order differs only
+        assert abs(float(np.load(tmp_path / f"loss_{r}.npy")[0]) - ref_loss) < 1e-6
+        np.testing.assert_allclose(np.load(tmp_path / f"avg_{r}.npy"), np.full(5, 1.5))
