@@ -156,30 +156,44 @@ __global__ void __launch_bounds__(kWarps * 32, 24 / kWarps) blend_forward_kernel
             }
             unsigned m = __ballot_sync(0xffffffffu, hit);
             while (m) {
-                const int j = j0 + __ffs(m) - 1;
-                m &= m - 1;
-                const float4 ra = r[3 * j], rb = r[3 * j + 1];
-                const float2 rc = *reinterpret_cast<const float2 *>(&r[3 * j + 2]);
-                const float dx = ra.x - fx, dy = ra.y - fy;
-                const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
-                const bool cand = !done && power <= 0.0f && !(power < rc.y);
-                if (!__any_sync(0xffffffffu, cand)) continue;
-                const float alpha = fminf(kAlphaMax, rb.y * expf(power));
-                const bool ok = cand && alpha >= kAlphaMin;
-                const float test_T = T * (1.0f - alpha);
-                const bool stop = ok && test_T < kTMin;
-                if (ok && !stop) {
-                    const float w = alpha * T;
-                    C0 += rb.z * w;
-                    C1 += rb.w * w;
-                    C2 += rc.x * w;
-                    T = test_T;
-                    last = base + (uint32_t)j + 1u;
+                // up to 4 survivors per step: everything that does not depend on the running transmittance (record
+                // fetch, power, exponential, alpha) is evaluated for all four first (independent instruction streams),
+                // then the four are applied in list order
+                float alpha[4], cr[4], cg[4], cb[4];
+                uint32_t pos1[4];
+                bool valid[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool has = m != 0;
+                    const int j = j0 + (has ? __ffs(m) - 1 : 0);
+                    m &= m - 1;
+                    const float4 ra = r[3 * j], rb = r[3 * j + 1];
+                    const float blue = r[3 * j + 2].x;
+                    const float dx = ra.x - fx, dy = ra.y - fy;
+                    const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
+                    alpha[q] = fminf(kAlphaMax, rb.y * expf(power));
+                    valid[q] = has && power <= 0.0f && alpha[q] >= kAlphaMin;
+                    cr[q] = rb.z; cg[q] = rb.w; cb[q] = blue;
+                    pos1[q] = base + (uint32_t)j + 1u;
                 }
-                done = done || stop;
-                if (__any_sync(0xffffffffu, stop)) {
-                    wdone = __all_sync(0xffffffffu, done);
-                    if (wdone) break;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool ok = valid[q] && !done;
+                    const float test_T = T * (1.0f - alpha[q]);
+                    const bool stop = ok && test_T < kTMin;
+                    if (ok && !stop) {
+                        const float w = alpha[q] * T;
+                        C0 += cr[q] * w;
+                        C1 += cg[q] * w;
+                        C2 += cb[q] * w;
+                        T = test_T;
+                        last = pos1[q];
+                    }
+                    done = done || stop;
+                }
+                if (__all_sync(0xffffffffu, done)) {
+                    wdone = true;
+                    break;
                 }
             }
         }
@@ -315,7 +329,8 @@ __global__ void __launch_bounds__(kWarps * 32, 16 / kWarps) blend_backward_kerne
                 if (!__any_sync(0xffffffffu, active)) continue;
                 float v[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (active) {
-                    T = T / (1.0f - alpha);
+                    const float rinv = 1.0f / (1.0f - alpha);
+                    T = T * rinv;
                     const float dch = alpha * T;
                     a0 = last_alpha * lc0 + (1.f - last_alpha) * a0;
                     a1 = last_alpha * lc1 + (1.f - last_alpha) * a1;
@@ -325,7 +340,7 @@ __global__ void __launch_bounds__(kWarps * 32, 16 / kWarps) blend_backward_kerne
                     v[6] = dch * dp0; v[7] = dch * dp1; v[8] = dch * dp2;
                     dL_dalpha *= T;
                     last_alpha = alpha;
-                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                    dL_dalpha += (-T_final * rinv) * bg_dot;
                     const float dL_dG = rb.y * dL_dalpha;   // the 0.99 clamp is not masked (upstream behaviour)
                     const float gdx = G * dx, gdy = G * dy;
                     const float dG_ddelx = -gdx * ra.z - gdy * ra.w;

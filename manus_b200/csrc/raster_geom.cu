@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
     const float *v = cam, *p = cam + 16;
     const int i = blockIdx.x * 256 + tid;
     bool visible = false;
+    uint32_t my_tiles = 0;
     if (i < a.P) {
         int radius = 0;
         uint32_t tiles = 0, key = 0xffffffffu;
@@ -161,12 +162,26 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
             }
         }
         a.radii[i] = radius;
+        my_tiles = tiles;
         a.g.tiles_touched[i] = tiles;
         a.g.depth_key[i] = key;
         a.g.ident[i] = (uint32_t)i;
     }
+    // per-CTA totals: visible Gaussians and instances (num_rendered is known as soon as this kernel has run)
+    __shared__ uint32_t s_vis, s_tiles;
+    if (tid == 0) { s_vis = 0; s_tiles = 0; }
+    __syncthreads();
     const unsigned vis = __ballot_sync(0xffffffffu, visible);
-    if ((tid & 31) == 0 && vis) atomicAdd(&a.g.counters[kCntVisible], (uint32_t)__popc(vis));
+    const uint32_t wt = __reduce_add_sync(0xffffffffu, my_tiles);
+    if ((tid & 31) == 0 && vis) {
+        atomicAdd(&s_vis, (uint32_t)__popc(vis));
+        atomicAdd(&s_tiles, wt);
+    }
+    __syncthreads();
+    if (tid == 0 && s_vis) {
+        atomicAdd(&a.g.counters[kCntVisible], s_vis);
+        atomicAdd(&a.g.counters[kCntRendered], s_tiles);
+    }
 }
 
 // Instance emission, warp-cooperative: a warp owns 32 consecutive depth-sorted Gaussians; their (tile id, gaussian id)
@@ -175,30 +190,78 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
 // Gaussians that cover more than kBigTiles tiles (up to the whole screen) are queued and written by whole CTAs in
 // emit_big_kernel, so that no warp is left with thousands of slots.
 constexpr uint32_t kBigTiles = 64;
+enum : uint32_t { kScanAggregate = 1u << 30, kScanPrefix = 2u << 30, kScanMask = (1u << 30) - 1u };
 
+// The instance offsets (exclusive scan of the tile counts in depth order) are computed here as well, single pass:
+// a CTA takes the next chunk of 256 depth-sorted Gaussians (dynamic chunk id), scans its counts, publishes the chunk
+// total and gets the total of all earlier chunks by decoupled look-back (warp 0 reads 32 predecessors per step).
 __global__ void __launch_bounds__(256) emit_instances_kernel(int P, int gx, const uint32_t *__restrict__ sorted_idx,
-                                                             const uint32_t *__restrict__ offsets,
                                                              const uint32_t *__restrict__ tiles_touched,
                                                              const ushort4 *__restrict__ rect,
-                                                             uint32_t *__restrict__ counters, int64_t capacity,
-                                                             uint32_t *__restrict__ tile_out, uint32_t *__restrict__ gid_out,
-                                                             uint32_t *__restrict__ big_list) {
+                                                             uint32_t *__restrict__ counters, volatile uint32_t *status,
+                                                             int64_t capacity, uint32_t *__restrict__ tile_out,
+                                                             uint32_t *__restrict__ gid_out, uint2 *__restrict__ big_list) {
+    __shared__ uint32_t s_chunk, s_base, s_warp[8];
     if (blockIdx.x == 0 && threadIdx.x == 0 && (int64_t)counters[kCntRendered] > capacity) counters[kCntOverflow] = 1;
-    const int lane = threadIdx.x & 31;
-    const int warps_total = (gridDim.x * blockDim.x) >> 5;
-    for (int i0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; i0 < P; i0 += warps_total * 32) {
-        const int i = i0 + lane;
-        uint32_t g = 0, cnt = 0, off = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nchunks = (P + 255) / 256;
+    while (true) {
+        __syncthreads();   // s_chunk / s_base / s_warp of the previous chunk are no longer read
+        if (threadIdx.x == 0) s_chunk = atomicAdd(&counters[kCntEmitCursor], 1u);
+        __syncthreads();
+        const int chunk = (int)s_chunk;
+        if (chunk >= nchunks) return;
+        const int i = chunk * 256 + (int)threadIdx.x;
+        uint32_t g = 0, cnt = 0;
         ushort4 r = make_ushort4(0, 0, 1, 1);
         if (i < P) {
             g = sorted_idx[i];
             cnt = tiles_touched[g];
-            off = offsets[i];
             if (cnt) r = rect[g];
-            if (cnt > kBigTiles) {
-                big_list[atomicAdd(&counters[kCntBig], 1u)] = (uint32_t)i;
-                cnt = 0;
+        }
+        // scan of the full counts (big Gaussians keep their slots; they are written by emit_big_kernel)
+        uint32_t incl_all = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl_all, o);
+            if (lane >= o) incl_all += t;
+        }
+        if (lane == 31) s_warp[warp] = incl_all;
+        __syncthreads();
+        uint32_t warp_excl = 0, chunk_total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t t = s_warp[w];
+            if (w < warp) warp_excl += t;
+            chunk_total += t;
+        }
+        if (warp == 0) {
+            if (lane == 0) status[chunk] = (chunk == 0 ? kScanPrefix : kScanAggregate) | chunk_total;
+            uint32_t before = 0;
+            if (chunk > 0) {
+                int p = chunk - 1;   // nearest predecessor not yet accounted for
+                while (true) {
+                    const int idx = p - lane;
+                    const uint32_t v = idx >= 0 ? status[idx] : kScanPrefix;   // virtual zero prefix in front of chunk 0
+                    const unsigned not_ready = __ballot_sync(0xffffffffu, (v & ~kScanMask) == 0);
+                    const unsigned is_prefix = __ballot_sync(0xffffffffu, (v & ~kScanMask) == kScanPrefix);
+                    const int first_nr = not_ready ? __ffs(not_ready) - 1 : 32;
+                    const int first_pf = is_prefix ? __ffs(is_prefix) - 1 : 32;
+                    const int take = min(first_nr, first_pf < 32 ? first_pf + 1 : 32);   // lanes [0, take) are usable
+                    const uint32_t part = __reduce_add_sync(0xffffffffu, lane < take ? (v & kScanMask) : 0u);
+                    before += part;
+                    if (first_pf < first_nr) break;
+                    p -= take;
+                }
+                if (lane == 0) status[chunk] = kScanPrefix | (before + chunk_total);
             }
+            if (lane == 0) s_base = before;
+        }
+        __syncthreads();
+        uint32_t off = s_base + warp_excl + incl_all - cnt;
+        if (cnt > kBigTiles) {
+            big_list[atomicAdd(&counters[kCntBig], 1u)] = make_uint2((uint32_t)i, off);
+            cnt = 0;
         }
         uint32_t incl = cnt;
 #pragma unroll
@@ -234,17 +297,17 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, int gx, cons
 
 // one CTA per queued big Gaussian (grid-stride)
 __global__ void __launch_bounds__(256) emit_big_kernel(int gx, const uint32_t *__restrict__ sorted_idx,
-                                                       const uint32_t *__restrict__ offsets,
                                                        const uint32_t *__restrict__ tiles_touched,
                                                        const ushort4 *__restrict__ rect, const uint32_t *__restrict__ counters,
-                                                       int64_t capacity, const uint32_t *__restrict__ big_list,
+                                                       int64_t capacity, const uint2 *__restrict__ big_list,
                                                        uint32_t *__restrict__ tile_out, uint32_t *__restrict__ gid_out) {
     const uint32_t nbig = counters[kCntBig];
     for (uint32_t e = blockIdx.x; e < nbig; e += gridDim.x) {
-        const uint32_t i = big_list[e], g = sorted_idx[i], cnt = tiles_touched[g];
+        const uint2 entry = big_list[e];
+        const uint32_t g = sorted_idx[entry.x], cnt = tiles_touched[g];
         const ushort4 r = rect[g];
         const uint32_t w = (uint32_t)(r.z - r.x);
-        const int64_t off = offsets[i];
+        const int64_t off = entry.y;
         for (uint32_t local = threadIdx.x; local < cnt; local += blockDim.x) {
             const int64_t pos = off + local;
             if (pos < capacity) {
@@ -277,14 +340,28 @@ __device__ __forceinline__ int weight_bucket(uint32_t w) {
     return 1 + 4 * e + m;
 }
 
+constexpr int kOrderPerThread = 16;   // 1024 threads x 16 = 16384 tiles per pass (a 4K image has 32400: the loop repeats)
+
 __global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t *__restrict__ weight, const uint2 *__restrict__ ranges,
                                                           int tiles, uint32_t *__restrict__ order) {
     __shared__ uint32_t hist[132], base[132];
     for (int b = threadIdx.x; b < 132; b += blockDim.x) hist[b] = 0;
     __syncthreads();
-    for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
-        const uint32_t w = weight ? weight[t] : ranges[t].y - ranges[t].x;
-        atomicAdd(&hist[weight_bucket(w)], 1u);
+    // all loads of a thread are issued before the first shared-memory atomic (the kernel is pure latency otherwise)
+    for (int t0 = 0; t0 < tiles; t0 += 1024 * kOrderPerThread) {
+        int bkt[kOrderPerThread];
+#pragma unroll
+        for (int e = 0; e < kOrderPerThread; ++e) {
+            const int t = t0 + e * 1024 + threadIdx.x;
+            bkt[e] = t < tiles ? weight_bucket(weight ? weight[t] : ranges[t].y - ranges[t].x) : -1;
+        }
+#pragma unroll
+        for (int e = 0; e < kOrderPerThread; ++e) {
+            // empty tiles are the majority: one atomic per warp for bucket 0
+            const unsigned zeros = __ballot_sync(0xffffffffu, bkt[e] == 0);
+            if (bkt[e] > 0) atomicAdd(&hist[bkt[e]], 1u);
+            else if (bkt[e] == 0 && (threadIdx.x & 31) == __ffs(zeros) - 1) atomicAdd(&hist[0], (uint32_t)__popc(zeros));
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -292,9 +369,23 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t *__rest
         for (int b = 131; b >= 0; --b) { base[b] = run; run += hist[b]; }
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
-        const uint32_t w = weight ? weight[t] : ranges[t].y - ranges[t].x;
-        order[atomicAdd(&base[weight_bucket(w)], 1u)] = (uint32_t)t;
+    for (int t0 = 0; t0 < tiles; t0 += 1024 * kOrderPerThread) {
+        int bkt[kOrderPerThread];
+#pragma unroll
+        for (int e = 0; e < kOrderPerThread; ++e) {
+            const int t = t0 + e * 1024 + threadIdx.x;
+            bkt[e] = t < tiles ? weight_bucket(weight ? weight[t] : ranges[t].y - ranges[t].x) : -1;
+        }
+#pragma unroll
+        for (int e = 0; e < kOrderPerThread; ++e) {
+            const unsigned zeros = __ballot_sync(0xffffffffu, bkt[e] == 0);
+            const int leader = __ffs(zeros) - 1;
+            uint32_t zstart = 0;
+            if (bkt[e] == 0 && (int)(threadIdx.x & 31) == leader) zstart = atomicAdd(&base[0], (uint32_t)__popc(zeros));
+            if (zeros) zstart = __shfl_sync(0xffffffffu, zstart, leader);
+            if (bkt[e] > 0) order[atomicAdd(&base[bkt[e]], 1u)] = (uint32_t)(t0 + e * 1024 + threadIdx.x);
+            else if (bkt[e] == 0) order[zstart + __popc(zeros & lanemask_lt())] = (uint32_t)(t0 + e * 1024 + threadIdx.x);
+        }
     }
 }
 
@@ -339,15 +430,15 @@ int build_instances(const mb_raster_inputs *in, const RasterDims &d, const GeomS
     MB_CUDA(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)d.tiles, s));
     {
     KernelTimer kt("emit_instances", s);
-    emit_instances_kernel<<<grid_p, 256, 0, s>>>(d.P, d.gx, g.sorted_idx, g.offsets, g.tiles_touched, g.rect, g.counters,
+    emit_instances_kernel<<<grid_p, 256, 0, s>>>(d.P, d.gx, g.sorted_idx, g.tiles_touched, g.rect, g.counters, g.scan_status,
                                                  capacity, b.tile_a, b.gid_a, g.big_list);
     }
     int rc = check_launch("emit_instances", dbg, s);
     if (rc) return rc;
     {
     KernelTimer kt("emit_big", s);
-    emit_big_kernel<<<sm_count() * 2, 256, 0, s>>>(d.gx, g.sorted_idx, g.offsets, g.tiles_touched, g.rect, g.counters, capacity,
-                                                  g.big_list, b.tile_a, b.gid_a);
+    emit_big_kernel<<<sm_count() * 2, 256, 0, s>>>(d.gx, g.sorted_idx, g.tiles_touched, g.rect, g.counters, capacity, g.big_list,
+                                                  b.tile_a, b.gid_a);
     }
     rc = check_launch("emit_big", dbg, s);
     if (rc) return rc;
@@ -388,7 +479,8 @@ extern "C" int mb_raster_forward_geom(const mb_raster_inputs *in, void *geom, si
         return MB_ERR_WORKSPACE;
     }
     const bool dbg = in->debug != 0;
-    MB_CUDA(cudaMemsetAsync(g.counters, 0, sizeof(uint32_t) * kNumCounters, s));
+    // counters + look-back words of the instance-offset scan (contiguous)
+    MB_CUDA(cudaMemsetAsync(g.counters, 0, (size_t)((char *)(g.scan_status + (d.P + 255) / 256 + 1) - (char *)g.counters), s));
     if (d.P > 0) {
         PreArgs a;
         a.P = d.P; a.W = d.W; a.H = d.H; a.gx = d.gx; a.gy = d.gy; a.deg = in->sh_degree; a.M = in->sh_coeffs;
@@ -412,10 +504,6 @@ extern "C" int mb_raster_forward_geom(const mb_raster_inputs *in, void *geom, si
         // depth order (stable; culled Gaussians carry key 0xffffffff and sink to the end)
         SortWorkspace ws = carve_sort_workspace(g.sort_ws, d.P);
         rc = radix_sort_pairs(g.depth_key, g.ident, g.sorted_key, g.sorted_idx, d.P, nullptr, d.P, 0, 32, ws, s, dbg);
-        if (rc) return rc;
-        // instance offsets in depth order; total = num_rendered
-        rc = exclusive_scan_gather(g.tiles_touched, g.sorted_idx, g.offsets, g.counters + kCntRendered, d.P, g.scan_partials,
-                                   s, dbg);
         if (rc) return rc;
     }
     if (num_rendered_host) {

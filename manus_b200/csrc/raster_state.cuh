@@ -3,7 +3,7 @@
 // HBM layout (all arrays 256-B aligned inside their buffer):
 //   geom    (per Gaussian, P rows)  : 48-B blend record | cov3D f32x6 (scale/rotation mode only) | tiles u32 | tile rect u16x4 |
 //                                     SH clamp mask u32 | depth key u32 | identity idx u32 | depth-sorted key/idx u32 |
-//                                     instance offsets (depth order) u32 | scan partials | sort workspace | counters
+//                                     sort workspace | counters + look-back words of the instance-offset scan
 //   binning (per instance, D rows)  : tile id u32 x2 (ping-pong) | gaussian id u32 x2 (ping-pong; the sorted one is the per-tile
 //                                     depth-ordered list the tile kernels walk) | sort workspace
 //   image   (per pixel / per tile)  : final_T f32 | n_contrib u32 | tile range u32x2 | deepest last-contributor per tile u32 |
@@ -21,7 +21,7 @@
 
 namespace mb {
 
-enum Counter { kCntRendered = 0, kCntVisible = 1, kCntOverflow = 2, kCntTileCursor = 3, kCntBwdCursor = 4, kCntBig = 5, kNumCounters = 16 };
+enum Counter { kCntRendered = 0, kCntVisible = 1, kCntOverflow = 2, kCntTileCursor = 3, kCntBwdCursor = 4, kCntBig = 5, kCntEmitCursor = 6, kNumCounters = 16 };
 
 struct Record {   // 48 bytes, 16-B aligned
     float4 a;     // x, y, conic.x, conic.y
@@ -37,8 +37,9 @@ struct GeomState {
     uint32_t *tiles_touched;
     ushort4 *rect;     // tile rectangle (x0, y0, x1, y1), exclusive upper bounds
     uint32_t *clamped;
-    uint32_t *depth_key, *ident, *sorted_key, *sorted_idx, *offsets, *scan_partials;
-    uint32_t *big_list;   // depth-order indices of the Gaussians that cover more than kBigTiles tiles
+    uint32_t *scan_status;   // [ceil(P/256)] look-back words of the instance-offset scan (zeroed with the counters)
+    uint32_t *depth_key, *ident, *sorted_key, *sorted_idx;
+    uint2 *big_list;   // (depth-order index, instance offset) of the Gaussians that cover more than kBigTiles tiles
     void *sort_ws;
     size_t bytes;
 
@@ -47,6 +48,7 @@ struct GeomState {
         GeomState g;
         const size_t n = (size_t)(P > 0 ? P : 1);
         g.counters = c.take<uint32_t>(kNumCounters);
+        g.scan_status = c.take<uint32_t>((n + 255) / 256 + 1);
         g.rec = c.take<Record>(n);
         g.cov3D = c.take<float>(6 * n);
         g.tiles_touched = c.take<uint32_t>(n);
@@ -56,9 +58,7 @@ struct GeomState {
         g.ident = c.take<uint32_t>(n);
         g.sorted_key = c.take<uint32_t>(n);
         g.sorted_idx = c.take<uint32_t>(n);
-        g.offsets = c.take<uint32_t>(n);
-        g.scan_partials = c.take<uint32_t>((size_t)scan_blocks((int64_t)n) + 1);
-        g.big_list = c.take<uint32_t>(n);
+        g.big_list = c.take<uint2>(n);
         g.sort_ws = c.take<char>(sort_workspace_bytes((int64_t)n));
         g.bytes = c.off;
         return g;
