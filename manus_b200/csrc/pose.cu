@@ -14,6 +14,8 @@
 //
 // HBM bytes per Gaussian (fp32, K=16, B bones): forward 236 + 4B read, 52 written; backward re-reads the parameters
 // and the 52 B of upstream gradients and writes 236 B of parameter gradients.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mb {
@@ -23,7 +25,7 @@ constexpr int kMaxBones = 64;
 constexpr int kMaxArrays = 12;
 
 struct PoseArgs {
-    int N, n_skinned, B, deg, K, iso;
+    int N, n_skinned, B, deg, K, iso, stages;
     const float *xyz, *log_scale, *quat, *opacity_logit, *f_dc, *f_rest, *skin, *bone_tf, *campos;
     // forward outputs
     float *posed_xyz, *cov6, *colors, *opacity, *tf_out;
@@ -59,9 +61,19 @@ __host__ __device__ inline TileLayout tile_layout(int K, int B, int iso, bool ba
     return L;
 }
 
-inline size_t pose_smem_bytes(int B, int K, int iso, bool backward) {
-    // bones (13 floats each) + camera + 2 mbarriers, then two tile stages
-    return sizeof(float) * ((size_t)kMaxBones * 13 + 8) + 2 * sizeof(float) * (size_t)tile_layout(K, B, iso, backward).floats;
+inline size_t pose_smem_bytes(int B, int K, int iso, bool backward, int stages) {
+    // bones (13 floats each) + camera + 2 mbarriers, then the tile stage(s)
+    return sizeof(float) * ((size_t)kMaxBones * 13 + 8) + stages * sizeof(float) * (size_t)tile_layout(K, B, iso, backward).floats;
+}
+
+// 1 = one stage per CTA and twice the CTAs per SM (default), 2 = double-buffered stages inside a CTA
+static int pose_stages() {
+    static int cached = 0;
+    if (!cached) {
+        const char *e = getenv("MB_POSE_STAGES");
+        cached = (e && atoi(e) == 2) ? 2 : 1;
+    }
+    return cached;
 }
 
 struct Transfer {   // one dense array of a tile: global <-> shared
@@ -289,20 +301,36 @@ __device__ __forceinline__ void run_tiles(const PoseArgs &a, float *smem, Body b
     }
     __syncthreads();
     const int ntiles = (a.N + kPoseThreads - 1) / kPoseThreads;
-    if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) pipe.prefetch(blockIdx.x, 0);
-    int k = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
-        const int next = tile + gridDim.x;
-        if (threadIdx.x == 0 && next < ntiles) {
-            bulk_wait_read_all();   // the stores of two tiles ago have finished reading the stage that is refilled now
-            pipe.prefetch(next, k + 1);
+    if (a.stages == 1) {
+        // one stage per CTA, more CTAs per SM: the loads of one CTA overlap the arithmetic of the others
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            __syncthreads();            // plain-path stores of the previous tile have read the stage
+            if (threadIdx.x == 0) {
+                bulk_wait_read_all();   // the bulk stores of the previous tile have finished reading the stage
+                pipe.prefetch(tile, 0);
+            }
+            __syncthreads();
+            pipe.acquire(tile, 0, phase);
+            const int row = threadIdx.x, i = tile * kPoseThreads + row;
+            if (i < a.N) body(pipe.L, pipe.stage(0), i, row, bones_s, cam_s);
+            pipe.release(tile, 0);
         }
-        pipe.acquire(tile, k, phase);
-        const int row = threadIdx.x, i = tile * kPoseThreads + row;
-        if (i < a.N) body(pipe.L, pipe.stage(k), i, row, bones_s, cam_s);
-        pipe.release(tile, k);
-        __syncthreads();   // plain-path stores have read the stage before it is refilled
+    } else {
+        if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) pipe.prefetch(blockIdx.x, 0);
+        int k = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+            const int next = tile + gridDim.x;
+            if (threadIdx.x == 0 && next < ntiles) {
+                bulk_wait_read_all();   // the stores of two tiles ago have finished reading the stage that is refilled now
+                pipe.prefetch(next, k + 1);
+            }
+            pipe.acquire(tile, k, phase);
+            const int row = threadIdx.x, i = tile * kPoseThreads + row;
+            if (i < a.N) body(pipe.L, pipe.stage(k), i, row, bones_s, cam_s);
+            pipe.release(tile, k);
+            __syncthreads();   // plain-path stores have read the stage before it is refilled
+        }
     }
     if (threadIdx.x == 0) bulk_wait_all();
 }
@@ -524,8 +552,9 @@ static PoseArgs pose_args(const mb_pose_inputs *in) {
 }
 
 template <int DEG>
-static int launch_pose(const PoseArgs &a, bool backward, cudaStream_t s) {
-    const size_t smem = pose_smem_bytes(a.B, a.K, a.iso, backward);
+static int launch_pose(PoseArgs a, bool backward, cudaStream_t s) {
+    a.stages = pose_stages();
+    const size_t smem = pose_smem_bytes(a.B, a.K, a.iso, backward, a.stages);
     const int ntiles = (a.N + kPoseThreads - 1) / kPoseThreads;
     int per_sm = (int)((size_t)(220 * 1024) / smem);
     if (per_sm < 1) {

@@ -538,7 +538,8 @@ static int blend_warps() {
     static int cached = 0;
     if (!cached) {
         const char *e = getenv("MB_BLEND_WARPS");
-        cached = (e && atoi(e) == 8) ? 8 : 4;
+        const int v = e ? atoi(e) : 4;
+        cached = (v == 8 || v == 2) ? v : 4;
     }
     return cached;
 }
@@ -580,13 +581,13 @@ extern "C" int mb_raster_forward_render(const mb_raster_inputs *in, void *geom, 
                   image_bytes, im.bytes);
         return MB_ERR_WORKSPACE;
     }
-    MB_CUDA(cudaMemsetAsync(im.ranges, 0, (size_t)((char *)im.order_fwd - (char *)im.ranges), s));   // ranges + tile_maxlast
+    MB_CUDA(cudaMemsetAsync(im.ranges, 0, (size_t)((char *)im.order_fwd - (char *)im.ranges), s));   // ranges + tile_maxlast + order workspace
     const bool dbg = in->debug != 0;
     const uint32_t *order = nullptr;
     if (d.P > 0 && capacity > 0) {
         rc = build_instances(in, d, g, b, im, capacity, s);
         if (rc) return rc;
-        rc = tile_order(nullptr, im.ranges, d.tiles, im.order_fwd, s, dbg);
+        rc = tile_order(nullptr, im.ranges, d.tiles, im.order_fwd, im.order_ws, s, dbg);
         if (rc) return rc;
         order = im.order_fwd;
     }
@@ -595,6 +596,9 @@ extern "C" int mb_raster_forward_render(const mb_raster_inputs *in, void *geom, 
         if (blend_warps() == 4)
             blend_forward_kernel<4><<<d.tiles * 2, 128, 0, s>>>(g.rec, b.gid_b, im.ranges, order, d.W, d.H, d.gx, in->background,
                                                                 out_color, im.final_T, im.n_contrib, im.tile_maxlast);
+        else if (blend_warps() == 2)
+            blend_forward_kernel<2><<<d.tiles * 4, 64, 0, s>>>(g.rec, b.gid_b, im.ranges, order, d.W, d.H, d.gx, in->background,
+                                                               out_color, im.final_T, im.n_contrib, im.tile_maxlast);
         else
             blend_forward_kernel<8><<<d.tiles, 256, 0, s>>>(g.rec, b.gid_b, im.ranges, order, d.W, d.H, d.gx, in->background,
                                                             out_color, im.final_T, im.n_contrib, im.tile_maxlast);
@@ -632,7 +636,7 @@ extern "C" int mb_raster_backward(const mb_raster_inputs *in, const int32_t *rad
     float *acc = reinterpret_cast<float *>(grad_scratch);
     MB_CUDA(cudaMemsetAsync(acc, 0, (size_t)d.P * kAccStride * sizeof(float), s));
     if (capacity > 0) {
-        rc = tile_order(im.tile_maxlast, nullptr, d.tiles, im.order_bwd, s, dbg);
+        rc = tile_order(im.tile_maxlast, nullptr, d.tiles, im.order_bwd, im.order_ws + kOrderWs, s, dbg);
         if (rc) return rc;
         {
             KernelTimer kt("blend_backward", s);
@@ -640,6 +644,10 @@ extern "C" int mb_raster_backward(const mb_raster_inputs *in, const int32_t *rad
                 blend_backward_kernel<4><<<d.tiles * 2, 128, 0, s>>>(g.rec, b.gid_b, im.ranges, im.order_bwd, im.tile_maxlast, d.W, d.H,
                                                                      d.gx, in->background, im.final_T, im.n_contrib, dL_dout,
                                                                      stride_c, stride_y, stride_x, acc);
+            else if (blend_warps() == 2)
+                blend_backward_kernel<2><<<d.tiles * 4, 64, 0, s>>>(g.rec, b.gid_b, im.ranges, im.order_bwd, im.tile_maxlast, d.W, d.H,
+                                                                    d.gx, in->background, im.final_T, im.n_contrib, dL_dout,
+                                                                    stride_c, stride_y, stride_x, acc);
             else
                 blend_backward_kernel<8><<<d.tiles, 256, 0, s>>>(g.rec, b.gid_b, im.ranges, im.order_bwd, im.tile_maxlast, d.W, d.H,
                                                                  d.gx, in->background, im.final_T, im.n_contrib, dL_dout, stride_c,

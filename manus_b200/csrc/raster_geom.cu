@@ -332,7 +332,9 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t *__rest
 }
 
 // Work order of the tile kernels: tiles by descending weight (list length for the forward, deepest last-contributor for
-// the backward) so that the longest lists start first.  Counting sort over 129 quarter-octave buckets, single CTA.
+// the backward) so that the longest lists start first.  Counting sort over 129 quarter-octave buckets in ONE launch of a
+// few co-resident CTAs: bucket counts go to global memory, the CTAs meet at an arrival counter, then every tile takes the
+// next slot of its bucket (the order inside a bucket does not matter).  The last CTA to leave clears the workspace.
 __device__ __forceinline__ int weight_bucket(uint32_t w) {
     if (w == 0) return 0;
     const int e = 31 - __clz(w);
@@ -340,58 +342,83 @@ __device__ __forceinline__ int weight_bucket(uint32_t w) {
     return 1 + 4 * e + m;
 }
 
-constexpr int kOrderPerThread = 16;   // 1024 threads x 16 = 16384 tiles per pass (a 4K image has 32400: the loop repeats)
+constexpr int kOrderThreads = 256;
 
-__global__ void __launch_bounds__(1024) tile_order_kernel(const uint32_t *__restrict__ weight, const uint2 *__restrict__ ranges,
-                                                          int tiles, uint32_t *__restrict__ order) {
-    __shared__ uint32_t hist[132], base[132];
-    for (int b = threadIdx.x; b < 132; b += blockDim.x) hist[b] = 0;
+__global__ void __launch_bounds__(kOrderThreads) tile_order_kernel(const uint32_t *__restrict__ weight, const uint2 *__restrict__ ranges,
+                                                                   int tiles, uint32_t *__restrict__ order, uint32_t *ws) {
+    __shared__ uint32_t hist[kOrderBuckets], base[kOrderBuckets];
+    __shared__ bool s_last;
+    uint32_t *g_hist = ws, *g_cursor = ws + kOrderBuckets;
+    volatile uint32_t *arrive = ws + 2 * kOrderBuckets;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int b = tid; b < kOrderBuckets; b += kOrderThreads) hist[b] = 0;
     __syncthreads();
-    // all loads of a thread are issued before the first shared-memory atomic (the kernel is pure latency otherwise)
-    for (int t0 = 0; t0 < tiles; t0 += 1024 * kOrderPerThread) {
-        int bkt[kOrderPerThread];
-#pragma unroll
-        for (int e = 0; e < kOrderPerThread; ++e) {
-            const int t = t0 + e * 1024 + threadIdx.x;
-            bkt[e] = t < tiles ? weight_bucket(weight ? weight[t] : ranges[t].y - ranges[t].x) : -1;
-        }
-#pragma unroll
-        for (int e = 0; e < kOrderPerThread; ++e) {
-            // empty tiles are the majority: one atomic per warp for bucket 0
-            const unsigned zeros = __ballot_sync(0xffffffffu, bkt[e] == 0);
-            if (bkt[e] > 0) atomicAdd(&hist[bkt[e]], 1u);
-            else if (bkt[e] == 0 && (threadIdx.x & 31) == __ffs(zeros) - 1) atomicAdd(&hist[0], (uint32_t)__popc(zeros));
-        }
+    const int stride = gridDim.x * kOrderThreads;
+    for (int t0 = blockIdx.x * kOrderThreads; t0 < tiles; t0 += stride) {
+        const int t = t0 + tid;
+        const int bkt = t < tiles ? weight_bucket(weight ? weight[t] : ranges[t].y - ranges[t].x) : -1;
+        // empty tiles are the majority: one atomic per warp for bucket 0
+        const unsigned zeros = __ballot_sync(0xffffffffu, bkt == 0);
+        if (bkt > 0) atomicAdd(&hist[bkt], 1u);
+        else if (bkt == 0 && lane == __ffs(zeros) - 1) atomicAdd(&hist[0], (uint32_t)__popc(zeros));
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    for (int b = tid; b < kOrderBuckets; b += kOrderThreads)
+        if (hist[b]) atomicAdd(&g_hist[b], hist[b]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        atomicAdd((uint32_t *)arrive, 1u);
+        while (arrive[0] < gridDim.x) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    // start of every bucket in the descending order
+    if (tid < 32) {
         uint32_t run = 0;
-        for (int b = 131; b >= 0; --b) { base[b] = run; run += hist[b]; }
+        for (int b0 = kOrderBuckets - 1; b0 >= 0; b0 -= 32) {
+            const int b = b0 - lane;
+            const uint32_t v = b >= 0 ? __ldcg(&g_hist[b]) : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (b >= 0) base[b] = run + incl - v;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
     }
     __syncthreads();
-    for (int t0 = 0; t0 < tiles; t0 += 1024 * kOrderPerThread) {
-        int bkt[kOrderPerThread];
-#pragma unroll
-        for (int e = 0; e < kOrderPerThread; ++e) {
-            const int t = t0 + e * 1024 + threadIdx.x;
-            bkt[e] = t < tiles ? weight_bucket(weight ? weight[t] : ranges[t].y - ranges[t].x) : -1;
-        }
-#pragma unroll
-        for (int e = 0; e < kOrderPerThread; ++e) {
-            const unsigned zeros = __ballot_sync(0xffffffffu, bkt[e] == 0);
-            const int leader = __ffs(zeros) - 1;
-            uint32_t zstart = 0;
-            if (bkt[e] == 0 && (int)(threadIdx.x & 31) == leader) zstart = atomicAdd(&base[0], (uint32_t)__popc(zeros));
-            if (zeros) zstart = __shfl_sync(0xffffffffu, zstart, leader);
-            if (bkt[e] > 0) order[atomicAdd(&base[bkt[e]], 1u)] = (uint32_t)(t0 + e * 1024 + threadIdx.x);
-            else if (bkt[e] == 0) order[zstart + __popc(zeros & lanemask_lt())] = (uint32_t)(t0 + e * 1024 + threadIdx.x);
-        }
+    for (int t0 = blockIdx.x * kOrderThreads; t0 < tiles; t0 += stride) {
+        const int t = t0 + tid;
+        const int bkt = t < tiles ? weight_bucket(weight ? weight[t] : ranges[t].y - ranges[t].x) : -1;
+        const unsigned zeros = __ballot_sync(0xffffffffu, bkt == 0);
+        const int leader = __ffs(zeros) - 1;
+        uint32_t zstart = 0;
+        if (bkt == 0 && lane == leader) zstart = atomicAdd(&g_cursor[0], (uint32_t)__popc(zeros));
+        if (zeros) zstart = __shfl_sync(0xffffffffu, zstart, leader);
+        if (bkt > 0) order[base[bkt] + atomicAdd(&g_cursor[bkt], 1u)] = (uint32_t)t;
+        else if (bkt == 0) order[base[0] + zstart + __popc(zeros & lanemask_lt())] = (uint32_t)t;
     }
+    // leave the workspace zeroed for the next launch
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd((uint32_t *)arrive + 1, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last)
+        for (int b = tid; b < kOrderWs; b += kOrderThreads) ws[b] = 0;
 }
 
-int tile_order(const uint32_t *weight_or_null, const uint2 *ranges_or_null, int tiles, uint32_t *order, cudaStream_t s, bool debug) {
+int tile_order(const uint32_t *weight_or_null, const uint2 *ranges_or_null, int tiles, uint32_t *order, uint32_t *ws,
+               cudaStream_t s, bool debug) {
     KernelTimer kt("tile_order", s);
-    tile_order_kernel<<<1, 1024, 0, s>>>(weight_or_null, ranges_or_null, tiles, order);
+    // every CTA must be resident at the same time (they wait for each other): at most one CTA per SM
+    const int grid = max(1, min((tiles + kOrderThreads - 1) / kOrderThreads, sm_count()));
+    tile_order_kernel<<<grid, kOrderThreads, 0, s>>>(weight_or_null, ranges_or_null, tiles, order, ws);
     return check_launch("tile_order", debug, s);
 }
 

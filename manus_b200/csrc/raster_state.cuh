@@ -87,11 +87,15 @@ struct BinningState {
     }
 };
 
+constexpr int kOrderBuckets = 132;            // quarter-octave weight buckets of tile_order
+constexpr int kOrderWs = 2 * kOrderBuckets + 8;   // counts | cursors | arrival counters
+
 struct ImageState {
     float *final_T;          // [H*W]
     uint32_t *n_contrib;     // [H*W]
     uint2 *ranges;           // [tiles] (start, end) into the sorted id list
     uint32_t *tile_maxlast;  // [tiles] max over the tile's pixels of n_contrib (how far the backward has to walk)
+    uint32_t *order_ws;      // [2][kOrderWs] bucket counts / cursors / arrival counters of the two tile_order launches (kept zero)
     uint32_t *order_fwd;     // [tiles] tiles by descending list length
     uint32_t *order_bwd;     // [tiles] tiles by descending tile_maxlast
     size_t bytes;
@@ -105,6 +109,7 @@ struct ImageState {
         s.n_contrib = c.take<uint32_t>(px ? px : 1);
         s.ranges = c.take<uint2>(tiles ? tiles : 1);
         s.tile_maxlast = c.take<uint32_t>(tiles ? tiles : 1);
+        s.order_ws = c.take<uint32_t>(2 * kOrderWs);
         s.order_fwd = c.take<uint32_t>(tiles ? tiles : 1);
         s.order_bwd = c.take<uint32_t>(tiles ? tiles : 1);
         s.bytes = c.off;
@@ -133,7 +138,9 @@ inline RasterDims raster_dims(const mb_raster_inputs *in) {
 
 int validate_raster_inputs(const mb_raster_inputs *in, const char *who);
 
-// order[i] = tile with the i-th largest weight (approximately: descending power-of-two-ish buckets); single CTA
-int tile_order(const uint32_t *weight_or_null, const uint2 *ranges_or_null, int tiles, uint32_t *order, cudaStream_t s, bool debug);
+// order[i] = tile with the i-th largest weight (approximately: descending quarter-octave buckets).  `ws` = kOrderWs zeroed
+// words; the kernel leaves them zeroed again.
+int tile_order(const uint32_t *weight_or_null, const uint2 *ranges_or_null, int tiles, uint32_t *order, uint32_t *ws,
+               cudaStream_t s, bool debug);
 
 }  // namespace mb

@@ -43,8 +43,12 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t
         if (h[p][tid]) atomicAdd(&hist[p * 256 + tid], h[p][tid]);
 }
 
-constexpr uint32_t kFlagAggregate = 1u << 30, kFlagPrefix = 2u << 30, kCountMask = (1u << 30) - 1u;
+enum : uint32_t { kFlagAggregate = 1u << 30, kFlagPrefix = 2u << 30, kCountMask = (1u << 30) - 1u };
+constexpr int kLookBack = 8;   // predecessors polled per look-back step (independent loads: one L2 round trip per step)
 
+// One radix pass over one chunk per CTA.  Ranks are stable; the chunk is first reordered in shared memory (digit-major),
+// so that the scatter to global memory writes runs of consecutive addresses, and the (key, value) pairs are parked there
+// while the look-back for the counts of the earlier chunks is in flight.
 __global__ void __launch_bounds__(kSortThreads) radix_pass_kernel(const uint32_t *__restrict__ keys_in,
                                                                   const uint32_t *__restrict__ vals_in,
                                                                   uint32_t *__restrict__ keys_out,
@@ -56,8 +60,9 @@ __global__ void __launch_bounds__(kSortThreads) radix_pass_kernel(const uint32_t
     const int64_t nchunks = (n + kSortChunk - 1) / kSortChunk;
     __shared__ uint32_t warp_cnt[kSortWarps][256];
     __shared__ uint32_t base_s[256];
-    __shared__ uint32_t scan_s[kSortWarps];
+    __shared__ uint32_t scan_s[2][kSortWarps];
     __shared__ uint32_t chunk_s;
+    __shared__ uint32_t keys_s[kSortChunk], vals_s[kSortChunk];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = lanemask_lt();
     if (tid == 0) chunk_s = atomicAdd(cursor, 1u);
@@ -66,18 +71,24 @@ __global__ void __launch_bounds__(kSortThreads) radix_pass_kernel(const uint32_t
     __syncthreads();
     const int64_t chunk = chunk_s;
     if (chunk >= nchunks) return;
+    const int64_t chunk_base = chunk * kSortChunk;
+    const int nvalid = (int)(n - chunk_base < kSortChunk ? n - chunk_base : kSortChunk);
     // stable rank of every key among the keys of its warp's 512-element slice with the same digit
-    const int64_t base = chunk * kSortChunk + (int64_t)warp * (32 * kSortItems);
-    uint32_t key[kSortItems], rank[kSortItems];
+    const int wbase = warp * (32 * kSortItems);
+    uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        const int64_t idx = base + r * 32 + lane;
-        key[r] = idx < n ? keys_in[idx] : 0xffffffffu;
+        const int e = wbase + r * 32 + lane;
+        key[r] = e < nvalid ? keys_in[chunk_base + e] : 0xffffffffu;
     }
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        const int64_t idx = base + r * 32 + lane;
-        const bool valid = idx < n;
+        const int e = wbase + r * 32 + lane;
+        val[r] = e < nvalid ? vals_in[chunk_base + e] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const bool valid = wbase + r * 32 + lane < nvalid;
         const uint32_t digit = valid ? ((key[r] >> shift) & 255u) : 256u;
         const uint32_t peers = __match_any_sync(0xffffffffu, digit);
         const int leader = __ffs(peers) - 1;
@@ -100,47 +111,74 @@ __global__ void __launch_bounds__(kSortThreads) radix_pass_kernel(const uint32_t
         mine += t;
     }
     status[chunk * 256 + tid] = (chunk == 0 ? kFlagPrefix : kFlagAggregate) | mine;
-    // first global position of the digit = exclusive prefix of the digit histogram (block scan of 256 values)
-    uint32_t digit_base;
+    // two block scans of 256 values at once: first global position of the digit (histogram of all keys) and first
+    // position of the digit inside this chunk
+    uint32_t digit_base, local_start;
     {
         const uint32_t v = hist[tid];
-        uint32_t incl = v;
+        uint32_t incl = v, incl_l = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o), tl = __shfl_up_sync(0xffffffffu, incl_l, o);
+            if (lane >= o) { incl += t; incl_l += tl; }
         }
-        if (lane == 31) scan_s[warp] = incl;
-        __syncthreads();
-        uint32_t wp = 0;
+        if (lane == 31) { scan_s[0][warp] = incl; scan_s[1][warp] = incl_l; }
+        __syncthreads();     // also: every thread has read its warp_cnt column before the prefixes are used below
+        uint32_t wp = 0, wpl = 0;
 #pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) wp += (w < warp) ? scan_s[w] : 0u;
-        digit_base = wp + incl - v;
-    }
-    // decoupled look-back: keys with this digit in all earlier chunks
-    uint32_t before = 0;
-    if (chunk > 0) {
-        int64_t p = chunk - 1;
-        while (true) {
-            const uint32_t v = status[p * 256 + tid];
-            const uint32_t f = v & ~kCountMask;
-            if (f == 0) continue;   // predecessor has not published yet (it is running: chunk ids are handed out in start order)
-            before += v & kCountMask;
-            if (f == kFlagPrefix) break;
-            --p;
+        for (int w = 0; w < kSortWarps; ++w) {
+            wp += (w < warp) ? scan_s[0][w] : 0u;
+            wpl += (w < warp) ? scan_s[1][w] : 0u;
         }
-        status[chunk * 256 + tid] = kFlagPrefix | (before + mine);
+        digit_base = wp + incl - v;
+        local_start = wpl + incl_l - mine;
     }
-    base_s[tid] = digit_base + before;
+    base_s[tid] = local_start;
+    __syncthreads();
+    // park the pairs digit-major in shared memory
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        if (wbase + r * 32 + lane < nvalid) {
+            const uint32_t digit = (key[r] >> shift) & 255u;
+            const uint32_t lp = base_s[digit] + warp_cnt[warp][digit] + rank[r];
+            keys_s[lp] = key[r];
+            vals_s[lp] = val[r];
+        }
+    }
+    // decoupled look-back: keys with this digit in all earlier chunks (kLookBack status words per step)
+    uint32_t before = 0;
+    {
+        int64_t p = chunk - 1;
+        bool found = chunk == 0;
+        while (!found) {
+            uint32_t v[kLookBack];
+#pragma unroll
+            for (int k = 0; k < kLookBack; ++k) v[k] = p - k >= 0 ? status[(p - k) * 256 + tid] : kFlagPrefix;
+            int used = 0;
+#pragma unroll
+            for (int k = 0; k < kLookBack; ++k) {
+                const uint32_t f = v[k] & ~kCountMask;
+                if (used == k && f != 0 && !found) {     // contiguous run of published words, up to the first prefix
+                    before += v[k] & kCountMask;
+                    ++used;
+                    found = f == kFlagPrefix;
+                }
+            }
+            p -= used;
+        }
+        if (chunk > 0) status[chunk * 256 + tid] = kFlagPrefix | (before + mine);
+    }
+    __syncthreads();     // base_s (local starts) has been read by everyone, the parked pairs are complete
+    base_s[tid] = digit_base + before - local_start;     // global position = base_s[digit] + position in the chunk
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        const int64_t idx = base + r * 32 + lane;
-        if (idx < n) {
-            const uint32_t digit = (key[r] >> shift) & 255u;
-            const uint32_t pos = base_s[digit] + warp_cnt[warp][digit] + rank[r];
-            keys_out[pos] = key[r];
-            vals_out[pos] = vals_in[idx];
+        const int lp = r * kSortThreads + tid;
+        if (lp < nvalid) {
+            const uint32_t k = keys_s[lp];
+            const uint32_t pos = base_s[(k >> shift) & 255u] + (uint32_t)lp;
+            if (keys_out) keys_out[pos] = k;
+            vals_out[pos] = vals_s[lp];
         }
     }
 }
