@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--views", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python each step instead of replaying the captured CUDA graph")
     return ap.parse_args()
 
 
@@ -234,21 +235,38 @@ def main():
         _, c, b = r.view_inputs_host(v)
         staged[v] = (c.to(dev), b.to(dev))
 
-    def step_resident(it):
+    # ---- untimed: instance / visible counts of every view (exact mode), then reserve mode (no host read-back per frame)
+    from manus_b200 import rasterizer as _rz
+    from manus_b200.dist import CAM_FLOATS, GraphedStep
+    set_capacity_mode("exact")
+    D_all, V_all = view_counts(r, staged, views)
+    set_capacity_mode("reserve", margin=1.1)
+    _rz.reserve_capacity(dev.index, scene.n, H, W, max(D_all.values()))
+
+    loss_fn = lambda image, target: (image * target).sum()
+    graphed = None if args.no_graph else GraphedStep(r, loss_fn, G_dev, view=views[0])
+
+    def step_resident(it, eager=False):
         v = my_view(it)
-        out = r.render(v, sink=r.flat.grads, cam_dev=staged[v][0], bones_dev=staged[v][1])
-        loss = (out["render"] * G_dev).sum()
-        loss.backward()
+        if graphed is not None and not eager:
+            # the whole step (pose fwd -> raster fwd -> loss -> raster bwd -> pose bwd) is ONE graph launch; the per-view
+            # camera / bones are copied device-to-device into the graph's static inputs
+            graphed.set_inputs(staged[v][0], staged[v][1], None)
+            loss = graphed.replay()
+        else:
+            out = r.render(v, sink=r.flat.grads, cam_dev=staged[v][0], bones_dev=staged[v][1])
+            loss = loss_fn(out["render"], G_dev)
+            loss.backward()
         if world > 1:
             dist.all_reduce(r.flat.grad)
-        return loss, out
+        return loss
 
-    # End-to-end step: the step's inputs (camera 35 floats + fov 2, posed bones 320 floats, target image H*W*3 floats) come
+    # End-to-end step: the step's inputs (packed camera 39 floats, posed bones 320 floats, target image H*W*3 floats) come
     # from pinned host memory every step and the loss is read back every step.  The copies of step i+1 are enqueued on a
     # copy stream while step i computes (double buffered), so the PCIe transfer overlaps the kernels; every copy is inside
     # the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
-    slots = [dict(g=torch.empty_like(G_dev), cam=torch.empty(37, device=dev), bones=torch.empty(320, device=dev),
+    slots = [dict(g=torch.empty_like(G_dev), cam=torch.empty(CAM_FLOATS, device=dev), bones=torch.empty(320, device=dev),
                   ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
 
     def stage_inputs(it):
@@ -268,20 +286,17 @@ def main():
         cur = torch.cuda.current_stream(dev)
         cur.wait_event(slot["ready"])
         stage_inputs(it + 1); slots[(it + 1) % 2]["staged"] = it + 1
-        out = r.render(my_view(it), sink=r.flat.grads, cam_dev=slot["cam"], bones_dev=slot["bones"])
-        loss = (out["render"] * slot["g"]).sum()
-        loss.backward()
+        if graphed is not None:
+            graphed.set_inputs(slot["cam"], slot["bones"], slot["g"])
+            loss = graphed.replay()
+        else:
+            out = r.render(my_view(it), sink=r.flat.grads, cam_dev=slot["cam"], bones_dev=slot["bones"])
+            loss = loss_fn(out["render"], slot["g"])
+            loss.backward()
         if world > 1:
             dist.all_reduce(r.flat.grad)
         slot["free"].record(cur)
         return float(loss.detach())                             # device -> host read of the step's result
-
-    # ---- untimed: instance / visible counts of every view (exact mode), then reserve mode (no host sync per frame)
-    from manus_b200 import rasterizer as _rz
-    set_capacity_mode("exact")
-    D_all, V_all = view_counts(r, staged, views)
-    set_capacity_mode("reserve", margin=1.1)
-    _rz._Plan.high_water[(dev.index, scene.n, H, W)] = max(D_all.values())
 
     def timed(fn, steps, sampler=None):
         for it in range(WU):
@@ -317,12 +332,16 @@ def main():
     ms_step = timed(step_resident, K, sampler)
     clocks = sampler.summary()
     ms_e2e = timed(step_e2e, K)
+    # reserve mode reads nothing back per frame: make sure no timed frame ran out of instance capacity
+    if graphed is not None:
+        graphed.check()
+    _rz.check_overflow()
 
     # ---- per-kernel pass (CUDA events around every launch, on the launching stream): roofline of the dominant kernel
     _lib.profile_enable(True)
     _lib.profile_report()
     for it in range(K):
-        step_resident(WU + it)
+        step_resident(WU + it, eager=True)     # same kernels as the graph, launched one by one so that each can be timed
     torch.cuda.synchronize()
     prof = _lib.profile_report()
     _lib.profile_enable(False)
@@ -345,13 +364,14 @@ def main():
     fbytes = frame_bytes(n_hand, n_obj, D_mean, P)
     value = world * 1e3 / ms_step
     e2e_val = world * 1e3 / ms_e2e
-    h2d = G_host.numel() * 4 + (37 + 320) * 4
+    h2d = G_host.numel() * 4 + (CAM_FLOATS + 320) * 4
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": WU, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
             "gpu_launches": int(round(launches_per_step * K)), "host_enqueue_ms_per_step": host_enqueue_ms,
+            "launch_mode": "eager (one launch per kernel)" if graphed is None else "CUDA graph replay (one launch per step)",
             "roofline": roofline,
             "frame": {"num_rendered_mean": D_mean, "visible_mean": V_mean, "algorithmic_bytes": fbytes,
                       "achieved_gbps": fbytes * (1e3 / ms_step) / 1e9, "frac_of_hbm_peak": fbytes * (1e3 / ms_step) / 1e9 / peak,

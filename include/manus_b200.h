@@ -77,6 +77,9 @@ typedef struct mb_raster_inputs {
     const float *viewmatrix;     /* [16] */
     const float *projmatrix;     /* [16] */
     const float *campos;         /* [3]  */
+    const float *tanfov_dev;     /* optional [2] = (tanfovx, tanfovy) in DEVICE memory; when non-NULL it replaces the two host
+                                    values above, so that one enqueued frame (e.g. a captured CUDA graph) can be replayed with a
+                                    different camera without touching kernel arguments */
 } mb_raster_inputs;
 
 size_t mb_raster_geom_bytes(int32_t num_points);

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmanus_b200.so")
+LIB_PATH = os.environ.get("MANUS_B200_LIB") or os.path.join(_HERE, "lib", "libmanus_b200.so")   # env override: kernel experiments
 
 f32p = C.POINTER(C.c_float)
 i32p = C.POINTER(C.c_int32)
@@ -25,6 +25,7 @@ class RasterInputs(C.Structure):
         ("background", C.c_void_p), ("means3D", C.c_void_p), ("opacities", C.c_void_p), ("colors_precomp", C.c_void_p),
         ("shs", C.c_void_p), ("cov3D_precomp", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
         ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+        ("tanfov_dev", C.c_void_p),
     ]
 
 

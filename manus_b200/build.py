@@ -36,6 +36,26 @@ def _deps_mtime() -> float:
     return max(os.path.getmtime(f) for f in files)
 
 
+def build_variant(name: str, flags) -> str:
+    """Extra build for kernel experiments: manus_b200/lib/variants/lib<name>.so compiled with additional nvcc flags."""
+    out_dir = os.path.join(HERE, "lib", "variants")
+    os.makedirs(os.path.join(out_dir, name), exist_ok=True)
+    cc = nvcc()
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(out_dir, name, src.replace(".cu", ".o"))
+        cmd = [cc, "-c", os.path.join(CSRC, src), "-o", obj] + ARCH + COMMON + PER_FILE_FLAGS.get(src, []) + list(flags)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(r.stdout + r.stderr)
+        objs.append(obj)
+    lib = os.path.join(out_dir, f"lib{name}.so")
+    r = subprocess.run([cc, "-shared", "-o", lib] + objs + ARCH + ["-Xcompiler", "-fPIC"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(r.stdout + r.stderr)
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
         return LIB

@@ -42,6 +42,7 @@ class Camera:
     full_proj_transform: np.ndarray    # [4,4] float32, = (P . extr_4x4)^T
     camera_center: np.ndarray          # [3]   float32
     projection_matrix: np.ndarray      # [4,4] float32, = P^T
+    tanfov_dev: object = None          # optional CUDA tensor [2] = (tan(fovx/2), tan(fovy/2)); used instead of fovx / fovy
 
     @property
     def tanfovx(self) -> float:

@@ -564,12 +564,20 @@ static int launch_pose(PoseArgs a, bool backward, cudaStream_t s) {
     }
     if (per_sm > 8) per_sm = 8;
     const int grid = min(ntiles, sm_count() * per_sm);
+    // raise the dynamic shared-memory limit once per (kernel, device): not a stream operation, kept out of the per-frame path
+    static thread_local int limit[2][16] = {};
+    int dev = 0;
+    MB_CUDA(cudaGetDevice(&dev));
+    int &cur = limit[backward ? 1 : 0][dev & 15];
+    if (cur < (int)smem) {
+        if (backward) MB_CUDA(cudaFuncSetAttribute(pose_backward_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else MB_CUDA(cudaFuncSetAttribute(pose_forward_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = (int)smem;
+    }
     if (backward) {
-        MB_CUDA(cudaFuncSetAttribute(pose_backward_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelTimer kt("pose_backward", s);
         pose_backward_kernel<DEG><<<grid, kPoseThreads, smem, s>>>(a);
     } else {
-        MB_CUDA(cudaFuncSetAttribute(pose_forward_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KernelTimer kt("pose_forward", s);
         pose_forward_kernel<DEG><<<grid, kPoseThreads, smem, s>>>(a);
     }

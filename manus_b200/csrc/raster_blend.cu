@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kWarps * 32, 16 / kWarps) blend_backward_kerne
 struct PreBwdArgs {
     int P, W, H, deg, M;
     float tanx, tany, focx, focy, scale_mod;
-    const float *means3D, *cov3D, *scales, *rots, *shs, *view, *proj, *campos;
+    const float *means3D, *cov3D, *scales, *rots, *shs, *view, *proj, *campos, *tanfov_dev;
     const int32_t *radii;
     const uint32_t *clamped;
     const float *acc;
@@ -378,6 +378,10 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBwdArgs a) 
     else if (tid < 32) cam[tid] = a.proj[tid - 16];
     else if (tid < 35) cam[tid] = a.campos[tid - 32];
     __syncthreads();
+    if (a.tanfov_dev) {
+        a.tanx = a.tanfov_dev[0]; a.tany = a.tanfov_dev[1];
+        a.focx = a.W / (2.0f * a.tanx); a.focy = a.H / (2.0f * a.tany);
+    }
     const float *v = cam, *p = cam + 16;
     const int i = blockIdx.x * 256 + tid;
     if (i >= a.P) return;
@@ -661,6 +665,7 @@ extern "C" int mb_raster_backward(const mb_raster_inputs *in, const int32_t *rad
     a.tanx = in->tanfovx; a.tany = in->tanfovy; a.focx = d.focx; a.focy = d.focy; a.scale_mod = in->scale_modifier;
     a.means3D = in->means3D; a.cov3D = in->cov3D_precomp ? in->cov3D_precomp : g.cov3D; a.scales = in->scales;
     a.rots = in->rotations; a.shs = in->shs; a.view = in->viewmatrix; a.proj = in->projmatrix; a.campos = in->campos;
+    a.tanfov_dev = in->tanfov_dev;
     a.radii = radii; a.clamped = g.clamped; a.acc = acc;
     a.dL_dmeans2D = dL_dmeans2D; a.dL_dcolors = dL_dcolors; a.dL_dopacity = dL_dopacity; a.dL_dmeans3D = dL_dmeans3D;
     a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh; a.dL_dscales = dL_dscales; a.dL_drots = dL_drotations;

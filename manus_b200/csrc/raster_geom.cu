@@ -13,7 +13,7 @@ namespace mb {
 struct PreArgs {
     int P, W, H, gx, gy, deg, M;
     float tanx, tany, focx, focy, scale_mod;
-    const float *means3D, *opac, *colors, *cov3D_precomp, *scales, *rots, *shs, *view, *proj, *campos;
+    const float *means3D, *opac, *colors, *cov3D_precomp, *scales, *rots, *shs, *view, *proj, *campos, *tanfov_dev;
     GeomState g;
     int32_t *radii;
 };
@@ -26,13 +26,17 @@ __device__ __forceinline__ void tile_rect(float px, float py, int rad, int gx, i
 }
 
 template <bool kPrecompCov, bool kSH>
-__global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {
+__global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {   // `a` is a by-value copy: the camera override below is local
     __shared__ float cam[36];
     const int tid = threadIdx.x;
     if (tid < 16) cam[tid] = a.view[tid];
     else if (tid < 32) cam[tid] = a.proj[tid - 16];
     else if (tid < 35) cam[tid] = a.campos[tid - 32];
     __syncthreads();
+    if (a.tanfov_dev) {   // camera intrinsics from device memory (same fp32 expressions as raster_dims on the host)
+        a.tanx = a.tanfov_dev[0]; a.tany = a.tanfov_dev[1];
+        a.focx = a.W / (2.0f * a.tanx); a.focy = a.H / (2.0f * a.tany);
+    }
     const float *v = cam, *p = cam + 16;
     const int i = blockIdx.x * 256 + tid;
     bool visible = false;
@@ -193,8 +197,14 @@ constexpr uint32_t kBigTiles = 64;
 enum : uint32_t { kScanAggregate = 1u << 30, kScanPrefix = 2u << 30, kScanMask = (1u << 30) - 1u };
 
 // The instance offsets (exclusive scan of the tile counts in depth order) are computed here as well, single pass:
-// a CTA takes the next chunk of 256 depth-sorted Gaussians (dynamic chunk id), scans its counts, publishes the chunk
+// a CTA takes the next chunk of 1024 depth-sorted Gaussians (dynamic chunk id), scans its counts, publishes the chunk
 // total and gets the total of all earlier chunks by decoupled look-back (warp 0 reads 32 predecessors per step).
+#ifndef MB_EMIT_ITEMS
+#define MB_EMIT_ITEMS 2
+#endif
+constexpr int kEmitItems = MB_EMIT_ITEMS;          // Gaussians per thread
+constexpr int kEmitChunk = 256 * kEmitItems;       // Gaussians per chunk
+
 __global__ void __launch_bounds__(256) emit_instances_kernel(int P, int gx, const uint32_t *__restrict__ sorted_idx,
                                                              const uint32_t *__restrict__ tiles_touched,
                                                              const ushort4 *__restrict__ rect,
@@ -204,29 +214,41 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, int gx, cons
     __shared__ uint32_t s_chunk, s_base, s_warp[8];
     if (blockIdx.x == 0 && threadIdx.x == 0 && (int64_t)counters[kCntRendered] > capacity) counters[kCntOverflow] = 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nchunks = (P + 255) / 256;
+    const int nchunks = (P + kEmitChunk - 1) / kEmitChunk;
     while (true) {
         __syncthreads();   // s_chunk / s_base / s_warp of the previous chunk are no longer read
         if (threadIdx.x == 0) s_chunk = atomicAdd(&counters[kCntEmitCursor], 1u);
         __syncthreads();
         const int chunk = (int)s_chunk;
         if (chunk >= nchunks) return;
-        const int i = chunk * 256 + (int)threadIdx.x;
-        uint32_t g = 0, cnt = 0;
-        ushort4 r = make_ushort4(0, 0, 1, 1);
-        if (i < P) {
-            g = sorted_idx[i];
-            cnt = tiles_touched[g];
-            if (cnt) r = rect[g];
-        }
-        // scan of the full counts (big Gaussians keep their slots; they are written by emit_big_kernel)
-        uint32_t incl_all = cnt;
+        // a warp owns 32 * kEmitItems consecutive depth-sorted Gaussians, item k of lane l is Gaussian first + 32 k + l;
+        // the three dependent loads of all items are in flight together
+        const int first = chunk * kEmitChunk + warp * (32 * kEmitItems);
+        uint32_t g[kEmitItems], cnt[kEmitItems];
+        ushort4 r[kEmitItems];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl_all, o);
-            if (lane >= o) incl_all += t;
+        for (int k = 0; k < kEmitItems; ++k) {
+            const int i = first + 32 * k + lane;
+            g[k] = i < P ? sorted_idx[i] : 0xffffffffu;
         }
-        if (lane == 31) s_warp[warp] = incl_all;
+#pragma unroll
+        for (int k = 0; k < kEmitItems; ++k) cnt[k] = g[k] != 0xffffffffu ? tiles_touched[g[k]] : 0u;
+#pragma unroll
+        for (int k = 0; k < kEmitItems; ++k) r[k] = cnt[k] ? rect[g[k]] : make_ushort4(0, 0, 1, 1);
+        // scan of the full counts (big Gaussians keep their slots; they are written by emit_big_kernel)
+        uint32_t excl[kEmitItems], run = 0;
+#pragma unroll
+        for (int k = 0; k < kEmitItems; ++k) {
+            uint32_t incl = cnt[k];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            excl[k] = run + incl - cnt[k];
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) s_warp[warp] = run;
         __syncthreads();
         uint32_t warp_excl = 0, chunk_total = 0;
 #pragma unroll
@@ -242,7 +264,7 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, int gx, cons
                 int p = chunk - 1;   // nearest predecessor not yet accounted for
                 while (true) {
                     const int idx = p - lane;
-                    const uint32_t v = idx >= 0 ? status[idx] : kScanPrefix;   // virtual zero prefix in front of chunk 0
+                    const uint32_t v = idx >= 0 ? status[idx] : (uint32_t)kScanPrefix;   // virtual zero prefix in front of chunk 0
                     const unsigned not_ready = __ballot_sync(0xffffffffu, (v & ~kScanMask) == 0);
                     const unsigned is_prefix = __ballot_sync(0xffffffffu, (v & ~kScanMask) == kScanPrefix);
                     const int first_nr = not_ready ? __ffs(not_ready) - 1 : 32;
@@ -258,38 +280,43 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, int gx, cons
             if (lane == 0) s_base = before;
         }
         __syncthreads();
-        uint32_t off = s_base + warp_excl + incl_all - cnt;
-        if (cnt > kBigTiles) {
-            big_list[atomicAdd(&counters[kCntBig], 1u)] = make_uint2((uint32_t)i, off);
-            cnt = 0;
-        }
-        uint32_t incl = cnt;
+        const uint32_t wbase = s_base + warp_excl;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t width = (uint32_t)(r.z - r.x);
-        for (uint32_t s0 = 0; s0 < total; s0 += 32) {
-            const uint32_t sl = s0 + lane;
-            int lo = 0, hi = 31;   // first lane whose inclusive count exceeds sl
-#pragma unroll
-            for (int it = 0; it < 5; ++it) {
-                const int mid = (lo + hi) >> 1;
-                const uint32_t v = __shfl_sync(0xffffffffu, incl, mid);
-                if (v > sl) hi = mid; else lo = mid + 1;
+        for (int k = 0; k < kEmitItems; ++k) {
+            const uint32_t off = wbase + excl[k];
+            uint32_t c = cnt[k];
+            if (c > kBigTiles) {
+                big_list[atomicAdd(&counters[kCntBig], 1u)] = make_uint2((uint32_t)(first + 32 * k + lane), off);
+                c = 0;
             }
-            const uint32_t o_incl = __shfl_sync(0xffffffffu, incl, lo), o_cnt = __shfl_sync(0xffffffffu, cnt, lo);
-            const uint32_t o_g = __shfl_sync(0xffffffffu, g, lo), o_w = __shfl_sync(0xffffffffu, width, lo);
-            const uint32_t o_x0 = __shfl_sync(0xffffffffu, (uint32_t)r.x, lo), o_y0 = __shfl_sync(0xffffffffu, (uint32_t)r.y, lo);
-            const uint32_t o_off = __shfl_sync(0xffffffffu, off, lo);
-            const uint32_t local = sl - (o_incl - o_cnt);
-            const int64_t pos = (int64_t)o_off + local;
-            if (sl < total && pos < capacity) {
-                const uint32_t ty = local / o_w, tx = local - ty * o_w;
-                tile_out[pos] = (o_y0 + ty) * (uint32_t)gx + o_x0 + tx;
-                gid_out[pos] = o_g;
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t width = (uint32_t)(r[k].z - r[k].x);
+            for (uint32_t s0 = 0; s0 < total; s0 += 32) {
+                const uint32_t sl = s0 + lane;
+                int lo = 0, hi = 31;   // first lane whose inclusive count exceeds sl
+#pragma unroll
+                for (int it = 0; it < 5; ++it) {
+                    const int mid = (lo + hi) >> 1;
+                    const uint32_t v = __shfl_sync(0xffffffffu, incl, mid);
+                    if (v > sl) hi = mid; else lo = mid + 1;
+                }
+                const uint32_t o_incl = __shfl_sync(0xffffffffu, incl, lo), o_cnt = __shfl_sync(0xffffffffu, c, lo);
+                const uint32_t o_g = __shfl_sync(0xffffffffu, g[k], lo), o_w = __shfl_sync(0xffffffffu, width, lo);
+                const uint32_t o_x0 = __shfl_sync(0xffffffffu, (uint32_t)r[k].x, lo), o_y0 = __shfl_sync(0xffffffffu, (uint32_t)r[k].y, lo);
+                const uint32_t o_off = __shfl_sync(0xffffffffu, off, lo);
+                const uint32_t local = sl - (o_incl - o_cnt);
+                const int64_t pos = (int64_t)o_off + local;
+                if (sl < total && pos < capacity) {
+                    const uint32_t ty = local / o_w, tx = local - ty * o_w;
+                    tile_out[pos] = (o_y0 + ty) * (uint32_t)gx + o_x0 + tx;
+                    gid_out[pos] = o_g;
+                }
             }
         }
     }
@@ -439,7 +466,7 @@ int validate_raster_inputs(const mb_raster_inputs *in, const char *who) {
                    "%s: shs has %d coefficients, degree %d needs %d (max 16)", who, in->sh_coeffs, in->sh_degree,
                    (in->sh_degree + 1) * (in->sh_degree + 1));
     }
-    MB_REQUIRE(in->tanfovx > 0.f && in->tanfovy > 0.f, "%s: tanfov must be positive", who);
+    MB_REQUIRE(in->tanfov_dev || (in->tanfovx > 0.f && in->tanfovy > 0.f), "%s: tanfov must be positive", who);
     return MB_OK;
 }
 
@@ -453,7 +480,7 @@ static int tile_bits(int tiles) {
 int build_instances(const mb_raster_inputs *in, const RasterDims &d, const GeomState &g, const BinningState &b,
                     const ImageState &im, int64_t capacity, cudaStream_t s) {
     const bool dbg = in->debug != 0;
-    const int grid_p = max(1, min((d.P + 255) / 256, sm_count() * 8));
+    const int grid_p = max(1, min((d.P + kEmitChunk - 1) / kEmitChunk, sm_count() * 8));
     MB_CUDA(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)d.tiles, s));
     {
     KernelTimer kt("emit_instances", s);
@@ -514,6 +541,7 @@ extern "C" int mb_raster_forward_geom(const mb_raster_inputs *in, void *geom, si
         a.tanx = in->tanfovx; a.tany = in->tanfovy; a.focx = d.focx; a.focy = d.focy; a.scale_mod = in->scale_modifier;
         a.means3D = in->means3D; a.opac = in->opacities; a.cov3D_precomp = in->cov3D_precomp; a.scales = in->scales;
         a.rots = in->rotations; a.shs = in->shs; a.colors = in->colors_precomp; a.view = in->viewmatrix; a.proj = in->projmatrix; a.campos = in->campos;
+        a.tanfov_dev = in->tanfov_dev;
         a.g = g; a.radii = radii;
         const int grid = (d.P + 255) / 256;
         {

@@ -131,7 +131,7 @@ inline RasterDims raster_dims(const mb_raster_inputs *in) {
     d.gx = (d.W + kTile - 1) / kTile;
     d.gy = (d.H + kTile - 1) / kTile;
     d.tiles = d.gx * d.gy;
-    d.focx = d.W / (2.0f * in->tanfovx);
+    d.focx = d.W / (2.0f * in->tanfovx);   // overridden on the device when in->tanfov_dev is given
     d.focy = d.H / (2.0f * in->tanfovy);
     return d;
 }

@@ -44,12 +44,21 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t
 }
 
 enum : uint32_t { kFlagAggregate = 1u << 30, kFlagPrefix = 2u << 30, kCountMask = (1u << 30) - 1u };
-constexpr int kLookBack = 8;   // predecessors polled per look-back step (independent loads: one L2 round trip per step)
+#ifndef MB_LOOKBACK
+#define MB_LOOKBACK 8
+#endif
+#ifndef MB_RANK_MATCH
+#define MB_RANK_MATCH 0
+#endif
+#ifndef MB_SORT_MINBLOCKS
+#define MB_SORT_MINBLOCKS 2
+#endif
+constexpr int kLookBack = MB_LOOKBACK;   // predecessors polled per look-back step (independent loads: one L2 round trip per step)
 
 // One radix pass over one chunk per CTA.  Ranks are stable; the chunk is first reordered in shared memory (digit-major),
 // so that the scatter to global memory writes runs of consecutive addresses, and the (key, value) pairs are parked there
 // while the look-back for the counts of the earlier chunks is in flight.
-__global__ void __launch_bounds__(kSortThreads) radix_pass_kernel(const uint32_t *__restrict__ keys_in,
+__global__ void __launch_bounds__(kSortThreads, MB_SORT_MINBLOCKS) radix_pass_kernel(const uint32_t *__restrict__ keys_in,
                                                                   const uint32_t *__restrict__ vals_in,
                                                                   uint32_t *__restrict__ keys_out,
                                                                   uint32_t *__restrict__ vals_out, int64_t n_host,
@@ -81,25 +90,46 @@ __global__ void __launch_bounds__(kSortThreads) radix_pass_kernel(const uint32_t
         const int e = wbase + r * 32 + lane;
         key[r] = e < nvalid ? keys_in[chunk_base + e] : 0xffffffffu;
     }
+    // peers = lanes of the warp holding the same digit: eight ballots per round (fixed cost, unlike match.any whose cost
+    // grows with the number of distinct digits in the warp), all rounds independent
+    uint32_t peers[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const bool valid = wbase + r * 32 + lane < nvalid;
+        const uint32_t digit = (key[r] >> shift) & 255u;
+#if MB_RANK_MATCH
+        const uint32_t m = __match_any_sync(0xffffffffu, valid ? digit : 256u);
+#else
+        uint32_t m = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const bool bit = (digit >> b) & 1u;
+            const uint32_t v = __ballot_sync(0xffffffffu, bit);
+            m &= bit ? v : ~v;
+        }
+#endif
+        peers[r] = valid ? m : 0u;
+    }
+    // the first lane of every peer group adds the group size to the warp's digit counter; the shared-memory atomics of
+    // consecutive rounds are issued back to back (no register dependency between rounds)
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t digit = (key[r] >> shift) & 255u;
+        uint32_t old = 0;
+        if (peers[r] && (peers[r] & lt) == 0) old = atomicAdd(&warp_cnt[warp][digit], (uint32_t)__popc(peers[r]));
+        __syncwarp();
+        rank[r] = old;
+    }
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const int leader = peers[r] ? __ffs(peers[r]) - 1 : lane;
+        rank[r] = __shfl_sync(0xffffffffu, rank[r], leader) + __popc(peers[r] & lt);
+    }
+    // the values travel with the keys from here on; their loads overlap the scans below
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const int e = wbase + r * 32 + lane;
         val[r] = e < nvalid ? vals_in[chunk_base + e] : 0u;
-    }
-#pragma unroll
-    for (int r = 0; r < kSortItems; ++r) {
-        const bool valid = wbase + r * 32 + lane < nvalid;
-        const uint32_t digit = valid ? ((key[r] >> shift) & 255u) : 256u;
-        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (valid && lane == leader) {
-            old = warp_cnt[warp][digit];
-            warp_cnt[warp][digit] = old + __popc(peers);
-        }
-        __syncwarp();
-        old = __shfl_sync(0xffffffffu, old, leader);
-        rank[r] = old + __popc(peers & lt);
     }
     __syncthreads();
     // thread `tid` owns digit `tid`

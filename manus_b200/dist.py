@@ -132,6 +132,17 @@ def sharded_step(flat: FlatGaussians, my_views: Sequence[int],
     return total / max(n_views, 1.0)
 
 
+CAM_FLOATS = 39   # view 16 | proj 16 | centre 3 | fovx, fovy | tan(fovx/2), tan(fovy/2)
+
+
+def pack_camera(cam):
+    """One camera as the flat fp32 record the renderer takes per view (host side, numpy)."""
+    import numpy as np
+
+    return np.concatenate([np.asarray(cam.world_view_transform).reshape(-1), np.asarray(cam.full_proj_transform).reshape(-1),
+                           np.asarray(cam.camera_center).reshape(-1), [cam.fovx, cam.fovy, cam.tanfovx, cam.tanfovy]]).astype("float32")
+
+
 class SceneRenderer:
     """Everything one rank needs to render views of a (hand | object | composite) scene forward + backward through the
     public API: resident parameters (flat), skin weights, rest bones, and per-view cameras / bone poses."""
@@ -155,14 +166,17 @@ class SceneRenderer:
         if view not in self._cams:
             cam = self._synth.camera(view, self.W, self.H)
             import numpy as np
-            packed = np.concatenate([cam.world_view_transform.reshape(-1), cam.full_proj_transform.reshape(-1),
-                                     cam.camera_center.reshape(-1), [cam.fovx, cam.fovy]]).astype("float32")
+            packed = pack_camera(cam)
             bones = self._synth.posed_bones(view).reshape(-1).astype("float32")
             self._cams[view] = (cam, torch.from_numpy(packed).pin_memory(), torch.from_numpy(bones).pin_memory())
         return self._cams[view]
 
-    def render(self, view: int, sink: Optional[Dict[str, torch.Tensor]] = None, cam_dev=None, bones_dev=None):
-        """Forward of one view through render_fused; returns the result dict (image is out['render'], HWC)."""
+    def render(self, view: int, sink: Optional[Dict[str, torch.Tensor]] = None, cam_dev=None, bones_dev=None,
+               device_intrinsics: bool = False):
+        """Forward of one view through render_fused; returns the result dict (image is out['render'], HWC).
+        cam_dev / bones_dev: the packed per-view inputs already on the device (``view_inputs_host`` layout).
+        device_intrinsics: read tan(fov/2) from cam_dev[37:39] on the device instead of from the host camera, so that the
+        enqueued frame does not depend on which view ``cam_dev`` holds (CUDA-graph replay)."""
         from .cameras import Camera
         from .pose import bone_transforms
         from .render import render_fused
@@ -171,9 +185,70 @@ class SceneRenderer:
         if cam_dev is None:
             cam_dev = cam_host.to(self.device, non_blocking=True)
             bones_dev = bones_host.to(self.device, non_blocking=True)
-        dcam = Camera(cam.width, cam.height, cam.fovx, cam.fovy, cam_dev[0:16].view(4, 4), cam_dev[16:32].view(4, 4), cam_dev[32:35], None)
+        dcam = Camera(cam.width, cam.height, cam.fovx, cam.fovy, cam_dev[0:16].view(4, 4), cam_dev[16:32].view(4, 4), cam_dev[32:35], None,
+                      tanfov_dev=cam_dev[37:39] if device_intrinsics else None)
         bone_tf = None
         if self.n_hand > 0:
             bone_tf = torch.cat([torch.bmm(bones_dev.view(-1, 4, 4), self.rest_inv), self._eye], dim=0)   # = bone_transforms(...)
         return render_fused(self.flat.leaves(), self.skin, bone_tf, dcam, self.bg, self.sh_degree, self.flat.isotropic,
                             self.n_hand, grad_sink=sink)
+
+
+class GraphedStep:
+    """One training view -- pose forward, rasterizer forward, loss, rasterizer backward, pose backward into the flat gradient
+    buffer -- captured ONCE in a CUDA graph and replayed per step with a single launch.  The per-view inputs (packed camera,
+    posed bones, loss target) live in static device tensors that the caller overwrites before ``replay()``; nothing in the
+    captured frame depends on host values of the view (intrinsics are read from ``cam`` on the device) and nothing is read
+    back (reserve capacity mode), so the same graph serves every view of the scene.
+
+    loss_fn(image[H,W,3], target) -> scalar tensor.  After ``replay()``: ``loss`` (device scalar) and ``renderer.flat.grad``
+    hold the step's results.  ``check()`` (synchronises) raises if a replayed frame overflowed the reserved capacity.
+    """
+
+    def __init__(self, renderer: SceneRenderer, loss_fn, target_like: torch.Tensor, view: int = 0, warmup: int = 3):
+        from . import rasterizer as rz
+
+        if rz._Plan.mode != "reserve":
+            raise RuntimeError("GraphedStep needs set_capacity_mode('reserve') and reserve_capacity(...) (no host read-back in a graph)")
+        self.r = renderer
+        dev = renderer.device
+        _, cam_host, bones_host = renderer.view_inputs_host(view)
+        self.cam = cam_host.to(dev)
+        self.bones = bones_host.to(dev)
+        self.target = target_like.to(dev).clone()
+        self.view = view
+        self.loss_fn = loss_fn
+
+        def frame():
+            out = renderer.render(view, sink=renderer.flat.grads, cam_dev=self.cam, bones_dev=self.bones, device_intrinsics=True)
+            loss = loss_fn(out["render"], self.target)
+            loss.backward()
+            return loss.detach(), out["radii"]
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                frame()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.radii = frame()
+        self.state = rz._Plan.last_state
+
+    def set_inputs(self, cam_dev: torch.Tensor, bones_dev: torch.Tensor, target_dev: Optional[torch.Tensor] = None) -> None:
+        """Device-to-device copies into the static slots (enqueued on the current stream)."""
+        self.cam.copy_(cam_dev, non_blocking=True)
+        self.bones.copy_(bones_dev, non_blocking=True)
+        if target_dev is not None:
+            self.target.copy_(target_dev, non_blocking=True)
+
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.loss
+
+    def check(self) -> int:
+        from . import rasterizer as rz
+
+        return rz.check_overflow(self.state)

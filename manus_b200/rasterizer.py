@@ -54,12 +54,30 @@ class _Plan:
     mode = "exact"
     margin = 1.3
     high_water = {}
+    last_state = None      # RasterState of the most recent forward (for check_overflow)
 
 
 def set_capacity_mode(mode: str, margin: float = 1.3) -> None:
     assert mode in ("exact", "reserve")
     _Plan.mode, _Plan.margin = mode, margin
     _Plan.high_water.clear()
+
+
+def reserve_capacity(device_index: int, num_points: int, height: int, width: int, instances: int) -> None:
+    """Reserve-mode sizing: frames of this (device, N, H, W) get room for ``instances * margin`` instances."""
+    key = (device_index, num_points, height, width)
+    _Plan.high_water[key] = max(_Plan.high_water.get(key, 0), int(instances))
+
+
+def check_overflow(st: "Optional[RasterState]" = None) -> int:
+    """Reserve mode reads nothing back per frame; call this when convenient (it synchronises the stream): returns
+    num_rendered of the given / most recent forward, raises if that frame needed more instances than were reserved."""
+    st = st if st is not None else _Plan.last_state
+    if st is None:
+        return 0
+    st.num_rendered = -1
+    st.host_count = None
+    return st.resolve()
 
 
 class RasterState:
@@ -69,8 +87,11 @@ class RasterState:
     def resolve(self) -> int:
         """num_rendered of this frame (waits for the count copy if it is still in flight); raises on overflow."""
         if self.num_rendered < 0:
-            self.event.synchronize()
-            self.num_rendered = int(self.host_count.item())
+            if self.host_count is None:      # reserve mode: read the device counters (synchronises the stream)
+                self.num_rendered = raster_query(self)[0]
+            else:
+                self.event.synchronize()
+                self.num_rendered = int(self.host_count.item())
             _Plan.high_water[self.key] = max(_Plan.high_water.get(self.key, 0), self.num_rendered)
             if self.num_rendered > self.capacity:
                 raise _lib.ManusB200Error(
@@ -93,7 +114,18 @@ def _make_inputs(settings: GaussianRasterizationSettings, means3D, opacities, co
     ri.sh_degree = int(settings.sh_degree)
     ri.sh_coeffs = 0 if shs is None else int(shs.shape[1])
     ri.prefiltered, ri.debug = int(bool(settings.prefiltered)), int(bool(settings.debug))
-    ri.tanfovx, ri.tanfovy = float(settings.tanfovx), float(settings.tanfovy)
+    tx, ty = settings.tanfovx, settings.tanfovy
+    if torch.is_tensor(tx) and tx.is_cuda:
+        # camera intrinsics stay on the device (replayable frames: CUDA graphs, no host read of the tensor)
+        tx, ty = tx.reshape(-1)[:1], ty.reshape(-1)[:1]
+        if not (tx.dtype == ty.dtype == torch.float32 and ty.data_ptr() == tx.data_ptr() + 4):
+            tx = torch.cat([tx.float(), ty.float().to(dev)])     # (tanfovx, tanfovy) adjacent in memory
+        keep.append(tx)
+        ri.tanfovx = ri.tanfovy = 0.0
+        ri.tanfov_dev = ptr(tx)
+    else:
+        ri.tanfovx, ri.tanfovy = float(tx), float(ty)
+        ri.tanfov_dev = None
     ri.scale_modifier = float(settings.scale_modifier)
     ri.background, ri.viewmatrix, ri.projmatrix, ri.campos = ptr(bg), ptr(view), ptr(proj), ptr(cam)
     ri.means3D, ri.opacities = ptr(means3D), ptr(opacities)
@@ -120,21 +152,27 @@ def rasterize_forward(settings: GaussianRasterizationSettings, means3D, opacitie
         st.radii = torch.empty(N, dtype=torch.int32, device=dev)
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         st.key = (dev.index, N, H, W)
-        st.host_count = torch.zeros(1, dtype=torch.int64).pin_memory()
+        reserve = capacity is None and _Plan.mode == "reserve" and st.key in _Plan.high_water
+        # reserve mode: nothing is read back per frame (the frame can be captured in a CUDA graph); an overflow is
+        # recorded in the device counters and raised by check_overflow() / raster_query()
+        st.host_count = None if reserve else torch.zeros(1, dtype=torch.int64).pin_memory()
         _lib.check(L.mb_raster_forward_geom(C.byref(st.inputs), ptr(st.geom), st.geom.numel(), ptr(st.radii),
-                                            st.host_count.data_ptr(), stream), "mb_raster_forward_geom")
-        st.event = torch.cuda.Event()
-        st.event.record(torch.cuda.current_stream(dev))
+                                            None if reserve else st.host_count.data_ptr(), stream), "mb_raster_forward_geom")
         st.num_rendered = -1
-        if capacity is None and _Plan.mode == "reserve" and st.key in _Plan.high_water:
+        st.event = None
+        if reserve:
             capacity = int(_Plan.high_water[st.key] * _Plan.margin) + 1024      # no host synchronisation
-        elif capacity is None:
-            st.capacity = 1 << 62
-            capacity = st.resolve()                                              # one 8-byte host read, like upstream
+        else:
+            st.event = torch.cuda.Event()
+            st.event.record(torch.cuda.current_stream(dev))
+            if capacity is None:
+                st.capacity = 1 << 62
+                capacity = st.resolve()                                          # one 8-byte host read, like upstream
         st.capacity = int(capacity)
         st.binning = torch.empty(L.mb_raster_binning_bytes(st.capacity, W, H), dtype=torch.uint8, device=dev)
         _lib.check(L.mb_raster_forward_render(C.byref(st.inputs), ptr(st.geom), ptr(st.binning), st.binning.numel(), st.capacity,
                                               ptr(st.image), st.image.numel(), ptr(color), stream), "mb_raster_forward_render")
+    _Plan.last_state = st
     return color, st.radii, st
 
 
@@ -197,7 +235,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         st = ctx.state
         if st is None:
             return (None,) * 9
-        st.resolve()
+        if st.host_count is not None:
+            st.resolve()
         g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rot = rasterize_backward(st, grad_out_color)
         m3_shape, m2_shape, op_shape = ctx.shapes
         ctx.state = None

@@ -17,9 +17,11 @@ def _scalar(v) -> float:
 
 
 def _settings(camera, bg_color, sh_degree, device) -> GaussianRasterizationSettings:
+    tan_dev = getattr(camera, "tanfov_dev", None)     # optional CUDA tensor (tanfovx, tanfovy): intrinsics stay on the device
     return GaussianRasterizationSettings(
         image_height=int(_scalar(camera.height)), image_width=int(_scalar(camera.width)),
-        tanfovx=math.tan(_scalar(camera.fovx) * 0.5), tanfovy=math.tan(_scalar(camera.fovy) * 0.5),
+        tanfovx=tan_dev[0:1] if tan_dev is not None else math.tan(_scalar(camera.fovx) * 0.5),
+        tanfovy=tan_dev[1:2] if tan_dev is not None else math.tan(_scalar(camera.fovy) * 0.5),
         bg=bg_color, scale_modifier=1,
         viewmatrix=torch.as_tensor(camera.world_view_transform).to(device),
         projmatrix=torch.as_tensor(camera.full_proj_transform).to(device),

@@ -1,16 +1,18 @@
 #!/usr/bin/env python
 """Print the SASS listing of one kernel from `ncu --page source --csv` with samples, executed counts and dominant stall:
-python profiles/ncu_source_hot.py source.csv [min_samples]"""
+python profiles/ncu_source_hot.py source.csv [min_samples [instance]]"""
 import csv
 import sys
 
 
-def main(path, min_samples=0):
+def main(path, min_samples=0, instance=0):
     rows = list(csv.reader(open(path)))
-    h = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    heads = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+    rows = rows[heads[instance] - 1:]          # the instance-th kernel of the export
+    h = 1
     hdr = rows[h]
     end = next((i for i in range(h + 1, len(rows)) if rows[i] and rows[i][0] in ("Address", "Kernel Name")), len(rows))
-    rows = rows[:end]          # first kernel instance only
+    rows = rows[:end]
     c_src, c_s, c_ie = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
     c_thr = hdr.index("Avg. Predicated-On Threads Executed")
     stalls = [(i, n) for i, n in enumerate(hdr) if n.startswith("stall_") and "Not Issued" not in n]
@@ -29,4 +31,4 @@ def main(path, min_samples=0):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0, int(sys.argv[3]) if len(sys.argv) > 3 else 0)

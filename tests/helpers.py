@@ -78,3 +78,11 @@ def fragile_pixels(ref64_img: np.ndarray, ref32_img: np.ndarray, tol: float = IM
     """Pixels where the fp32 and fp64 oracles themselves disagree by more than the tolerance: a hard gate
     (alpha >= 1/255, T >= 1e-4, power <= 0) flipped under rounding.  [H,W] bool."""
     return (np.abs(ref64_img - ref32_img) > tol).any(0)
+
+
+def small_scene_inputs(seed: int, N: int = 3000, W: int = 160, H: int = 120, zoom: float = 1.6, device="cuda"):
+    """(camera, {means3D, cov3D, colors, opacity} as device tensors) of a small posed hand scene."""
+    sc = synth.make_hand(N, seed=seed)
+    cam = zoom_camera(seed * 7 % 51, W, H, zoom)
+    ps = posed_scene(sc, 3 * seed + 1, cam, 0.3, 1.0)
+    return cam, {k: torch.tensor(np.ascontiguousarray(v), device=device) for k, v in ps.items()}
