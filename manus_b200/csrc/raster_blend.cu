@@ -120,8 +120,10 @@ template <int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 24 / kWarps) blend_forward_kernel(
     const Record *__restrict__ recs, const uint32_t *__restrict__ list, const uint2 *__restrict__ ranges,
     const uint32_t *__restrict__ order, int W, int H, int gx, const float *__restrict__ bg, float *__restrict__ out_color,
-    float *__restrict__ final_T, uint32_t *__restrict__ n_contrib, uint32_t *__restrict__ tile_maxlast) {
+    float *__restrict__ final_T, uint32_t *__restrict__ n_contrib, uint32_t *__restrict__ tile_maxlast,
+    float4 *__restrict__ ckpt) {
     constexpr int kSplit = 8 / kWarps;
+    static_assert(kSeg % (kWarps * 32) == 0, "segment length must be a multiple of the batch size");
     __shared__ __align__(128) StageSmem<kWarps> sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int item = blockIdx.x / kSplit, sub = blockIdx.x % kSplit;
@@ -141,11 +143,15 @@ __global__ void __launch_bounds__(kWarps * 32, 24 / kWarps) blend_forward_kernel
     uint32_t last = 0;
     bool done = !inside;
     bool wdone = __all_sync(0xffffffffu, done);
+    const int ck_idx = (sub * kWarps + warp) * 32 + lane;   // pixel index inside the 16x16 tile
     for (int i = 0; i < st.nb; ++i) {
         st.advance(i);
         const int cnt = st.count(i);
         const float4 *r = st.records(i);
         const uint32_t base = (uint32_t)(i * st.B);
+        // state in front of list position `base`, once per kSeg entries: where a backward segment starts
+        if (i > 0 && base % kSeg == 0)
+            ckpt[BinningState::ckpt_slot((uint32_t)tile, range.x, base / kSeg - 1) * kTilePixels + ck_idx] = make_float4(T, C0, C1, C2);
         // 32 list entries per round: lane k box-tests entry j0+k against the warp's 8x4 pixel block, the survivors are
         // blended in list order with the exact reference arithmetic
         for (int j0 = 0; j0 < cnt && !wdone; j0 += 32) {
@@ -206,6 +212,10 @@ __global__ void __launch_bounds__(kWarps * 32, 24 / kWarps) blend_forward_kernel
     }
     const uint32_t wmax = __reduce_max_sync(0xffffffffu, last);
     if (lane == 0 && wmax) atomicMax(&sm.red, wmax);
+    // tiles whose list spans more than one segment: final (T, C) in the tile's spare checkpoint slot, for the backward
+    if (st.len > kSeg)
+        ckpt[BinningState::ckpt_slot((uint32_t)tile, range.x, (uint32_t)((st.len + kSeg - 1) / kSeg - 1)) * kTilePixels + ck_idx] =
+            make_float4(T, C0, C1, C2);
     if (inside) {
         const size_t pix = (size_t)py * W + px, plane = (size_t)W * H;
         final_T[pix] = T;
@@ -257,19 +267,27 @@ __device__ __forceinline__ float reduce_scatter9(const float (&v)[9], int lane) 
     return d;
 }
 
+// One work item = one segment [seg*kSeg, min((seg+1)*kSeg, maxlast)) of one (half / quarter) tile's list, walked back to
+// front.  A pixel whose last contributor lies beyond the segment starts from the forward's checkpoint in front of the far
+// end: T = transmittance there, accumulated "colour behind" = (C_final - C_front) / T; a pixel whose last contributor is
+// inside (or in front of) the segment starts from (T_final, 0) exactly like the unsegmented recurrence.
 template <int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 16 / kWarps) blend_backward_kernel(
     const Record *__restrict__ recs, const uint32_t *__restrict__ list, const uint2 *__restrict__ ranges,
-    const uint32_t *__restrict__ order, const uint32_t *__restrict__ tile_maxlast, int W, int H, int gx,
-    const float *__restrict__ bg, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
-    const float *__restrict__ dL_dout, int64_t sc, int64_t sy, int64_t sx, float *__restrict__ acc) {
+    const uint2 *__restrict__ items, const uint32_t *__restrict__ n_items, const uint32_t *__restrict__ tile_maxlast, int W, int H,
+    int gx, const float *__restrict__ bg, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
+    const float4 *__restrict__ ckpt, const float *__restrict__ dL_dout, int64_t sc, int64_t sy, int64_t sx,
+    float *__restrict__ acc) {
     constexpr int kSplit = 8 / kWarps;
     __shared__ __align__(128) StageSmem<kWarps> sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int item = blockIdx.x / kSplit, sub = blockIdx.x % kSplit;
-    const int tile = order ? (int)order[item] : item;
-    const int len = (int)tile_maxlast[tile];      // list positions [0, len) can matter, walked back to front
-    if (len == 0) return;
+    if ((uint32_t)item >= *n_items) return;
+    const uint2 it = items[item];
+    const int tile = (int)it.x;
+    const uint32_t s0 = it.y * (uint32_t)kSeg;
+    const uint32_t s1 = min(s0 + (uint32_t)kSeg, tile_maxlast[tile]);   // list positions [s0, s1) of this tile
+    const int len = (int)(s1 - s0);
     const uint2 range = ranges[tile];
     int px, py;
     pixel_of_thread(tile, gx, sub * kWarps + warp, lane, px, py);
@@ -289,22 +307,36 @@ __global__ void __launch_bounds__(kWarps * 32, 16 / kWarps) blend_backward_kerne
     const int slot = reduce_slot(lane);
     const float bcx = (float)(px - (lane & 7)) + 3.5f, bcy = (float)(py - (lane >> 3)) + 1.5f;   // centre of the warp's pixel block
 
-    ListStager<kWarps> st{sm, list, recs, range.x, len, 0, true};
+    float T = T_final, a0 = 0.f, a1 = 0.f, a2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
+    if (last > s1) {   // contributions behind this segment: resume from the forward's state in front of position s1
+        const int idx = (sub * kWarps + warp) * 32 + lane;
+        const uint32_t nseg_list = (range.y - range.x + (uint32_t)kSeg - 1u) / (uint32_t)kSeg;
+        const float4 ck = ckpt[BinningState::ckpt_slot((uint32_t)tile, range.x, it.y) * kTilePixels + idx];
+        const float4 fin = ckpt[BinningState::ckpt_slot((uint32_t)tile, range.x, nseg_list - 1u) * kTilePixels + idx];   // final (T, C)
+        const float inv = 1.0f / ck.x;
+        T = ck.x;
+        a0 = (fin.y - ck.y) * inv;
+        a1 = (fin.z - ck.z) * inv;
+        a2 = (fin.w - ck.w) * inv;
+    }
+
+    ListStager<kWarps> st{sm, list, recs, range.x + s0, len, 0, true};
     st.nb = (len + st.B - 1) / st.B;
     st.prologue();
 
-    // nothing to do for this warp's pixels behind their deepest last contributor
-    const uint32_t wlast = __reduce_max_sync(0xffffffffu, last);
-    float T = T_final, a0 = 0.f, a1 = 0.f, a2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
+    // nothing to do for this warp's pixels behind their deepest last contributor (positions relative to s0)
+    const uint32_t wlast_abs = __reduce_max_sync(0xffffffffu, last);
+    const int wlast = wlast_abs > s0 ? (int)min(wlast_abs - s0, (uint32_t)len) : 0;
+    const uint32_t last_rel = last > s0 ? last - s0 : 0u;
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
     for (int i = 0; i < st.nb; ++i) {
         st.advance(i);
         const int cnt = st.count(i);
         const float4 *r = st.records(i);
         const int b = st.batch_of(i);
-        const uint32_t *ids = &sm.ids[i % 3][(range.x + (uint32_t)(b * st.B)) & 3u];
+        const uint32_t *ids = &sm.ids[i % 3][(st.first + (uint32_t)(b * st.B)) & 3u];
         int jend = cnt;   // entries at or behind the warp's deepest last contributor cannot matter
-        if ((uint32_t)(b * st.B) + (uint32_t)cnt > wlast) jend = (int)wlast - b * st.B;
+        if (b * st.B + cnt > wlast) jend = wlast - b * st.B;
         for (int j0 = ((jend - 1) >> 5) << 5; j0 >= 0; j0 -= 32) {
             bool hit = false;
             if (j0 + lane < jend) {
@@ -321,7 +353,7 @@ __global__ void __launch_bounds__(kWarps * 32, 16 / kWarps) blend_backward_kerne
                 const float2 rc = *reinterpret_cast<const float2 *>(&r[3 * j + 2]);
                 const float dx = ra.x - fx, dy = ra.y - fy;
                 const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
-                const bool cand = (pos < last) && (power <= 0.0f) && !(power < rc.y);
+                const bool cand = (pos < last_rel) && (power <= 0.0f) && !(power < rc.y);
                 if (!__any_sync(0xffffffffu, cand)) continue;
                 const float G = expf(power);
                 const float alpha = fminf(kAlphaMax, rb.y * G);
@@ -555,7 +587,7 @@ using namespace mb;
 extern "C" int mb_raster_state_layout(int32_t num_points, int64_t capacity, int32_t w, int32_t h, int64_t *out, int32_t n_out) {
     MB_REQUIRE(out != nullptr && n_out >= 8, "mb_raster_state_layout: need room for 8 offsets");
     GeomState g = GeomState::carve(nullptr, num_points);
-    BinningState b = BinningState::carve(nullptr, capacity);
+    BinningState b = BinningState::carve(nullptr, capacity, ((w + kTile - 1) / kTile) * ((h + kTile - 1) / kTile));
     ImageState im = ImageState::carve(nullptr, w, h);
     out[0] = (int64_t)((char *)im.final_T - (char *)nullptr);
     out[1] = (int64_t)((char *)im.n_contrib - (char *)nullptr);
@@ -578,7 +610,7 @@ extern "C" int mb_raster_forward_render(const mb_raster_inputs *in, void *geom, 
     MB_REQUIRE(geom && binning && image_buf && out_color, "mb_raster_forward_render: null buffer");
     MB_REQUIRE(capacity >= 0 && capacity < (int64_t)0xffffffff, "mb_raster_forward_render: capacity out of range");
     GeomState g = GeomState::carve(geom, d.P);
-    BinningState b = BinningState::carve(binning, capacity);
+    BinningState b = BinningState::carve(binning, capacity, d.tiles);
     ImageState im = ImageState::carve(image_buf, d.W, d.H);
     if (binning_bytes < b.bytes || image_bytes < im.bytes) {
         set_error("mb_raster_forward_render: binning %zu/%zu or image %zu/%zu bytes too small", binning_bytes, b.bytes,
@@ -599,13 +631,13 @@ extern "C" int mb_raster_forward_render(const mb_raster_inputs *in, void *geom, 
         KernelTimer kt("blend_forward", s);
         if (blend_warps() == 4)
             blend_forward_kernel<4><<<d.tiles * 2, 128, 0, s>>>(g.rec, b.gid_b, im.ranges, order, d.W, d.H, d.gx, in->background,
-                                                                out_color, im.final_T, im.n_contrib, im.tile_maxlast);
+                                                                out_color, im.final_T, im.n_contrib, im.tile_maxlast, b.ckpt);
         else if (blend_warps() == 2)
             blend_forward_kernel<2><<<d.tiles * 4, 64, 0, s>>>(g.rec, b.gid_b, im.ranges, order, d.W, d.H, d.gx, in->background,
-                                                               out_color, im.final_T, im.n_contrib, im.tile_maxlast);
+                                                               out_color, im.final_T, im.n_contrib, im.tile_maxlast, b.ckpt);
         else
             blend_forward_kernel<8><<<d.tiles, 256, 0, s>>>(g.rec, b.gid_b, im.ranges, order, d.W, d.H, d.gx, in->background,
-                                                            out_color, im.final_T, im.n_contrib, im.tile_maxlast);
+                                                            out_color, im.final_T, im.n_contrib, im.tile_maxlast, b.ckpt);
     }
     return check_launch("blend_forward", dbg, s);
 }
@@ -635,27 +667,31 @@ extern "C" int mb_raster_backward(const mb_raster_inputs *in, const int32_t *rad
     }
     const bool dbg = in->debug != 0;
     GeomState g = GeomState::carve(const_cast<void *>(geom), d.P);
-    BinningState b = BinningState::carve(const_cast<void *>(binning), capacity);
+    BinningState b = BinningState::carve(const_cast<void *>(binning), capacity, d.tiles);
     ImageState im = ImageState::carve(const_cast<void *>(image_buf), d.W, d.H);
     float *acc = reinterpret_cast<float *>(grad_scratch);
     MB_CUDA(cudaMemsetAsync(acc, 0, (size_t)d.P * kAccStride * sizeof(float), s));
     if (capacity > 0) {
-        rc = tile_order(im.tile_maxlast, nullptr, d.tiles, im.order_bwd, im.order_ws + kOrderWs, s, dbg);
+        uint32_t *n_items = g.counters + kCntBwdItems;
+        rc = segment_items(im.tile_maxlast, d.tiles, b.bwd_items, n_items, im.order_ws + kOrderWs, s, dbg);
         if (rc) return rc;
         {
             KernelTimer kt("blend_backward", s);
+            // upper bound of the item count (the real one is on the device; surplus CTAs exit at once)
+            const int64_t bound = (int64_t)d.tiles + capacity / kSeg + 1;
+            const int64_t max_items = bound < b.max_items ? bound : b.max_items;
             if (blend_warps() == 4)
-                blend_backward_kernel<4><<<d.tiles * 2, 128, 0, s>>>(g.rec, b.gid_b, im.ranges, im.order_bwd, im.tile_maxlast, d.W, d.H,
-                                                                     d.gx, in->background, im.final_T, im.n_contrib, dL_dout,
-                                                                     stride_c, stride_y, stride_x, acc);
+                blend_backward_kernel<4><<<(unsigned)(max_items * 2), 128, 0, s>>>(g.rec, b.gid_b, im.ranges, b.bwd_items, n_items,
+                                                                                 im.tile_maxlast, d.W, d.H, d.gx, in->background, im.final_T,
+                                                                                 im.n_contrib, b.ckpt, dL_dout, stride_c, stride_y, stride_x, acc);
             else if (blend_warps() == 2)
-                blend_backward_kernel<2><<<d.tiles * 4, 64, 0, s>>>(g.rec, b.gid_b, im.ranges, im.order_bwd, im.tile_maxlast, d.W, d.H,
-                                                                    d.gx, in->background, im.final_T, im.n_contrib, dL_dout,
-                                                                    stride_c, stride_y, stride_x, acc);
+                blend_backward_kernel<2><<<(unsigned)(max_items * 4), 64, 0, s>>>(g.rec, b.gid_b, im.ranges, b.bwd_items, n_items,
+                                                                                im.tile_maxlast, d.W, d.H, d.gx, in->background, im.final_T,
+                                                                                im.n_contrib, b.ckpt, dL_dout, stride_c, stride_y, stride_x, acc);
             else
-                blend_backward_kernel<8><<<d.tiles, 256, 0, s>>>(g.rec, b.gid_b, im.ranges, im.order_bwd, im.tile_maxlast, d.W, d.H,
-                                                                 d.gx, in->background, im.final_T, im.n_contrib, dL_dout, stride_c,
-                                                                 stride_y, stride_x, acc);
+                blend_backward_kernel<8><<<(unsigned)max_items, 256, 0, s>>>(g.rec, b.gid_b, im.ranges, b.bwd_items, n_items,
+                                                                           im.tile_maxlast, d.W, d.H, d.gx, in->background, im.final_T,
+                                                                           im.n_contrib, b.ckpt, dL_dout, stride_c, stride_y, stride_x, acc);
         }
         rc = check_launch("blend_backward", dbg, s);
         if (rc) return rc;

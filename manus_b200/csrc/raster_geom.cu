@@ -449,6 +449,82 @@ int tile_order(const uint32_t *weight_or_null, const uint2 *ranges_or_null, int 
     return check_launch("tile_order", debug, s);
 }
 
+__global__ void __launch_bounds__(kOrderThreads) segment_items_kernel(const uint32_t *__restrict__ maxlast, int tiles,
+                                                                      uint2 *__restrict__ items, uint32_t *__restrict__ n_items,
+                                                                      uint32_t *ws) {
+    __shared__ uint32_t hist[kOrderBuckets], base[kOrderBuckets];
+    __shared__ bool s_last;
+    uint32_t *g_hist = ws, *g_cursor = ws + kOrderBuckets;
+    volatile uint32_t *arrive = ws + 2 * kOrderBuckets;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int bfull = weight_bucket((uint32_t)kSeg);
+    for (int b = tid; b < kOrderBuckets; b += kOrderThreads) hist[b] = 0;
+    __syncthreads();
+    const int stride = gridDim.x * kOrderThreads;
+    for (int t = blockIdx.x * kOrderThreads + tid; t < tiles; t += stride) {
+        const uint32_t ml = maxlast[t];
+        const uint32_t nfull = ml / kSeg, rem = ml % kSeg;
+        if (nfull) atomicAdd(&hist[bfull], nfull);
+        if (rem) atomicAdd(&hist[weight_bucket(rem)], 1u);
+    }
+    __syncthreads();
+    for (int b = tid; b < kOrderBuckets; b += kOrderThreads)
+        if (hist[b]) atomicAdd(&g_hist[b], hist[b]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        atomicAdd((uint32_t *)arrive, 1u);
+        while (arrive[0] < gridDim.x) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid < 32) {
+        uint32_t run = 0;
+        for (int b0 = kOrderBuckets - 1; b0 >= 0; b0 -= 32) {
+            const int b = b0 - lane;
+            const uint32_t v = b >= 0 ? __ldcg(&g_hist[b]) : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (b >= 0) base[b] = run + incl - v;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (blockIdx.x == 0 && lane == 0) *n_items = run;
+    }
+    __syncthreads();
+    for (int t = blockIdx.x * kOrderThreads + tid; t < tiles; t += stride) {
+        const uint32_t ml = maxlast[t];
+        const uint32_t nfull = ml / kSeg, rem = ml % kSeg;
+        if (nfull) {
+            const uint32_t p = base[bfull] + atomicAdd(&g_cursor[bfull], nfull);
+            for (uint32_t sgm = 0; sgm < nfull; ++sgm) items[p + sgm] = make_uint2((uint32_t)t, sgm);
+        }
+        if (rem) {
+            const int b = weight_bucket(rem);
+            items[base[b] + atomicAdd(&g_cursor[b], 1u)] = make_uint2((uint32_t)t, nfull);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd((uint32_t *)arrive + 1, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last)
+        for (int b = tid; b < kOrderWs; b += kOrderThreads) ws[b] = 0;
+}
+
+int segment_items(const uint32_t *maxlast, int tiles, uint2 *items, uint32_t *n_items, uint32_t *ws, cudaStream_t s, bool debug) {
+    KernelTimer kt("tile_order", s);
+    const int grid = max(1, min((tiles + kOrderThreads - 1) / kOrderThreads, sm_count()));
+    segment_items_kernel<<<grid, kOrderThreads, 0, s>>>(maxlast, tiles, items, n_items, ws);
+    return check_launch("segment_items", debug, s);
+}
+
 int validate_raster_inputs(const mb_raster_inputs *in, const char *who) {
     MB_REQUIRE(in != nullptr, "%s: null inputs", who);
     MB_REQUIRE(in->num_points >= 0 && in->image_width > 0 && in->image_height > 0, "%s: bad sizes P=%d W=%d H=%d", who,
@@ -514,8 +590,9 @@ using namespace mb;
 
 extern "C" size_t mb_raster_geom_bytes(int32_t num_points) { return GeomState::carve(nullptr, num_points).bytes; }
 
-extern "C" size_t mb_raster_binning_bytes(int64_t capacity, int32_t, int32_t) {
-    return BinningState::carve(nullptr, capacity).bytes;
+extern "C" size_t mb_raster_binning_bytes(int64_t capacity, int32_t w, int32_t h) {
+    const int tiles = ((w + kTile - 1) / kTile) * ((h + kTile - 1) / kTile);
+    return BinningState::carve(nullptr, capacity, tiles).bytes;
 }
 
 extern "C" size_t mb_raster_image_bytes(int32_t w, int32_t h) { return ImageState::carve(nullptr, w, h).bytes; }

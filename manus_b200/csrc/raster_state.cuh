@@ -21,7 +21,7 @@
 
 namespace mb {
 
-enum Counter { kCntRendered = 0, kCntVisible = 1, kCntOverflow = 2, kCntTileCursor = 3, kCntBwdCursor = 4, kCntBig = 5, kCntEmitCursor = 6, kNumCounters = 16 };
+enum Counter { kCntRendered = 0, kCntVisible = 1, kCntOverflow = 2, kCntTileCursor = 3, kCntBwdCursor = 4, kCntBig = 5, kCntEmitCursor = 6, kCntBwdItems = 7, kNumCounters = 16 };
 
 struct Record {   // 48 bytes, 16-B aligned
     float4 a;     // x, y, conic.x, conic.y
@@ -65,23 +65,43 @@ struct GeomState {
     }
 };
 
+// The backward walks a tile's consumed list in independent segments of kSeg entries (one work item per segment), so that
+// the few very deep tiles of a frame do not serialise the kernel.  To start in the middle of a list a segment needs the
+// per-pixel transmittance and accumulated colour in front of its far end: the forward writes that state (16 B per pixel)
+// every kSeg entries.
+#ifndef MB_BWD_SEG
+#define MB_BWD_SEG 512
+#endif
+constexpr int kSeg = MB_BWD_SEG;   // multiple of every batch size (64 / 128 / 256)
+
 constexpr int kListPad = 8;   // slack after the id list: 16-B aligned bulk copies may read up to 3 ids past a tile's range
 
 struct BinningState {
     uint32_t *tile_a, *tile_b;   // tile id per instance (ping-pong)
     uint32_t *gid_a, *gid_b;     // gaussian id per instance; gid_b = sorted by (tile, depth)
     void *sort_ws;
+    float4 *ckpt;                // [max_items][256] (T, C.rgb) per pixel in front of list position kSeg*(seg+1) of a tile
+    uint2 *bwd_items;            // [max_items] (tile, segment) work items of the backward, heaviest first
+    int64_t max_items;           // tiles + capacity / kSeg + 2
     size_t bytes;
 
-    static BinningState carve(void *p, int64_t capacity) {
+    // checkpoint slot of (tile, boundary kSeg*(seg+1)): consecutive tiles never overlap because their list ranges don't
+    __host__ __device__ static inline size_t ckpt_slot(uint32_t tile, uint32_t range_start, uint32_t seg) {
+        return (size_t)tile + range_start / kSeg + seg;
+    }
+
+    static BinningState carve(void *p, int64_t capacity, int tiles) {
         Carver c(p);
         BinningState b;
         const size_t n = (size_t)(capacity > 0 ? capacity : 1) + kListPad;
+        b.max_items = (int64_t)tiles + (int64_t)(n / kSeg) + 2;
         b.tile_a = c.take<uint32_t>(n);
         b.tile_b = c.take<uint32_t>(n);
         b.gid_a = c.take<uint32_t>(n);
         b.gid_b = c.take<uint32_t>(n);
         b.sort_ws = c.take<char>(sort_workspace_bytes((int64_t)n));
+        b.ckpt = c.take<float4>((size_t)b.max_items * kTilePixels);
+        b.bwd_items = c.take<uint2>((size_t)b.max_items);
         b.bytes = c.off;
         return b;
     }
@@ -97,7 +117,7 @@ struct ImageState {
     uint32_t *tile_maxlast;  // [tiles] max over the tile's pixels of n_contrib (how far the backward has to walk)
     uint32_t *order_ws;      // [2][kOrderWs] bucket counts / cursors / arrival counters of the two tile_order launches (kept zero)
     uint32_t *order_fwd;     // [tiles] tiles by descending list length
-    uint32_t *order_bwd;     // [tiles] tiles by descending tile_maxlast
+    uint32_t *order_bwd;     // unused (the backward work items live in the binning buffer)
     size_t bytes;
 
     static ImageState carve(void *p, int W, int H) {
@@ -142,5 +162,8 @@ int validate_raster_inputs(const mb_raster_inputs *in, const char *who);
 // words; the kernel leaves them zeroed again.
 int tile_order(const uint32_t *weight_or_null, const uint2 *ranges_or_null, int tiles, uint32_t *order, uint32_t *ws,
                cudaStream_t s, bool debug);
+// Backward work items: (tile, segment) for every kSeg-entry segment of every tile's consumed list [0, maxlast), full
+// segments first, then the partial ones by descending length.  *n_items = number of items.  `ws` as for tile_order.
+int segment_items(const uint32_t *maxlast, int tiles, uint2 *items, uint32_t *n_items, uint32_t *ws, cudaStream_t s, bool debug);
 
 }  // namespace mb
