@@ -159,6 +159,20 @@ int mb_pose_backward(const mb_pose_inputs *in, const float *g_posed_xyz, const f
                      float *g_f_dc, float *g_f_rest, float *g_skin_wts, mb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Photometric loss of the training step, value and gradient in one pass:
+ *     loss = w_l1 * mean|pred - gt| + w_ssim * (1 - mean(ssim_map(pred, gt)))
+ * Replaces l1_loss + ssim/_ssim of src/utils/loss_utils.py:22-97 as called by src/modules/base.py:323-365 on HWC
+ * images (pred [H,W,3], gt [1,H,W,3]; weights config/{OBJ_GAUSSIAN,HAND_GAUSSIAN,COMPOSITE}.yaml:22-23).  Because the
+ * reference takes `channel = img.size(-3)` (= H for HWC), its 11x11 SSIM window filters every image row separately over
+ * the (W, 3) plane; this entry point reproduces exactly that.
+ * pred, gt, d_pred: dense [H,W,3].  loss_out[3] = (loss, mean |pred - gt|, mean ssim).  d_pred = d loss / d pred.
+ * ---------------------------------------------------------------------------------------------- */
+size_t mb_photometric_loss_workspace_bytes(int32_t height, int32_t width);
+int mb_photometric_loss(const float *pred, const float *gt, int32_t height, int32_t width, float w_l1, float w_ssim,
+                        float *loss_out /*[3]*/, float *d_pred /*[H,W,3]*/, void *workspace, size_t workspace_bytes,
+                        mb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * distCUDA2: mean squared distance to the 3 nearest other points (exact).
  * ---------------------------------------------------------------------------------------------- */
 size_t mb_knn_workspace_bytes(int32_t num_points);

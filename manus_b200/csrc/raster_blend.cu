@@ -25,6 +25,30 @@ constexpr int kAccStride = 12;              // floats per Gaussian in the gradie
 int build_instances(const mb_raster_inputs *in, const RasterDims &d, const GeomState &g, const BinningState &b,
                     const ImageState &im, int64_t capacity, cudaStream_t s);
 
+// Optional per-CTA timeline of the tile kernels (tools/cta_trace.py): compiled in with -DMB_TRACE_CTA only.
+#ifdef MB_TRACE_CTA
+constexpr int kTraceMax = 1 << 17;
+__device__ ulonglong2 g_trace[2][kTraceMax];   // [kernel][cta] = (start ns, end ns)
+__device__ uint32_t g_trace_work[2][kTraceMax];
+__device__ __forceinline__ unsigned long long trace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define MB_TRACE_BEGIN() const unsigned long long trace_t0 = trace_now()
+#define MB_TRACE_END(k, work)                                                                       \
+    do {                                                                                            \
+        __syncthreads();                                                                            \
+        if (threadIdx.x == 0 && blockIdx.x < kTraceMax) {                                           \
+            g_trace[k][blockIdx.x] = make_ulonglong2(trace_t0, trace_now());                        \
+            g_trace_work[k][blockIdx.x] = (uint32_t)(work);                                         \
+        }                                                                                           \
+    } while (0)
+#else
+#define MB_TRACE_BEGIN()
+#define MB_TRACE_END(k, work)
+#endif
+
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -124,6 +148,7 @@ __global__ void __launch_bounds__(kWarps * 32, 24 / kWarps) blend_forward_kernel
     float4 *__restrict__ ckpt) {
     constexpr int kSplit = 8 / kWarps;
     static_assert(kSeg % (kWarps * 32) == 0, "segment length must be a multiple of the batch size");
+    MB_TRACE_BEGIN();
     __shared__ __align__(128) StageSmem<kWarps> sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int item = blockIdx.x / kSplit, sub = blockIdx.x % kSplit;
@@ -226,6 +251,7 @@ __global__ void __launch_bounds__(kWarps * 32, 24 / kWarps) blend_forward_kernel
     }
     __syncthreads();
     if (tid == 0 && sm.red) atomicMax(&tile_maxlast[tile], sm.red);
+    MB_TRACE_END(0, sm.red);
 }
 
 // lane -> which of the 9 reduced values it owns after the reduce-scatter (or -1)
@@ -714,3 +740,14 @@ extern "C" int mb_raster_backward(const mb_raster_inputs *in, const int32_t *rad
     else preprocess_backward_kernel<false, false><<<grid, 256, 0, s>>>(a);
     return check_launch("preprocess_backward", dbg, s);
 }
+
+#ifdef MB_TRACE_CTA
+// (variant builds only) copies the per-CTA timeline of the last launch of tile kernel `kernel` (0 forward) to the host
+extern "C" int mb_debug_cta_trace(int kernel, unsigned long long *times_host /*[n][2]*/, uint32_t *work_host /*[n]*/, int n) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return MB_ERR_CUDA;
+    if (n > kTraceMax) n = kTraceMax;
+    MB_CUDA(cudaMemcpyFromSymbol(times_host, g_trace, sizeof(ulonglong2) * (size_t)n, sizeof(ulonglong2) * (size_t)kTraceMax * kernel));
+    MB_CUDA(cudaMemcpyFromSymbol(work_host, g_trace_work, sizeof(uint32_t) * (size_t)n, sizeof(uint32_t) * (size_t)kTraceMax * kernel));
+    return MB_OK;
+}
+#endif

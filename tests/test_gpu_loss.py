@@ -1,0 +1,73 @@
+"""Fused photometric loss (manus_b200/csrc/loss.cu) against the golden vectors of the reference's own loss_utils and
+against the pinned oracle at other sizes (ragged widths, one-chunk and many-chunk rows, 1080p)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN
+from oracle import loss_ref
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(GOLDEN, "loss_golden.npz"))
+
+
+def run(pred, gt, w_l1=0.8, w_ssim=0.2):
+    from manus_b200.losses import photometric_loss
+
+    p = torch.tensor(pred, device="cuda").requires_grad_(True)
+    loss, l1, ss = photometric_loss(p, torch.tensor(gt, device="cuda")[None], w_l1, w_ssim, return_terms=True)
+    loss.backward()
+    return float(loss), float(l1), float(ss), p.grad.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", ["a", "b", "c", "d"])
+def test_loss_matches_reference_golden(built_lib, name):
+    loss, l1, ss, grad = run(G[f"{name}_pred"], G[f"{name}_gt"])
+    assert abs(l1 - float(G[f"{name}_l1"])) <= 1e-6 and abs(ss - float(G[f"{name}_ssim"])) <= 2e-6
+    assert abs(loss - float(G[f"{name}_loss"])) <= 1e-6
+    ref = G[f"{name}_grad"]
+    assert np.abs(grad - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("H,W", [(3, 1), (2, 255), (2, 256), (3, 257), (4, 600), (9, 1920)])
+def test_loss_matches_oracle_ragged(built_lib, H, W):
+    rng = np.random.default_rng(H * 1000 + W)
+    gt = rng.uniform(0, 1, (H, W, 3)).astype(np.float32)
+    pred = np.clip(gt + rng.normal(0, 0.2, gt.shape), 0, 1.3).astype(np.float32)
+    pred[0, : W // 2] = gt[0, : W // 2]                   # exact zeros of pred - gt: sign(0) = 0
+    o = loss_ref.photometric_loss(pred, gt, 0.7, 0.3, np.float64)
+    loss, l1, ss, grad = run(pred, gt, 0.7, 0.3)
+    assert abs(loss - o["loss"]) <= 2e-6 and abs(l1 - o["l1"]) <= 1e-6 and abs(ss - o["ssim"]) <= 2e-6
+    assert np.abs(grad - o["grad"]).max() <= 1e-5 * np.abs(o["grad"]).max()
+
+
+def test_named_wrappers_and_upstream_gradient_scale(built_lib):
+    from manus_b200.losses import l1_loss, photometric_loss, ssim
+
+    pred, gt = G["a_pred"], G["a_gt"]
+    p = torch.tensor(pred, device="cuda").requires_grad_(True)
+    g = torch.tensor(gt, device="cuda")[None]
+    total = 0.8 * l1_loss(p, g) + 0.2 * (1.0 - ssim(p, g))            # the reference's own composition (base.py:329-365)
+    total.backward()
+    assert abs(float(total) - float(G["a_loss"])) <= 1e-6
+    assert np.abs(p.grad.cpu().numpy() - G["a_grad"]).max() <= 1e-5 * np.abs(G["a_grad"]).max()
+    p2 = torch.tensor(pred, device="cuda").requires_grad_(True)
+    (3.0 * photometric_loss(p2, g)).backward()
+    assert np.abs(p2.grad.cpu().numpy() - 3.0 * G["a_grad"]).max() <= 3e-5 * np.abs(G["a_grad"]).max()
+
+
+def test_full_size_properties(built_lib):
+    """1080p: identical images give ssim = 1, l1 = 0 and a zero gradient; the loss is reproducible bit for bit."""
+    from manus_b200.losses import photometric_loss
+
+    g = torch.rand(1080, 1920, 3, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    p = g.clone().requires_grad_(True)
+    loss, l1, ss = photometric_loss(p, g, return_terms=True)
+    loss.backward()
+    assert float(l1) == 0.0 and abs(float(ss) - 1.0) <= 1e-6 and float(p.grad.abs().max()) <= 1e-9
+    q = (g + 0.1 * torch.randn_like(g)).requires_grad_(True)
+    a = photometric_loss(q, g)
+    b = photometric_loss(q, g)
+    assert float(a) == float(b) and 0.0 < float(a) < 1.0
