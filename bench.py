@@ -321,7 +321,7 @@ def main():
             slot["bones"].copy_(b, non_blocking=True)
             slot["ready"].record(copy_stream)
 
-    def step_e2e(it):
+    def step_e2e(it, graphed=graphed, loss_fn=loss_fn):
         slot = slots[it % 2]
         if not slot.get("staged") == it:
             stage_inputs(it)                                    # first step of a run: nothing was prefetched
@@ -374,6 +374,13 @@ def main():
     ms_step = timed(step_resident, K, sampler)
     clocks = sampler.summary()
     ms_e2e = timed(step_e2e, K)
+    # the same end-to-end step with the reference's training loss 0.8 L1 + 0.2 (1 - SSIM) (fused kernel, manus_b200.losses)
+    from manus_b200.losses import photometric_loss
+    photo_fn = lambda image, target: photometric_loss(image, target, 0.8, 0.2)
+    graphed_photo = None if args.no_graph else GraphedStep(r, photo_fn, G_dev, view=views[0])
+    ms_e2e_photo = timed(lambda it: step_e2e(it, graphed_photo, photo_fn), K)
+    if graphed_photo is not None:
+        graphed_photo.check()
     # reserve mode reads nothing back per frame: make sure no timed frame ran out of instance capacity
     if graphed is not None:
         graphed.check()
@@ -412,6 +419,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+            "e2e_reference_loss": {"value": world * 1e3 / ms_e2e_photo, "unit": UNIT, "ms_per_step": ms_e2e_photo,
+                                   "loss": "0.8 * L1 + 0.2 * (1 - SSIM) as in config/COMPOSITE.yaml:22-23 (fused kernel), host inputs as in e2e"},
             "gpu_launches": int(round(launches_per_step * K)), "host_enqueue_ms_per_step": host_enqueue_ms,
             "launch_mode": "eager (one launch per kernel)" if graphed is None else "CUDA graph replay (one launch per step)",
             "roofline": roofline,

@@ -165,10 +165,13 @@ int mb_pose_backward(const mb_pose_inputs *in, const float *g_posed_xyz, const f
  * images (pred [H,W,3], gt [1,H,W,3]; weights config/{OBJ_GAUSSIAN,HAND_GAUSSIAN,COMPOSITE}.yaml:22-23).  Because the
  * reference takes `channel = img.size(-3)` (= H for HWC), its 11x11 SSIM window filters every image row separately over
  * the (W, 3) plane; this entry point reproduces exactly that.
- * pred, gt, d_pred: dense [H,W,3].  loss_out[3] = (loss, mean |pred - gt|, mean ssim).  d_pred = d loss / d pred.
+ * gt, d_pred: dense [H,W,3].  pred is addressed as pred[y*stride_y + x*stride_x + c*stride_c] (element strides), so the
+ * rasterizer's [3,H,W] output permuted to HWC (src/utils/gaussian_utils.py:418) is read in place.
+ * loss_out[3] = (loss, mean |pred - gt|, mean ssim).  d_pred = d loss / d pred.
  * ---------------------------------------------------------------------------------------------- */
 size_t mb_photometric_loss_workspace_bytes(int32_t height, int32_t width);
-int mb_photometric_loss(const float *pred, const float *gt, int32_t height, int32_t width, float w_l1, float w_ssim,
+int mb_photometric_loss(const float *pred, int64_t pred_stride_y, int64_t pred_stride_x, int64_t pred_stride_c,
+                        const float *gt, int32_t height, int32_t width, float w_l1, float w_ssim,
                         float *loss_out /*[3]*/, float *d_pred /*[H,W,3]*/, void *workspace, size_t workspace_bytes,
                         mb_stream_t stream);
 

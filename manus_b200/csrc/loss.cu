@@ -33,7 +33,8 @@ __device__ __forceinline__ void mix3(const float *v, float *out) {
     out[2] = g2 * v[0] + g1 * v[1] + g0 * v[2];
 }
 
-__global__ void __launch_bounds__(kLossThreads) photometric_loss_kernel(const float *__restrict__ pred, const float *__restrict__ gt,
+__global__ void __launch_bounds__(kLossThreads) photometric_loss_kernel(const float *__restrict__ pred, int64_t ps_y, int64_t ps_x,
+                                                                        int64_t ps_c, const float *__restrict__ gt,
                                                                         int H, int W, float w_l1, float w_ssim,
                                                                         float *__restrict__ d_pred, double2 *__restrict__ partials) {
     __shared__ float sp[kLossLoad * 3], sg[kLossLoad * 3];      // staged rows, pixel-major (HWC)
@@ -41,14 +42,19 @@ __global__ void __launch_bounds__(kLossThreads) photometric_loss_kernel(const fl
     __shared__ float red[2][kLossThreads / 32];
     const int tid = threadIdx.x, y = blockIdx.y;
     const int x0 = blockIdx.x * kLossChunk;                     // first output pixel of this CTA
-    const float *prow = pred + (size_t)y * W * 3, *grow = gt + (size_t)y * W * 3;
-    // stage pixels [x0 - 10, x0 + 266) of the row; zero outside the image (conv2d zero padding)
+    const float *prow = pred + (int64_t)y * ps_y, *grow = gt + (size_t)y * W * 3;
+    // stage pixels [x0 - 10, x0 + 266) of the row; zero outside the image (conv2d zero padding).  gt is dense HWC; pred is
+    // read with its own strides (the rasterizer's [3,H,W] output viewed as HWC: three coalesced plane reads)
     for (int e = tid; e < kLossLoad * 3; e += kLossThreads) {
         const int xe = x0 - kLossHalo + e / 3;
         const bool in = xe >= 0 && xe < W;
         const ptrdiff_t off = (ptrdiff_t)(x0 - kLossHalo) * 3 + e;
-        sp[e] = in ? prow[off] : 0.f;
         sg[e] = in ? grow[off] : 0.f;
+    }
+    for (int e = tid; e < kLossLoad * 3; e += kLossThreads) {
+        const int c = e / kLossLoad, j = e - c * kLossLoad, xe = x0 - kLossHalo + j;   // channel-major order: coalesced for planar pred
+        const bool in = xe >= 0 && xe < W;
+        sp[j * 3 + c] = in ? prow[(int64_t)xe * ps_x + (int64_t)c * ps_c] : 0.f;
     }
     __syncthreads();
     const float inv_n = 1.0f / ((float)H * (float)W * 3.0f);
@@ -163,7 +169,8 @@ extern "C" size_t mb_photometric_loss_workspace_bytes(int32_t height, int32_t wi
     return align_up(chunks * sizeof(double2));
 }
 
-extern "C" int mb_photometric_loss(const float *pred, const float *gt, int32_t height, int32_t width, float w_l1, float w_ssim,
+extern "C" int mb_photometric_loss(const float *pred, int64_t pred_stride_y, int64_t pred_stride_x, int64_t pred_stride_c,
+                                   const float *gt, int32_t height, int32_t width, float w_l1, float w_ssim,
                                    float *loss_out, float *d_pred, void *workspace, size_t workspace_bytes, mb_stream_t stream) {
     MB_REQUIRE(height > 0 && width > 0, "mb_photometric_loss: bad image size %d x %d", width, height);
     MB_REQUIRE(pred && gt && loss_out && d_pred && workspace, "mb_photometric_loss: null pointer");
@@ -177,7 +184,8 @@ extern "C" int mb_photometric_loss(const float *pred, const float *gt, int32_t h
     double2 *partials = reinterpret_cast<double2 *>(workspace);
     {
         KernelTimer kt("photometric_loss", s);
-        photometric_loss_kernel<<<grid, kLossThreads, 0, s>>>(pred, gt, height, width, w_l1, w_ssim, d_pred, partials);
+        photometric_loss_kernel<<<grid, kLossThreads, 0, s>>>(pred, pred_stride_y, pred_stride_x, pred_stride_c, gt, height, width, w_l1, w_ssim,
+                                                              d_pred, partials);
     }
     int rc = check_launch("photometric_loss", false, s);
     if (rc) return rc;

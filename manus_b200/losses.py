@@ -15,30 +15,32 @@ from . import _lib
 from ._lib import ptr
 
 
-def _hw3(t: torch.Tensor, what: str) -> torch.Tensor:
+def _hw3(t: torch.Tensor, what: str, dense: bool) -> torch.Tensor:
     if t.dim() == 4 and t.shape[0] == 1:
         t = t[0]
     if t.dim() != 3 or t.shape[-1] != 3:
         raise RuntimeError(f"{what} must be [H,W,3] (or [1,H,W,3]) like pred['render'] / batch['rgb'][..., :3], got {tuple(t.shape)}")
     if not t.is_cuda:
         raise _lib.ManusB200Error("manus_b200.losses needs CUDA tensors (there is no CPU path)")
-    return t.float().contiguous()
+    t = t.float()
+    return t.contiguous() if dense else t      # pred is read with its strides (permuted [3,H,W] rasterizer output)
 
 
 class _PhotometricLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, gt, w_l1, w_ssim):
         L = _lib.lib()
-        p, g = _hw3(pred.detach(), "pred"), _hw3(gt.detach(), "gt")
+        p, g = _hw3(pred.detach(), "pred", False), _hw3(gt.detach(), "gt", True)
         if p.shape != g.shape:
             raise RuntimeError(f"pred {tuple(p.shape)} and gt {tuple(g.shape)} differ")
         H, W, _ = p.shape
         dev = p.device
         out = torch.empty(3, dtype=torch.float32, device=dev)
-        d_pred = torch.empty_like(p)
+        d_pred = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+        sy, sx, sc = p.stride()
         with torch.cuda.device(dev):
             ws = torch.empty(L.mb_photometric_loss_workspace_bytes(H, W), dtype=torch.uint8, device=dev)
-            _lib.check(L.mb_photometric_loss(ptr(p), ptr(g), H, W, float(w_l1), float(w_ssim), ptr(out), ptr(d_pred), ptr(ws), ws.numel(),
+            _lib.check(L.mb_photometric_loss(ptr(p), sy, sx, sc, ptr(g), H, W, float(w_l1), float(w_ssim), ptr(out), ptr(d_pred), ptr(ws), ws.numel(),
                                              torch.cuda.current_stream(dev).cuda_stream), "mb_photometric_loss")
         ctx.d_pred = d_pred
         ctx.pred_shape = pred.shape

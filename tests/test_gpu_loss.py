@@ -71,3 +71,15 @@ def test_full_size_properties(built_lib):
     a = photometric_loss(q, g)
     b = photometric_loss(q, g)
     assert float(a) == float(b) and 0.0 < float(a) < 1.0
+
+
+def test_permuted_rasterizer_layout_is_read_in_place(built_lib):
+    """pred as the rasterizer hands it over: [3,H,W] storage viewed as HWC (gaussian_utils.py:418)."""
+    from manus_b200.losses import photometric_loss
+
+    chw = torch.tensor(G["b_pred"], device="cuda").permute(2, 0, 1).contiguous().requires_grad_(True)
+    loss = photometric_loss(chw.permute(1, 2, 0), torch.tensor(G["b_gt"], device="cuda"))
+    loss.backward()
+    assert abs(float(loss) - float(G["b_loss"])) <= 1e-6
+    ref = np.transpose(G["b_grad"], (2, 0, 1))
+    assert np.abs(chw.grad.cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
