@@ -159,6 +159,21 @@ int mb_pose_backward(const mb_pose_inputs *in, const float *g_posed_xyz, const f
                      float *g_f_dc, float *g_f_rest, float *g_skin_wts, mb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Per-frame skin-weight lookup: skin_wts[i,:] = normalise(trilinear(grid_weights, xyz[i])).
+ * Replaces skinning_weights_from_voxel_grid (src/utils/gaussian_utils.py:167-196: grid_sample with align_corners=True and zero
+ * padding on the [D,H,W,C] grid, coord = (xyz - grid_center) / grid_scale with x -> W, y -> H, z -> D, then w / w.sum(-1)),
+ * called every step by HandGaussianModel.get_skin_weights (src/models/hand_gaussian.py:65-76).
+ * grid_weights: [D,H,W,C] as stored by the reference (C <= 64); grid_center [3], grid_scale [3] in device memory.
+ * Backward: g_xyz [N,3] is written; g_grid_weights ([D,H,W,C], may be NULL) is ACCUMULATED into (zero it first).
+ * ---------------------------------------------------------------------------------------------- */
+int mb_skin_weights_forward(const float *xyz, int32_t num_points, const float *grid_weights, int32_t depth, int32_t height,
+                            int32_t width, int32_t channels, const float *grid_center, const float *grid_scale,
+                            float *skin_wts /*[N,C]*/, mb_stream_t stream);
+int mb_skin_weights_backward(const float *xyz, int32_t num_points, const float *grid_weights, int32_t depth, int32_t height,
+                             int32_t width, int32_t channels, const float *grid_center, const float *grid_scale,
+                             const float *g_skin_wts /*[N,C]*/, float *g_xyz /*[N,3]*/, float *g_grid_weights, mb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Photometric loss of the training step, value and gradient in one pass:
  *     loss = w_l1 * mean|pred - gt| + w_ssim * (1 - mean(ssim_map(pred, gt)))
  * Replaces l1_loss + ssim/_ssim of src/utils/loss_utils.py:22-97 as called by src/modules/base.py:323-365 on HWC
