@@ -191,6 +191,17 @@ int mb_photometric_loss(const float *pred, int64_t pred_stride_y, int64_t pred_s
                         mb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused Adam over the flat parameter buffer.  Replaces the per-step work of
+ * torch.optim.Adam(l, lr=0, eps=1e-15) with its six lr-only param groups (src/models/gaussian.py:133-141): one kernel over
+ * elements [begin, end) of flat buffers whose segments [segment_end[s-1], segment_end[s]) use learning rate lr[s].
+ * step = 1-based step count t (bias corrections 1 - beta^t as in torch); grad is multiplied by grad_scale first
+ * (e.g. 1 / number of views).  segment_end_host / lr_host are HOST arrays of num_segments (<= 8) entries.
+ * ---------------------------------------------------------------------------------------------- */
+int mb_fused_adam(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t begin, int64_t end,
+                  int32_t num_segments, const int64_t *segment_end_host, const double *lr_host, int64_t step, double beta1,
+                  double beta2, double eps, float grad_scale, mb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * distCUDA2: mean squared distance to the 3 nearest other points (exact).
  * ---------------------------------------------------------------------------------------------- */
 size_t mb_knn_workspace_bytes(int32_t num_points);

@@ -64,6 +64,8 @@ SIGNATURES = {
                                           C.c_void_p, C.c_void_p]),
     "mb_skin_weights_backward": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mb_fused_adam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int64),
+                                C.POINTER(C.c_double), C.c_int64, C.c_double, C.c_double, C.c_double, C.c_float, C.c_void_p]),
     "mb_photometric_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "mb_photometric_loss": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -93,3 +93,42 @@ def test_two_ranks_equal_gradient_accumulation(tmp_path, views):
         np.testing.assert_allclose(got, ref_grad.numpy(), rtol=2e-6, atol=2e-6)       # fp32 sum order differs only
         assert abs(float(np.load(tmp_path / f"loss_{r}.npy")[0]) - ref_loss) < 1e-6
         np.testing.assert_allclose(np.load(tmp_path / f"avg_{r}.npy"), np.full(5, 1.5))
+
+
+# ---- ZeRO-1 style optimiser step (manus_b200.optim.sharded_adam_step): host logic on CPU with a stand-in update rule
+class _StubOpt:
+    """Same interface as FlatAdam, elementwise update p -= lr * g * grad_scale on the requested slice (CPU)."""
+
+    def __init__(self, flat):
+        self.flat, self.numel = flat, flat.data.numel()
+
+    def step(self, shard=None, grad=None, grad_scale=1.0, advance=True):
+        b, e = (0, self.numel) if shard is None else shard
+        g = self.flat.grad if grad is None else grad
+        self.flat.data[b:e] -= 0.1 * g[b:e] * grad_scale
+
+
+def _opt_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from manus_b200.optim import sharded_adam_step
+
+        flat = make_flat()
+        flat.grad.copy_(torch.arange(flat.grad.numel(), dtype=torch.float32) * (rank + 1) * 1e-3)
+        sharded_adam_step(_StubOpt(flat), n_views=world)
+        np.save(os.path.join(out_dir, f"param_{rank}.npy"), flat.data.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_optimizer_step_equals_allreduce_then_full_step(tmp_path):
+    world = 2
+    mp.spawn(_opt_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    flat = make_flat()
+    g = sum(torch.arange(flat.grad.numel(), dtype=torch.float32) * (r + 1) * 1e-3 for r in range(world))
+    flat.grad.copy_(g)
+    _StubOpt(flat).step(grad_scale=1.0 / world)
+    for r in range(world):
+        np.testing.assert_allclose(np.load(tmp_path / f"param_{r}.npy"), flat.data.numpy(), rtol=1e-6, atol=1e-7)
