@@ -209,6 +209,16 @@ int mb_dist2_knn3(const float *points /*[N,3]*/, int32_t num_points, float *out 
                   size_t workspace_bytes, mb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Contact distance: for every query point the Euclidean distance to, and the index of, its
+ * nearest reference point (exact; ties -> lowest index).  Replaces get_contact_dist (src/utils/gaussian_utils.py:521-554, an
+ * O(N*M) taichi loop; used by src/modules/composite.py:151-175 and scripts/process/mano_contacts.py:35) and get_contact_map
+ * (:514-518).  workspace: mb_nearest_workspace_bytes(num_queries, num_refs).
+ * ---------------------------------------------------------------------------------------------- */
+size_t mb_nearest_workspace_bytes(int32_t num_queries, int32_t num_refs);
+int mb_nearest_point(const float *queries /*[N,3]*/, int32_t num_queries, const float *refs /*[M,3]*/, int32_t num_refs,
+                     float *out_dist /*[N]*/, int32_t *out_index /*[N]*/, void *workspace, size_t workspace_bytes, mb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Utility exported for tests: stable LSD radix sort of (u32 key, u32 value) pairs on key bits [0, end_bit).
  * n may be given on the host (n_host >= 0) or read from device memory (*n_dev, when n_host < 0, bounded by max_n).
  * Result lands in keys_out / vals_out.  workspace: mb_sort_workspace_bytes(max_n).

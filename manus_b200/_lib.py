@@ -71,6 +71,8 @@ SIGNATURES = {
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mb_knn_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "mb_dist2_knn3": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mb_nearest_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "mb_nearest_point": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mb_sort_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "mb_radix_sort_pairs": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_size_t,
                                                         C.c_void_p]),

@@ -14,12 +14,14 @@
 namespace mb {
 
 constexpr int kBox = 1024;
+constexpr int kFine = 64;     // second, finer level of boxes inside every kBox run
 
 struct KnnWorkspace {
     uint32_t *minmax;  // 6 ordered-uint encoded floats: min xyz, max xyz
     uint32_t *codes, *ident, *codes_sorted, *order;
     float4 *pts;       // Morton order: x, y, z, original index (bits)
     float4 *box_lo, *box_hi;
+    float4 *fine_lo, *fine_hi;   // bounds of every run of kFine sorted points (nearest-point search only)
     void *sort_ws;
     size_t bytes;
     static KnnWorkspace carve(void *p, int64_t n) {
@@ -34,6 +36,8 @@ struct KnnWorkspace {
         w.pts = c.take<float4>(m);
         w.box_lo = c.take<float4>(boxes);
         w.box_hi = c.take<float4>(boxes);
+        w.fine_lo = c.take<float4>(boxes * (kBox / kFine));
+        w.fine_hi = c.take<float4>(boxes * (kBox / kFine));
         w.sort_ws = c.take<char>(sort_workspace_bytes((int64_t)m));
         w.bytes = c.off;
         return w;
@@ -112,11 +116,11 @@ __global__ void __launch_bounds__(256) knn_gather_kernel(const float *__restrict
 }
 
 __global__ void __launch_bounds__(256) knn_box_kernel(const float4 *__restrict__ sorted, int n, float4 *__restrict__ box_lo,
-                                                      float4 *__restrict__ box_hi) {
+                                                      float4 *__restrict__ box_hi, int bsz = kBox) {
     __shared__ float slo[8][3], shi[8][3];
     const int box = blockIdx.x;
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (int j = box * kBox + threadIdx.x; j < min(n, (box + 1) * kBox); j += 256) {
+    for (int j = box * bsz + threadIdx.x; j < min(n, (box + 1) * bsz); j += 256) {
         const float4 p = sorted[j];
         lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
         hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
@@ -184,9 +188,110 @@ __global__ void __launch_bounds__(256) knn_search_kernel(const float4 *__restric
     out[__float_as_uint(p.w)] = (b0 + b1 + b2) / 3.0f;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Nearest reference point of every query point (exact): the "contact distance" of the composite scene.
+// Replaces get_contact_dist (src/utils/gaussian_utils.py:521-554: an O(N*M) taichi loop, first index of the minimum) and
+// get_contact_map (:514-518: chunked torch.cdist().min()).  Both sets are Morton-ordered on their common bounding box;
+// a query starts from the reference points around its own Morton position (a tight upper bound), then descends only into
+// the 1024-point boxes, and inside them the 64-point boxes, that can still hold something closer.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void nearest_consider(float d2, uint32_t idx, float &best_d2, float &best_s, uint32_t &best_i) {
+    // the reference compares sqrt(d2) with '<' in ascending reference index: emulate that order-independently
+    if (d2 > best_d2 * 1.000001f) return;
+    const float sq = sqrtf(d2);
+    if (sq < best_s || (sq == best_s && idx < best_i)) {
+        best_s = sq;
+        best_i = idx;
+        best_d2 = fminf(best_d2, d2);
+    }
+}
+
+__global__ void __launch_bounds__(256) nearest_search_kernel(const float4 *__restrict__ queries, int nq, const uint32_t *__restrict__ qcodes,
+                                                             const float4 *__restrict__ refs, int nr, const uint32_t *__restrict__ rcodes,
+                                                             const float4 *__restrict__ box_lo, const float4 *__restrict__ box_hi, int boxes,
+                                                             const float4 *__restrict__ fine_lo, const float4 *__restrict__ fine_hi,
+                                                             float *__restrict__ out_dist, int32_t *__restrict__ out_idx) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nq) return;
+    const float4 p = queries[j];
+    // position of the query's Morton code among the reference codes
+    const uint32_t code = qcodes[j];
+    int lo = 0, hi = nr;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (rcodes[mid] < code) lo = mid + 1; else hi = mid;
+    }
+    float best_d2 = FLT_MAX, best_s = FLT_MAX;
+    uint32_t best_i = 0xffffffffu;
+    for (int k = max(0, lo - 4); k < min(nr, lo + 4); ++k) {
+        const float4 r = refs[k];
+        nearest_consider(dist2(p, r), __float_as_uint(r.w), best_d2, best_s, best_i);
+    }
+    for (int b = 0; b < boxes; ++b) {
+        const float4 blo = box_lo[b], bhi = box_hi[b];
+        const float ex = fmaxf(fmaxf(blo.x - p.x, p.x - bhi.x), 0.f), ey = fmaxf(fmaxf(blo.y - p.y, p.y - bhi.y), 0.f),
+                    ez = fmaxf(fmaxf(blo.z - p.z, p.z - bhi.z), 0.f);
+        if (ex * ex + ey * ey + ez * ez > best_d2 * 1.000001f) continue;
+        const int fend = min((nr + kFine - 1) / kFine, (b + 1) * (kBox / kFine));
+        for (int f = b * (kBox / kFine); f < fend; ++f) {
+            const float4 flo = fine_lo[f], fhi = fine_hi[f];
+            const float fx = fmaxf(fmaxf(flo.x - p.x, p.x - fhi.x), 0.f), fy = fmaxf(fmaxf(flo.y - p.y, p.y - fhi.y), 0.f),
+                        fz = fmaxf(fmaxf(flo.z - p.z, p.z - fhi.z), 0.f);
+            if (fx * fx + fy * fy + fz * fz > best_d2 * 1.000001f) continue;
+            const int end = min(nr, (f + 1) * kFine);
+            for (int k = f * kFine; k < end; ++k) {
+                const float4 r = refs[k];
+                nearest_consider(dist2(p, r), __float_as_uint(r.w), best_d2, best_s, best_i);
+            }
+        }
+    }
+    const uint32_t qi = __float_as_uint(p.w);
+    out_dist[qi] = best_s;
+    out_idx[qi] = (int32_t)best_i;
+}
+
 }  // namespace mb
 
 using namespace mb;
+
+extern "C" size_t mb_nearest_workspace_bytes(int32_t num_queries, int32_t num_refs) {
+    return KnnWorkspace::carve(nullptr, num_queries).bytes + KnnWorkspace::carve(nullptr, num_refs).bytes;
+}
+
+extern "C" int mb_nearest_point(const float *queries, int32_t nq, const float *refs, int32_t nr, float *out_dist, int32_t *out_index,
+                                void *workspace, size_t workspace_bytes, mb_stream_t stream) {
+    MB_REQUIRE(nq >= 0 && nr > 0, "mb_nearest_point: need at least one reference point (nq=%d nr=%d)", nq, nr);
+    if (nq == 0) return MB_OK;
+    MB_REQUIRE(queries && refs && out_dist && out_index && workspace, "mb_nearest_point: null pointer");
+    if (workspace_bytes < mb_nearest_workspace_bytes(nq, nr)) {
+        set_error("mb_nearest_point: workspace too small");
+        return MB_ERR_WORKSPACE;
+    }
+    KnnWorkspace wq = KnnWorkspace::carve(workspace, nq);
+    KnnWorkspace wr = KnnWorkspace::carve(reinterpret_cast<char *>(workspace) + wq.bytes, nr);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int gq = (nq + 255) / 256, gr = (nr + 255) / 256, boxes = (nr + kBox - 1) / kBox;
+    KernelTimer kt("nearest_point", s);
+    // common bounding box -> comparable Morton codes
+    knn_init_kernel<<<1, 32, 0, s>>>(wr.minmax);
+    knn_bounds_kernel<<<min(gq, sm_count() * 8), 256, 0, s>>>(queries, nq, wr.minmax);
+    knn_bounds_kernel<<<min(gr, sm_count() * 8), 256, 0, s>>>(refs, nr, wr.minmax);
+    knn_morton_kernel<<<gr, 256, 0, s>>>(refs, nr, wr.minmax, wr.codes, wr.ident);
+    knn_morton_kernel<<<gq, 256, 0, s>>>(queries, nq, wr.minmax, wq.codes, wq.ident);
+    int rc = check_launch("nearest_morton", false, s);
+    if (rc) return rc;
+    rc = radix_sort_pairs(wr.codes, wr.ident, wr.codes_sorted, wr.order, nr, nullptr, nr, 0, 30, carve_sort_workspace(wr.sort_ws, nr), s, false);
+    if (rc) return rc;
+    rc = radix_sort_pairs(wq.codes, wq.ident, wq.codes_sorted, wq.order, nq, nullptr, nq, 0, 30, carve_sort_workspace(wq.sort_ws, nq), s, false);
+    if (rc) return rc;
+    knn_gather_kernel<<<gr, 256, 0, s>>>(refs, nr, wr.order, wr.pts);
+    knn_gather_kernel<<<gq, 256, 0, s>>>(queries, nq, wq.order, wq.pts);
+    knn_box_kernel<<<boxes, 256, 0, s>>>(wr.pts, nr, wr.box_lo, wr.box_hi, kBox);
+    knn_box_kernel<<<(nr + kFine - 1) / kFine, 256, 0, s>>>(wr.pts, nr, wr.fine_lo, wr.fine_hi, kFine);
+    nearest_search_kernel<<<gq, 256, 0, s>>>(wq.pts, nq, wq.codes_sorted, wr.pts, nr, wr.codes_sorted, wr.box_lo, wr.box_hi, boxes, wr.fine_lo,
+                                             wr.fine_hi, out_dist, out_index);
+    return check_launch("nearest_search", false, s);
+}
 
 extern "C" size_t mb_knn_workspace_bytes(int32_t num_points) { return KnnWorkspace::carve(nullptr, num_points).bytes; }
 

@@ -38,3 +38,19 @@ def dist2_knn3_bruteforce(points: np.ndarray) -> np.ndarray:
         best = np.sort(d2)[:3]
         out[i] = np.float32((best[0] + best[1] + best[2]) / np.float32(3.0))
     return out
+
+
+def contact_dist(pt1: np.ndarray, pt2: np.ndarray):
+    """Restates get_contact_dist (/root/reference/src/utils/gaussian_utils.py:521-554): for every point of pt1 the
+    Euclidean distance to the nearest point of pt2 and its index, first index of the minimum (strict '<' in ascending j).
+    The reference loop is a taichi kernel (taichi is not installable here), so this restatement is pinned only by the
+    exact k-d tree cross-check in tests/test_oracle_knn_contact.py.  O(N*M) in float32, chunked."""
+    a, b = np.asarray(pt1, np.float32), np.asarray(pt2, np.float32)
+    dist, idx = np.zeros(a.shape[0], np.float32), np.zeros(a.shape[0], np.int64)
+    for s in range(0, a.shape[0], 2048):
+        d = a[s:s + 2048, None, :] - b[None, :, :]
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]      # accumulation order of the reference loop
+        dd = np.sqrt(d2)
+        idx[s:s + 2048] = dd.argmin(1)                                                    # first minimum
+        dist[s:s + 2048] = dd.min(1)
+    return dist, idx
