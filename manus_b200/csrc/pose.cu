@@ -20,7 +20,10 @@
 
 namespace mb {
 
-constexpr int kPoseThreads = 128;   // Gaussians per tile = threads per CTA
+#ifndef MB_POSE_THREADS
+#define MB_POSE_THREADS 128
+#endif
+constexpr int kPoseThreads = MB_POSE_THREADS;   // Gaussians per tile = threads per CTA
 constexpr int kMaxBones = 64;
 constexpr int kMaxArrays = 12;
 
@@ -562,7 +565,7 @@ static int launch_pose(PoseArgs a, bool backward, cudaStream_t s) {
                   a.K, a.B, smem);
         return MB_ERR_INVALID;
     }
-    if (per_sm > 8) per_sm = 8;
+    if (per_sm > 16) per_sm = 16;
     const int grid = min(ntiles, sm_count() * per_sm);
     // raise the dynamic shared-memory limit once per (kernel, device): not a stream operation, kept out of the per-frame path
     static thread_local int limit[2][16] = {};

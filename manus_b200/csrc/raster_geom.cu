@@ -125,8 +125,26 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {   // `a` i
                 if (area > 0) {
                     visible = true;
                     radius = rad;
-                    tiles = (uint32_t)area;
                     key = __float_as_uint(tz);
+                    const float op = a.opac[i];
+                    // below this power, op * exp(power) < 1/255 with a wide margin (NaN for op < 0: never skips)
+                    const float cut = -logf(255.0f * op) - 1e-4f;
+                    // half extents of the bounding box of { power >= cut }: dx^2 <= 2|cut| cov2D.xx, dy^2 <= 2|cut| cov2D.yy
+                    // (NaN when no pixel can pass the alpha gate: such a record never survives the tile kernels' box test)
+                    const float ex = sqrtf(-2.0f * cut * ca) * 1.0001f + 0.01f, ey = sqrtf(-2.0f * cut * cc) * 1.0001f + 0.01f;
+                    // Instances are only emitted for the tiles of upstream's rectangle that this box reaches: in the others
+                    // every pixel fails the alpha >= 1/255 gate, so dropping them changes neither image nor gradients
+                    // (it only shortens the lists; radii and visibility stay upstream's).
+                    if (ex >= 0.f && ey >= 0.f) {
+                        x0 = max(x0, (int)floorf((px - ex) / kTile));
+                        y0 = max(y0, (int)floorf((py - ey) / kTile));
+                        x1 = min(x1, (int)floorf((px + ex) / kTile) + 1);
+                        y1 = min(y1, (int)floorf((py + ey) / kTile) + 1);
+                        tiles = (uint32_t)(max(x1 - x0, 0) * max(y1 - y0, 0));
+                    } else {
+                        tiles = 0;
+                    }
+                    if (tiles == 0) x0 = y0 = x1 = y1 = 0;
                     a.g.rect[i] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
                     float rgb[3];
                     if (kSH) {   // step 10: colour from SH in the world-space view direction
@@ -151,12 +169,6 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {   // `a` i
 #pragma unroll
                         for (int ch = 0; ch < 3; ++ch) rgb[ch] = a.colors[3 * (size_t)i + ch];
                     }
-                    const float op = a.opac[i];
-                    // below this power, op * exp(power) < 1/255 with a wide margin (NaN for op < 0: never skips)
-                    const float cut = -logf(255.0f * op) - 1e-4f;
-                    // half extents of the bounding box of { power >= cut }: dx^2 <= 2|cut| cov2D.xx, dy^2 <= 2|cut| cov2D.yy
-                    // (NaN when no pixel can pass the alpha gate: such a record never survives the tile kernels' box test)
-                    const float ex = sqrtf(-2.0f * cut * ca) * 1.0001f + 0.01f, ey = sqrtf(-2.0f * cut * cc) * 1.0001f + 0.01f;
                     Record r;
                     r.a = make_float4(px, py, cc * di, -cb * di);
                     r.b = make_float4(ca * di, op, rgb[0], rgb[1]);
