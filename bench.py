@@ -140,6 +140,19 @@ class ClockSampler:
                 "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
+def measured_traffic(kernel):
+    """DRAM bytes (read + write) of one launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json,
+    written by profiles/extract_traffic.py); None when the capture does not hold it."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f).get(kernel)
+    if not t or "dram_read_bytes" not in t:
+        return None
+    return t["dram_read_bytes"] + t.get("dram_write_bytes", 0.0)
+
+
 def frame_bytes(n_hand, n_obj, D, P):
     """Algorithmic HBM bytes of one forward+backward frame (SURVEY.md section 8d / BASELINE.md section 4)."""
     return 1204 * n_hand + 1036 * n_obj + 244 * D + 40 * P
@@ -410,7 +423,8 @@ def main():
     per_launch_ms = top_ms / top_n
     fb = KERNEL_BYTES.get(top_name, lambda *a: None)(scene.n, n_hand, D_mean, P, V_mean)
     roofline = {"bound": "hbm", "kernel": top_name, "achieved": (fb / (per_launch_ms * 1e-3) / 1e9) if fb else None, "peak": peak,
-                "unit": "GB/s", "frac": (fb / (per_launch_ms * 1e-3) / 1e9 / peak) if fb else None, "traffic": None,
+                "unit": "GB/s", "frac": (fb / (per_launch_ms * 1e-3) / 1e9 / peak) if fb else None, "traffic": measured_traffic(top_name),
+                "traffic_source": "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, per launch)",
                 "peak_source": peak_src, "launch_ms": per_launch_ms, "share_of_step": top_ms / total_ms if total_ms else None,
                 "algorithmic_bytes_per_launch": fb,
                 "kernels_ms_per_step": {k: round(ms / K, 5) for k, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
