@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--views", type=int, default=50)
+    ap.add_argument("--scene", default="composite", choices=["composite", "hand", "object"],
+                    help="composite = BASELINE configs[3] (headline); hand = configs[2]; object = configs[1] (use --gaussians 100000 --width 800 --height 800)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python each step instead of replaying the captured CUDA graph")
     return ap.parse_args()
@@ -219,7 +221,7 @@ def run_reference(args, rank, world):
     from manus_b200 import synth
 
     threads = os.cpu_count() or 1
-    scene = synth.make_composite(args.gaussians, seed=0)
+    scene = make_scene(args)
     budget_s = 150.0          # the whole reference run must end within a few minutes
     t_warm = []
     for i in range(min(max(args.warmup, 1), 1)):
@@ -242,8 +244,20 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def make_scene(args):
+    from manus_b200 import synth
+
+    if args.scene == "hand":
+        return synth.make_hand(args.gaussians, seed=0)
+    if args.scene == "object":
+        return synth.make_object(args.gaussians, seed=1)
+    return synth.make_composite(args.gaussians, seed=0)
+
+
 def workload_config(args, world):
-    return {"workload": f"composite hand+object {args.gaussians} Gaussians (60% skinned by 20+1 bones, 40% static), "
+    kind = {"composite": "composite hand+object {n} Gaussians (60% skinned by 20+1 bones, 40% static)",
+            "hand": "articulated hand {n} Gaussians (all skinned by 20+1 bones)", "object": "static object {n} Gaussians (no skinning)"}[args.scene]
+    return {"workload": kind.format(n=args.gaussians) + ", " +
                         f"{args.views} shipped views/poses at {args.width}x{args.height}, SH degree 3, white background",
             "global_views_per_step": world, "parallelism": f"view-sharded dp{world}, one all-reduce of the flat gradient buffer",
             "l2": "working set per step (parameters 118 MB + gradients 118 MB + instance records) exceeds the 126 MB L2 and the view "
@@ -283,7 +297,7 @@ def main():
     _lib.lib()
 
     W, H, K, WU = args.width, args.height, args.steps, max(args.warmup, 3)
-    scene = synth.make_composite(args.gaussians, seed=0)
+    scene = make_scene(args)
     r = SceneRenderer(scene, dev, W, H)
     n_hand, n_obj = scene.n_hand, scene.n - scene.n_hand
     views = list(range(args.views))
