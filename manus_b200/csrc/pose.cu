@@ -271,7 +271,11 @@ struct TilePipe {
         fence_proxy_async();
         __syncthreads();
         Transfer t[kMaxArrays];
+#ifdef MB_POSE_NOSTORE      // experiment switch: loads only
+        const int n = 0;
+#else
         const int n = outputs(tile, t);
+#endif
         for (int j = 0; j < n; ++j) {
             if (!t[j].bytes) continue;
             float *dst = const_cast<float *>(t[j].g);
@@ -316,7 +320,9 @@ __device__ __forceinline__ void run_tiles(const PoseArgs &a, float *smem, Body b
             __syncthreads();
             pipe.acquire(tile, 0, phase);
             const int row = threadIdx.x, i = tile * kPoseThreads + row;
+#ifndef MB_POSE_NOCOMPUTE   // experiment switch (tools/pose_bench.py): data movement only
             if (i < a.N) body(pipe.L, pipe.stage(0), i, row, bones_s, cam_s);
+#endif
             pipe.release(tile, 0);
         }
     } else {

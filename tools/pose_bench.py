@@ -20,9 +20,13 @@ for it in range(12):
 rep = _lib.profile_report()
 print({k: round(ms / n * 1e3, 1) for k, (n, ms) in rep.items() if k.startswith("pose")})
 ''' % ROOT
-for lib in sys.argv[1:] or [""]:
+for spec in sys.argv[1:] or [""]:
     env = dict(os.environ)
+    lib, *extra = spec.split(",")          # "path/to/lib.so,NAME=VALUE,..." sets environment variables for that run
+    for kv in extra:
+        k, v = kv.split("=", 1)
+        env[k] = v
     if lib:
         env["MANUS_B200_LIB"] = os.path.abspath(lib)
     out = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
-    print(os.path.basename(lib) or "default", out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-400:])
+    print(os.path.basename(spec) or "default", out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-400:])
