@@ -122,6 +122,17 @@ def small_scene(seed, N=3000, W=160, H=120, zoom=1.6, scale_boost=0.3, opacity_b
     return sc, cam, posed_scene(sc, 3 * seed + 1, cam, scale_boost, opacity_boost)
 
 
+def test_many_backward_segments(built_lib, raster_ref, raster_ref64):
+    """Faint Gaussians: no pixel saturates, so whole lists of several thousand entries are consumed and the backward
+    walks them as many 512-entry segments resumed from the forward's checkpoints."""
+    from manus_b200.rasterizer import debug_views
+
+    sc, cam, ps = small_scene(5, N=30000, W=70, H=50, zoom=0.9, scale_boost=0.0, opacity_boost=-3.0)
+    G = np.random.default_rng(2).uniform(-1, 1, (3, cam.height, cam.width)).astype(np.float32)
+    st = check_against_oracle(cam, (0.3, 0.1, 0.7), ps, raster_ref, raster_ref64, G)
+    assert int(debug_views(st)["tile_maxlast"].max()) > 4 * 512
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_hand_scene_forward_backward(built_lib, raster_ref, raster_ref64, seed):
     sc, cam, ps = small_scene(seed)
