@@ -56,16 +56,24 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
+#ifndef MB_GATHER_AHEAD
+#define MB_GATHER_AHEAD 1
+#endif
+constexpr int kPre = MB_GATHER_AHEAD;       // batches of records in flight ahead of the one being blended
+constexpr int kRecSlots = kPre + 1, kIdSlots = kPre + 2;
+
 template <int kWarps>
 struct StageSmem {
     static constexpr int B = kWarps * 32;       // list entries per batch = threads per CTA
-    Record rec[2][B];                           // gathered records, double buffered
-    uint32_t ids[3][B + 4];                     // TMA-staged slices of the id list (16-B aligned source => up to 3 ids of slack)
-    uint64_t bar[3];
+    Record rec[kRecSlots][B];                   // gathered records: the batch being blended + kPre batches in flight
+    uint32_t ids[kIdSlots][B + 4];              // TMA-staged slices of the id list (16-B aligned source => up to 3 ids of slack)
+    uint64_t bar[kIdSlots];
     uint32_t red;                               // per-CTA scratch (max last contributor)
 };
 
 // Streams a tile's id list through shared memory: sequence step i handles batch i (forward) or nb-1-i (backward).
+// Pipeline: the id slice of batch i + kPre + 1 is requested from the TMA engine and the records of batch i + kPre are
+// gathered (three 128-bit cp.async per thread, L2 hits) while batch i is blended.
 template <int kWarps>
 struct ListStager {
     static constexpr int B = kWarps * 32;
@@ -82,18 +90,18 @@ struct ListStager {
         const int b = batch_of(i), cnt = min(B, len - b * B);
         const uint32_t start = first + (uint32_t)(b * B), o = start & 3u;
         const uint32_t bytes = ((o + (uint32_t)cnt) * 4u + 15u) & ~15u;
-        const int slot = i % 3;
+        const int slot = i % kIdSlots;
         mbar_expect_tx(&sm.bar[slot], bytes);
         bulk_g2s(&sm.ids[slot][0], list + (start - o), bytes, &sm.bar[slot]);
     }
     __device__ __forceinline__ void gather(int i) {      // all threads; one commit group per call
         const int b = batch_of(i), cnt = min(B, len - b * B);
         const uint32_t o = (first + (uint32_t)(b * B)) & 3u;
-        const int slot = i % 3;
-        mbar_wait(&sm.bar[slot], (uint32_t)((i / 3) & 1));
+        const int slot = i % kIdSlots;
+        mbar_wait(&sm.bar[slot], (uint32_t)((i / kIdSlots) & 1));
         if ((int)threadIdx.x < cnt) {
             const char *src = reinterpret_cast<const char *>(rec + sm.ids[slot][o + threadIdx.x]);
-            char *dst = reinterpret_cast<char *>(&sm.rec[i & 1][threadIdx.x]);
+            char *dst = reinterpret_cast<char *>(&sm.rec[i % kRecSlots][threadIdx.x]);
             cp_async16(dst, src);
             cp_async16(dst + 16, src + 16);
             cp_async16(dst + 32, src + 32);
@@ -102,37 +110,43 @@ struct ListStager {
     }
     __device__ __forceinline__ void prologue() {
         if (threadIdx.x == 0) {
-            mbar_init(&sm.bar[0], 1);
-            mbar_init(&sm.bar[1], 1);
-            mbar_init(&sm.bar[2], 1);
+#pragma unroll
+            for (int k = 0; k < kIdSlots; ++k) mbar_init(&sm.bar[k], 1);
             mbar_fence_init();
             sm.red = 0;
         }
         __syncthreads();
-        if (nb > 0) {
-            if (threadIdx.x == 0) {
-                issue_ids(0);
-                if (nb > 1) issue_ids(1);
-            }
-            gather(0);
+        if (threadIdx.x == 0)
+            for (int k = 0; k <= kPre && k < nb; ++k) issue_ids(k);
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            if (k < nb) gather(k);
+            else cp_async_commit();
         }
     }
     // top of sequence step i: keep the pipeline full, then make batch i visible to every thread
     __device__ __forceinline__ void advance(int i) {
-        if (threadIdx.x == 0 && i + 2 < nb) issue_ids(i + 2);
-        if (i + 1 < nb) gather(i + 1);
+        if (threadIdx.x == 0 && i + kPre + 1 < nb) issue_ids(i + kPre + 1);
+        if (i + kPre < nb) gather(i + kPre);
         else cp_async_commit();
-        cp_async_wait<1>();
+        cp_async_wait<kPre>();
         __syncthreads();
     }
     // leaving after step i with copies possibly in flight: nothing may land in shared memory after the CTA is gone
     __device__ __forceinline__ void drain(int i) {
         cp_async_wait<0>();
-        if (threadIdx.x == 0 && i + 2 < nb) mbar_wait(&sm.bar[(i + 2) % 3], (uint32_t)(((i + 2) / 3) & 1));
+        if (threadIdx.x == 0)
+            for (int k = i + kPre + 1; k < nb && k <= i + kPre + 1; ++k) mbar_wait(&sm.bar[k % kIdSlots], (uint32_t)((k / kIdSlots) & 1));
     }
     __device__ __forceinline__ int count(int i) const { return min(B, len - batch_of(i) * B); }
-    __device__ __forceinline__ const float4 *records(int i) const { return reinterpret_cast<const float4 *>(&sm.rec[i & 1][0]); }
+    __device__ __forceinline__ const float4 *records(int i) const { return reinterpret_cast<const float4 *>(&sm.rec[i % kRecSlots][0]); }
+    __device__ __forceinline__ const uint32_t *ids(int i) const { return &sm.ids[i % kIdSlots][(first + (uint32_t)(batch_of(i) * B)) & 3u]; }
 };
+
+#ifndef MB_FWD_GROUP
+#define MB_FWD_GROUP 4
+#endif
+constexpr int kGroup = MB_FWD_GROUP;   // survivors evaluated together in the forward (independent alpha evaluations)
 
 // pixel of a thread: the work item covers 8/kWarps... see kernel comments; vw = virtual warp index inside the 16x16 tile
 __device__ __forceinline__ void pixel_of_thread(int tile, int gx, int vw, int lane, int &px, int &py) {
@@ -187,14 +201,14 @@ __global__ void __launch_bounds__(kWarps * 32, 24 / kWarps) blend_forward_kernel
             }
             unsigned m = __ballot_sync(0xffffffffu, hit);
             while (m) {
-                // up to 4 survivors per step: everything that does not depend on the running transmittance (record
+                // up to kGroup survivors per step: everything that does not depend on the running transmittance (record
                 // fetch, power, exponential, alpha) is evaluated for all four first (independent instruction streams),
                 // then the four are applied in list order
-                float alpha[4], cr[4], cg[4], cb[4];
-                uint32_t pos1[4];
-                bool valid[4];
+                float alpha[kGroup], cr[kGroup], cg[kGroup], cb[kGroup];
+                uint32_t pos1[kGroup];
+                bool valid[kGroup];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < kGroup; ++q) {
                     const bool has = m != 0;
                     const int j = j0 + (has ? __ffs(m) - 1 : 0);
                     m &= m - 1;
@@ -208,7 +222,7 @@ __global__ void __launch_bounds__(kWarps * 32, 24 / kWarps) blend_forward_kernel
                     pos1[q] = base + (uint32_t)j + 1u;
                 }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < kGroup; ++q) {
                     const bool ok = valid[q] && !done;
                     const float test_T = T * (1.0f - alpha[q]);
                     const bool stop = ok && test_T < kTMin;
@@ -254,6 +268,14 @@ __global__ void __launch_bounds__(kWarps * 32, 24 / kWarps) blend_forward_kernel
     MB_TRACE_END(0, sm.red);
 }
 
+// 1 / x by the special-function unit (MUFU.RCP, <= 1 ulp) instead of the IEEE division sequence: used for 1 / (1 - alpha) in
+// the backward, where upstream itself reconstructs T by repeated division and the result feeds sums of thousands of terms
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // lane -> which of the 9 reduced values it owns after the reduce-scatter (or -1)
 __device__ __forceinline__ int reduce_slot(int lane) {
     const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
@@ -293,12 +315,15 @@ __device__ __forceinline__ float reduce_scatter9(const float (&v)[9], int lane) 
     return d;
 }
 
+#ifndef MB_BWD_WARPS_PER_SM
+#define MB_BWD_WARPS_PER_SM 32
+#endif
 // One work item = one segment [seg*kSeg, min((seg+1)*kSeg, maxlast)) of one (half / quarter) tile's list, walked back to
 // front.  A pixel whose last contributor lies beyond the segment starts from the forward's checkpoint in front of the far
 // end: T = transmittance there, accumulated "colour behind" = (C_final - C_front) / T; a pixel whose last contributor is
 // inside (or in front of) the segment starts from (T_final, 0) exactly like the unsegmented recurrence.
 template <int kWarps>
-__global__ void __launch_bounds__(kWarps * 32, 16 / kWarps) blend_backward_kernel(
+__global__ void __launch_bounds__(kWarps * 32, MB_BWD_WARPS_PER_SM / kWarps) blend_backward_kernel(
     const Record *__restrict__ recs, const uint32_t *__restrict__ list, const uint2 *__restrict__ ranges,
     const uint2 *__restrict__ items, const uint32_t *__restrict__ n_items, const uint32_t *__restrict__ tile_maxlast, int W, int H,
     int gx, const float *__restrict__ bg, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
@@ -360,7 +385,7 @@ __global__ void __launch_bounds__(kWarps * 32, 16 / kWarps) blend_backward_kerne
         const int cnt = st.count(i);
         const float4 *r = st.records(i);
         const int b = st.batch_of(i);
-        const uint32_t *ids = &sm.ids[i % 3][(st.first + (uint32_t)(b * st.B)) & 3u];
+        const uint32_t *ids = st.ids(i);
         int jend = cnt;   // entries at or behind the warp's deepest last contributor cannot matter
         if (b * st.B + cnt > wlast) jend = wlast - b * st.B;
         for (int j0 = ((jend - 1) >> 5) << 5; j0 >= 0; j0 -= 32) {
@@ -384,32 +409,33 @@ __global__ void __launch_bounds__(kWarps * 32, 16 / kWarps) blend_backward_kerne
                 const float G = expf(power);
                 const float alpha = fminf(kAlphaMax, rb.y * G);
                 const bool active = cand && (alpha >= kAlphaMin);
-                if (!__any_sync(0xffffffffu, active)) continue;
-                float v[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (active) {
-                    const float rinv = 1.0f / (1.0f - alpha);
-                    T = T * rinv;
-                    const float dch = alpha * T;
-                    a0 = last_alpha * lc0 + (1.f - last_alpha) * a0;
-                    a1 = last_alpha * lc1 + (1.f - last_alpha) * a1;
-                    a2 = last_alpha * lc2 + (1.f - last_alpha) * a2;
-                    lc0 = rb.z; lc1 = rb.w; lc2 = rc.x;
-                    float dL_dalpha = (lc0 - a0) * dp0 + (lc1 - a1) * dp1 + (lc2 - a2) * dp2;
-                    v[6] = dch * dp0; v[7] = dch * dp1; v[8] = dch * dp2;
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha += (-T_final * rinv) * bg_dot;
-                    const float dL_dG = rb.y * dL_dalpha;   // the 0.99 clamp is not masked (upstream behaviour)
-                    const float gdx = G * dx, gdy = G * dy;
-                    const float dG_ddelx = -gdx * ra.z - gdy * ra.w;
-                    const float dG_ddely = -gdy * rb.x - gdx * ra.w;
-                    v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                    v[1] = dL_dG * dG_ddely * ddely_dy;
-                    v[2] = -0.5f * gdx * dx * dL_dG;
-                    v[3] = -0.5f * gdx * dy * dL_dG;
-                    v[4] = -0.5f * gdy * dy * dL_dG;
-                    v[5] = G * dL_dalpha;
-                }
+                // Branch-free update: a lane for which this Gaussian does not contribute keeps its state (selects) and its
+                // partial gradients vanish because their common factors (alpha * T, dL/dalpha) are zeroed.
+                const float rinv = fast_rcp(1.0f - alpha);
+                const float T_new = T * rinv;
+                const float n0 = last_alpha * lc0 + (1.f - last_alpha) * a0;
+                const float n1 = last_alpha * lc1 + (1.f - last_alpha) * a1;
+                const float n2 = last_alpha * lc2 + (1.f - last_alpha) * a2;
+                const float c0 = rb.z, c1 = rb.w, c2 = rc.x;
+                float dL_dalpha = ((c0 - n0) * dp0 + (c1 - n1) * dp1 + (c2 - n2) * dp2) * T_new + (-T_final * rinv) * bg_dot;
+                dL_dalpha = active ? dL_dalpha : 0.f;
+                const float dch = active ? alpha * T_new : 0.f;
+                T = active ? T_new : T;
+                a0 = active ? n0 : a0; a1 = active ? n1 : a1; a2 = active ? n2 : a2;
+                lc0 = active ? c0 : lc0; lc1 = active ? c1 : lc1; lc2 = active ? c2 : lc2;
+                last_alpha = active ? alpha : last_alpha;
+                const float dL_dG = rb.y * dL_dalpha;   // the 0.99 clamp is not masked (upstream behaviour)
+                const float gdx = G * dx, gdy = G * dy;
+                const float dG_ddelx = -gdx * ra.z - gdy * ra.w;
+                const float dG_ddely = -gdy * rb.x - gdx * ra.w;
+                float v[9];
+                v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                v[1] = dL_dG * dG_ddely * ddely_dy;
+                v[2] = -0.5f * gdx * dx * dL_dG;
+                v[3] = -0.5f * gdx * dy * dL_dG;
+                v[4] = -0.5f * gdy * dy * dL_dG;
+                v[5] = G * dL_dalpha;
+                v[6] = dch * dp0; v[7] = dch * dp1; v[8] = dch * dp2;
                 const float total = reduce_scatter9(v, lane);
                 if (slot >= 0) red_add(acc + (size_t)ids[j] * kAccStride + slot, total);
             }
@@ -653,10 +679,12 @@ extern "C" int mb_raster_forward_render(const mb_raster_inputs *in, void *geom, 
         if (rc) return rc;
         order = im.order_fwd;
     }
+    static int pad = -1;       // experiment switch: dynamic shared memory that only lowers the number of co-resident CTAs
+    if (pad < 0) pad = getenv("MB_FWD_SMEM_PAD") ? atoi(getenv("MB_FWD_SMEM_PAD")) : 0;
     {
         KernelTimer kt("blend_forward", s);
         if (blend_warps() == 4)
-            blend_forward_kernel<4><<<d.tiles * 2, 128, 0, s>>>(g.rec, b.gid_b, im.ranges, order, d.W, d.H, d.gx, in->background,
+            blend_forward_kernel<4><<<d.tiles * 2, 128, pad, s>>>(g.rec, b.gid_b, im.ranges, order, d.W, d.H, d.gx, in->background,
                                                                 out_color, im.final_T, im.n_contrib, im.tile_maxlast, b.ckpt);
         else if (blend_warps() == 2)
             blend_forward_kernel<2><<<d.tiles * 4, 64, 0, s>>>(g.rec, b.gid_b, im.ranges, order, d.W, d.H, d.gx, in->background,

@@ -24,6 +24,9 @@ print({k: round(ms / n * 1e3, 1) for k, (n, ms) in rep.items() if k.startswith("
 for spec in sys.argv[1:] or [""]:
     env = dict(os.environ)
     for kv in filter(None, spec.split(",")):
+        if "=" not in kv:
+            env["MANUS_B200_LIB"] = os.path.abspath(kv)      # a variant library
+            continue
         k, v = kv.split("=", 1)
         env[k] = v
     out = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)
