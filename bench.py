@@ -359,7 +359,6 @@ def main():
             stage_inputs(it)                                    # first step of a run: nothing was prefetched
         cur = torch.cuda.current_stream(dev)
         cur.wait_event(slot["ready"])
-        stage_inputs(it + 1); slots[(it + 1) % 2]["staged"] = it + 1
         if graphed is not None:
             graphed.set_inputs(slot["cam"], slot["bones"], slot["g"])
             loss = graphed.replay()
@@ -370,6 +369,8 @@ def main():
         if world > 1:
             dist.all_reduce(r.flat.grad)
         slot["free"].record(cur)
+        # the next step's host->device copies are enqueued (copy stream) while this step runs
+        stage_inputs(it + 1); slots[(it + 1) % 2]["staged"] = it + 1
         return float(loss.detach())                             # device -> host read of the step's result
 
     def timed(fn, steps, sampler=None):
