@@ -189,7 +189,13 @@ class SceneRenderer:
                       tanfov_dev=cam_dev[37:39] if device_intrinsics else None)
         bone_tf = None
         if self.n_hand > 0:
-            bone_tf = torch.cat([torch.bmm(bones_dev.view(-1, 4, 4), self.rest_inv), self._eye], dim=0)   # = bone_transforms(...)
+            # = bone_transforms(posed, rest, append_identity=True), written into a persistent [B+1,4,4] buffer whose last
+            # row stays the identity "background" bone (one small batched product per frame, no concatenation)
+            nb = self.rest_inv.shape[0]
+            if getattr(self, "_bone_tf", None) is None:
+                self._bone_tf = torch.eye(4, dtype=torch.float32, device=self.device).repeat(nb + 1, 1, 1)
+            torch.bmm(bones_dev.view(-1, 4, 4), self.rest_inv, out=self._bone_tf[:nb])
+            bone_tf = self._bone_tf
         return render_fused(self.flat.leaves(), self.skin, bone_tf, dcam, self.bg, self.sh_degree, self.flat.isotropic,
                             self.n_hand, grad_sink=sink)
 

@@ -228,12 +228,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.state = st
         ctx.shapes = (means3D.shape, means2D.shape, opacities.shape)
         ctx.mark_non_differentiable(radii)
+        ctx.set_materialize_grads(False)      # no zero tensor for the (integer) radii output on every backward
         return color, radii
 
     @staticmethod
     def backward(ctx, grad_out_color, _grad_radii):
         st = ctx.state
-        if st is None:
+        if st is None or grad_out_color is None:
             return (None,) * 9
         if st.host_count is not None:
             st.resolve()

@@ -34,15 +34,32 @@ def calculate_colors_from_sh(posed_means, cano_features, cano_means, camera, sh_
     raise NotImplementedError("use render_fused / pose_gaussians (the fused path never materialises tf)")
 
 
+_ZEROS = {}
+
+
+def _screenspace_leaf(posed_means):
+    """A [N,3] zero tensor that receives the screen-space gradient, without a fill kernel per frame: the rasterizer never
+    reads means2D, so a cached zero buffer is re-used and only a fresh autograd leaf is made on top of it."""
+    key = (posed_means.device, tuple(posed_means.shape), posed_means.dtype)
+    z = _ZEROS.get(key)
+    if z is None:
+        _ZEROS.clear()
+        z = _ZEROS[key] = torch.zeros_like(posed_means, requires_grad=False)
+    return z.detach().requires_grad_(True)
+
+
 def render_gaussians(posed_means, posed_cov, cano_means, cano_features, cano_opacity, camera, bg_color, colors_precomp=None,
-                     sh_degree=3, tf=None, device=torch.device("cuda")):
+                     sh_degree=3, tf=None, device=torch.device("cuda"), _cached_screenspace=False):
     """gaussian_utils.py:349-428.  ``colors_precomp`` must be given (MANUS computes it with calculate_colors_from_sh
     before the call, :401-404; in this package colours come out of ``pose_gaussians``)."""
-    screenspace_points = torch.zeros_like(posed_means, dtype=posed_means.dtype, requires_grad=True, device=device) + 0
-    try:
-        screenspace_points.retain_grad()
-    except Exception:
-        pass
+    if _cached_screenspace:
+        screenspace_points = _screenspace_leaf(posed_means)          # a leaf: .grad is populated without retain_grad()
+    else:
+        screenspace_points = torch.zeros_like(posed_means, dtype=posed_means.dtype, requires_grad=True, device=device) + 0
+        try:
+            screenspace_points.retain_grad()
+        except Exception:
+            pass
     if colors_precomp is None:
         raise ValueError("render_gaussians: pass colors_precomp (from manus_b200.pose_gaussians)")
     rasterizer = GaussianRasterizer(raster_settings=_settings(camera, bg_color, sh_degree, device))
@@ -61,6 +78,6 @@ def render_fused(params, skin_wts, bone_tf, camera, bg_color, sh_degree=3, isotr
     posed_xyz, posed_cov, colors, opacity = pose_gaussians(xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, bone_tf,
                                                           campos, sh_degree, isotropic, num_skinned, grad_sink)
     out = render_gaussians(posed_xyz, posed_cov, xyz, None, opacity, camera, bg_color, colors_precomp=colors,
-                           sh_degree=sh_degree, device=device)
+                           sh_degree=sh_degree, device=device, _cached_screenspace=True)
     out.update(posed_xyz=posed_xyz, posed_cov=posed_cov, colors=colors, cano_opacity=opacity)
     return out
