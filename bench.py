@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--scene", default="composite", choices=["composite", "hand", "object"],
                     help="composite = BASELINE configs[3] (headline); hand = configs[2]; object = configs[1] (use --gaussians 100000 --width 800 --height 800)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--plain-allreduce", action="store_true",
+                    help="N > 1: all-reduce the whole flat gradient buffer instead of the compact exchange (rank-one SH gradients)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python each step instead of replaying the captured CUDA graph")
     return ap.parse_args()
 
@@ -259,7 +261,7 @@ def workload_config(args, world):
             "hand": "articulated hand {n} Gaussians (all skinned by 20+1 bones)", "object": "static object {n} Gaussians (no skinning)"}[args.scene]
     return {"workload": kind.format(n=args.gaussians) + ", " +
                         f"{args.views} shipped views/poses at {args.width}x{args.height}, SH degree 3, white background",
-            "global_views_per_step": world, "parallelism": f"view-sharded dp{world}, one all-reduce of the flat gradient buffer",
+            "global_views_per_step": world, "parallelism": f"view-sharded dp{world}, one exchange of per-Gaussian gradients per step",
             "l2": "working set per step (parameters 118 MB + gradients 118 MB + instance records) exceeds the 126 MB L2 and the view "
                   "changes every step; no explicit flush",
             "loss": "sum(image * G), G ~ U[0,1] fixed (seed 7)"}
@@ -318,7 +320,18 @@ def main():
     _rz.reserve_capacity(dev.index, scene.n, H, W, max(D_all.values()))
 
     loss_fn = lambda image, target: (image * target).sum()
-    graphed = None if args.no_graph else GraphedStep(r, loss_fn, G_dev, view=views[0])
+    # N > 1: the backward skips the f_rest gradient and the ranks exchange the rank-one SH gradient factors instead of
+    # all-reducing all 59 floats per Gaussian (manus_b200.dist.CompactGradExchange)
+    compact = world > 1 and not args.plain_allreduce
+    from manus_b200.dist import CompactGradExchange
+    exchange = CompactGradExchange(r) if compact else None
+    graphed = None if args.no_graph else GraphedStep(r, loss_fn, G_dev, view=views[0], compact_sh=compact)
+
+    def reduce_gradients():
+        if exchange is not None:
+            exchange()
+        elif world > 1:
+            dist.all_reduce(r.flat.grad)
 
     def step_resident(it, eager=False):
         v = my_view(it)
@@ -328,11 +341,10 @@ def main():
             graphed.set_inputs(staged[v][0], staged[v][1], None)
             loss = graphed.replay()
         else:
-            out = r.render(v, sink=r.flat.grads, cam_dev=staged[v][0], bones_dev=staged[v][1])
+            out = r.render(v, sink=r.flat.grads, cam_dev=staged[v][0], bones_dev=staged[v][1], compact_sh=compact)
             loss = loss_fn(out["render"], G_dev)
             loss.backward()
-        if world > 1:
-            dist.all_reduce(r.flat.grad)
+        reduce_gradients()
         return loss
 
     # End-to-end step: the step's inputs (packed camera 39 floats, posed bones 320 floats, target image H*W*3 floats) come
@@ -363,11 +375,10 @@ def main():
             graphed.set_inputs(slot["cam"], slot["bones"], slot["g"])
             loss = graphed.replay()
         else:
-            out = r.render(my_view(it), sink=r.flat.grads, cam_dev=slot["cam"], bones_dev=slot["bones"])
+            out = r.render(my_view(it), sink=r.flat.grads, cam_dev=slot["cam"], bones_dev=slot["bones"], compact_sh=compact)
             loss = loss_fn(out["render"], slot["g"])
             loss.backward()
-        if world > 1:
-            dist.all_reduce(r.flat.grad)
+        reduce_gradients()
         slot["free"].record(cur)
         # the next step's host->device copies are enqueued (copy stream) while this step runs
         stage_inputs(it + 1); slots[(it + 1) % 2]["staged"] = it + 1
@@ -410,7 +421,7 @@ def main():
     # the same end-to-end step with the reference's training loss 0.8 L1 + 0.2 (1 - SSIM) (fused kernel, manus_b200.losses)
     from manus_b200.losses import photometric_loss
     photo_fn = lambda image, target: photometric_loss(image, target, 0.8, 0.2)
-    graphed_photo = None if args.no_graph else GraphedStep(r, photo_fn, G_dev, view=views[0])
+    graphed_photo = None if args.no_graph else GraphedStep(r, photo_fn, G_dev, view=views[0], compact_sh=compact)
     ms_e2e_photo = timed(lambda it: step_e2e(it, graphed_photo, photo_fn), K)
     if graphed_photo is not None:
         graphed_photo.check()
@@ -460,7 +471,10 @@ def main():
             "roofline": roofline,
             "frame": {"num_rendered_mean": D_mean, "visible_mean": V_mean, "algorithmic_bytes": fbytes,
                       "achieved_gbps": fbytes * (1e3 / ms_step) / 1e9, "frac_of_hbm_peak": fbytes * (1e3 / ms_step) / 1e9 / peak,
-                      "allreduce_bytes": r.flat.allreduce_bytes() if world > 1 else 0}}
+                      "allreduce_bytes": r.flat.allreduce_bytes() if world > 1 else 0,
+                      "exchange": ("none" if world == 1 else "compact: all-gather of the DC gradients (12 B per Gaussian and rank) + all-reduce of "
+                                   "the 11 non-SH floats + local rebuild of the SH gradients" if compact else "all-reduce of the flat gradient buffer"),
+                      "exchange_bytes_per_rank": (0 if world == 1 else (scene.n * (12 * world + 44)) if compact else r.flat.allreduce_bytes())}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         cb = cpu_baseline_frame(scene, W, H, 0, threads)

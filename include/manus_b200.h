@@ -153,10 +153,22 @@ typedef struct mb_pose_inputs {
 int mb_pose_forward(const mb_pose_inputs *in, float *posed_xyz /*[N,3]*/, float *posed_cov6 /*[N,6]*/,
                     float *colors /*[N,3]*/, float *opacity /*[N]*/, float *tf_out, mb_stream_t stream);
 
-/* g_skin_wts: optional [num_skinned,B].  All other outputs are required and fully written. */
+/* g_skin_wts: optional [num_skinned,B].  g_f_rest: optional (see mb_sh_grad_from_views).  All other outputs are required and
+ * fully written. */
 int mb_pose_backward(const mb_pose_inputs *in, const float *g_posed_xyz, const float *g_posed_cov6, const float *g_colors,
                      const float *g_opacity, float *g_xyz, float *g_log_scale, float *g_quat, float *g_opacity_logit,
                      float *g_f_dc, float *g_f_rest, float *g_skin_wts, mb_stream_t stream);
+
+/* SH-coefficient gradients of a SUM over num_views views from the views' DC gradients (data-parallel step, SURVEY.md
+ * section 8e): for one view g_f_rest[k][c] = basis_k(dir) * g_f_dc[c] / basis_0, with dir the canonical-space view direction
+ * that mb_pose_forward uses (src/utils/gaussian_utils.py:431-449).  Ranks therefore all-gather g_f_dc (3 floats per Gaussian
+ * and view) and the per-view (bone_tf, campos) instead of all-reducing the 48 SH floats, and call this on the gathered data.
+ * bone_tf_all [num_views,B,4,4], campos_all [num_views,3], g_f_dc_all [num_views,N,3]; writes g_f_dc [N,3], g_f_rest [N,K-1,3].
+ * view_stride = 0: the three per-view arrays are dense; otherwise view r of each starts view_stride floats after view r-1 (the
+ * three pointers then address one gathered record per rank: DC gradients | bone transforms | camera centre). */
+int mb_sh_grad_from_views(const float *xyz, int32_t num_points, const float *skin_wts, int32_t num_skinned, int32_t num_bones,
+                          int32_t sh_degree, int32_t sh_coeffs, int32_t num_views, const float *bone_tf_all, const float *campos_all,
+                          const float *g_f_dc_all, int64_t view_stride, float *g_f_dc, float *g_f_rest, mb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Per-frame skin-weight lookup: skin_wts[i,:] = normalise(trilinear(grid_weights, xyz[i])).

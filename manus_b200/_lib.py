@@ -69,6 +69,8 @@ SIGNATURES = {
     "mb_photometric_loss_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "mb_photometric_loss": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mb_sh_grad_from_views": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mb_knn_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "mb_dist2_knn3": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mb_nearest_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),

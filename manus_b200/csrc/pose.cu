@@ -8,9 +8,10 @@
 //
 // Persistent CTAs walk tiles of 128 Gaussians (one thread per Gaussian).  Every per-Gaussian array of a tile is one
 // dense run in HBM (f_rest 23 KB, skin weights 10.5 KB, xyz / scales / quaternions / ... 0.5-2 KB), so a tile is fetched by
-// a handful of 1-D bulk TMA copies (cp.async.bulk + mbarrier) into the shared-memory stage that is not being computed
-// on, results are written over the thread's own input rows and leave the same way (cp.async.bulk shared -> global).
-// Two stages per CTA and two CTAs per SM keep ~80 KB of loads in flight per SM while the ALUs work on the other stage.
+// a handful of 1-D bulk TMA copies (cp.async.bulk + mbarrier) into the CTA's shared-memory stage, results are written over
+// the thread's own input rows and leave the same way (cp.async.bulk shared -> global).
+// One stage per CTA and four CTAs per SM: the loads of one CTA overlap the arithmetic of the others (a double-buffered
+// stage per CTA with half as many CTAs was measured slower).
 //
 // HBM bytes per Gaussian (fp32, K=16, B bones): forward 236 + 4B read, 52 written; backward re-reads the parameters
 // and the 52 B of upstream gradients and writes 236 B of parameter gradients.
@@ -28,7 +29,7 @@ constexpr int kMaxBones = 64;
 constexpr int kMaxArrays = 12;
 
 struct PoseArgs {
-    int N, n_skinned, B, deg, K, iso, stages;
+    int N, n_skinned, B, deg, K, iso;
     const float *xyz, *log_scale, *quat, *opacity_logit, *f_dc, *f_rest, *skin, *bone_tf, *campos;
     // forward outputs
     float *posed_xyz, *cov6, *colors, *opacity, *tf_out;
@@ -64,19 +65,9 @@ __host__ __device__ inline TileLayout tile_layout(int K, int B, int iso, bool ba
     return L;
 }
 
-inline size_t pose_smem_bytes(int B, int K, int iso, bool backward, int stages) {
-    // bones (13 floats each) + camera + 2 mbarriers, then the tile stage(s)
-    return sizeof(float) * ((size_t)kMaxBones * 13 + 8) + stages * sizeof(float) * (size_t)tile_layout(K, B, iso, backward).floats;
-}
-
-// 1 = one stage per CTA and twice the CTAs per SM (default), 2 = double-buffered stages inside a CTA
-static int pose_stages() {
-    static int cached = 0;
-    if (!cached) {
-        const char *e = getenv("MB_POSE_STAGES");
-        cached = (e && atoi(e) == 2) ? 2 : 1;
-    }
-    return cached;
+inline size_t pose_smem_bytes(int B, int K, int iso, bool backward) {
+    // bones (13 floats each) + camera + 2 mbarriers, then the tile stage
+    return sizeof(float) * ((size_t)kMaxBones * 13 + 8) + sizeof(float) * (size_t)tile_layout(K, B, iso, backward).floats;
 }
 
 struct Transfer {   // one dense array of a tile: global <-> shared
@@ -224,7 +215,7 @@ struct TilePipe {
             t[n++] = {a.colors + (size_t)base * 3, L.fdc, (uint32_t)(cnt * 12)};
             t[n++] = {a.opacity + base, L.opac, (uint32_t)(cnt * 4)};
         } else {
-            t[n++] = {a.g_f_rest ? a.g_f_rest + (size_t)base * rs : nullptr, L.fr, (uint32_t)(rs > 0 ? cnt * rs * 4 : 0)};
+            t[n++] = {a.g_f_rest ? a.g_f_rest + (size_t)base * rs : nullptr, L.fr, (uint32_t)(a.g_f_rest && rs > 0 ? cnt * rs * 4 : 0)};
             t[n++] = {a.g_skin ? a.g_skin + (size_t)base * a.B : nullptr, L.sk, (uint32_t)(a.g_skin ? nsk * a.B * 4 : 0)};
             t[n++] = {a.g_xyz + (size_t)base * 3, L.gpx, (uint32_t)(cnt * 12)};
             t[n++] = {a.g_log_scale + (size_t)base * lsw, L.ls, (uint32_t)(cnt * lsw * 4)};
@@ -309,37 +300,20 @@ __device__ __forceinline__ void run_tiles(const PoseArgs &a, float *smem, Body b
     __syncthreads();
     const int ntiles = (a.N + kPoseThreads - 1) / kPoseThreads;
     uint32_t phase = 0;
-    if (a.stages == 1) {
-        // one stage per CTA, more CTAs per SM: the loads of one CTA overlap the arithmetic of the others
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            __syncthreads();            // plain-path stores of the previous tile have read the stage
-            if (threadIdx.x == 0) {
-                bulk_wait_read_all();   // the bulk stores of the previous tile have finished reading the stage
-                pipe.prefetch(tile, 0);
-            }
-            __syncthreads();
-            pipe.acquire(tile, 0, phase);
-            const int row = threadIdx.x, i = tile * kPoseThreads + row;
+    // one stage per CTA, four CTAs per SM: the loads of one CTA overlap the arithmetic of the others
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();            // plain-path stores of the previous tile have read the stage
+        if (threadIdx.x == 0) {
+            bulk_wait_read_all();   // the bulk stores of the previous tile have finished reading the stage
+            pipe.prefetch(tile, 0);
+        }
+        __syncthreads();
+        pipe.acquire(tile, 0, phase);
+        const int row = threadIdx.x, i = tile * kPoseThreads + row;
 #ifndef MB_POSE_NOCOMPUTE   // experiment switch (tools/pose_bench.py): data movement only
-            if (i < a.N) body(pipe.L, pipe.stage(0), i, row, bones_s, cam_s);
+        if (i < a.N) body(pipe.L, pipe.stage(0), i, row, bones_s, cam_s);
 #endif
-            pipe.release(tile, 0);
-        }
-    } else {
-        if (threadIdx.x == 0 && (int)blockIdx.x < ntiles) pipe.prefetch(blockIdx.x, 0);
-        int k = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
-            const int next = tile + gridDim.x;
-            if (threadIdx.x == 0 && next < ntiles) {
-                bulk_wait_read_all();   // the stores of two tiles ago have finished reading the stage that is refilled now
-                pipe.prefetch(next, k + 1);
-            }
-            pipe.acquire(tile, k, phase);
-            const int row = threadIdx.x, i = tile * kPoseThreads + row;
-            if (i < a.N) body(pipe.L, pipe.stage(k), i, row, bones_s, cam_s);
-            pipe.release(tile, k);
-            __syncthreads();   // plain-path stores have read the stage before it is refilled
-        }
+        pipe.release(tile, 0);
     }
     if (threadIdx.x == 0) bulk_wait_all();
 }
@@ -494,11 +468,12 @@ __global__ void __launch_bounds__(kPoseThreads) pose_backward_kernel(PoseArgs a)
             for (int c = 0; c < 3; ++c) {
                 const float sv = fr[3 * (k - 1) + c] * go[c];
                 gd[0] += bxg[k] * sv; gd[1] += byg[k] * sv; gd[2] += bzg[k] * sv;
-                fr[3 * (k - 1) + c] = basis[k] * go[c];
+                if (a.g_f_rest) fr[3 * (k - 1) + c] = basis[k] * go[c];
             }
-        for (int k = nb; k < a.K; ++k)   // coefficients above the active degree get no gradient
+        if (a.g_f_rest)
+            for (int k = nb; k < a.K; ++k)   // coefficients above the active degree get no gradient
 #pragma unroll
-            for (int c = 0; c < 3; ++c) fr[3 * (k - 1) + c] = 0.f;
+                for (int c = 0; c < 3; ++c) fr[3 * (k - 1) + c] = 0.f;
         const float dot = dir[0] * gd[0] + dir[1] * gd[1] + dir[2] * gd[2];
         const float gdd[3] = {(gd[0] - dir[0] * dot) / dn, (gd[1] - dir[1] * dot) / dn, (gd[2] - dir[2] * dot) / dn};
 #pragma unroll
@@ -533,6 +508,98 @@ __global__ void __launch_bounds__(kPoseThreads) pose_backward_kernel(PoseArgs a)
     });
 }
 
+// Rebuilds the SH-coefficient gradients of a sum over R views from what every view contributes through its DC term.
+// For one view, g_f_dc[c] = basis_0 * go[c] and g_f_rest[k][c] = basis_k(dir) * go[c], where go is the colour gradient after
+// the clamp mask and dir the view direction in canonical space (function of the view's bone transforms and camera centre).
+// So ranks exchange g_f_dc (3 floats per Gaussian and view, all-gather) plus the tiny per-view (bone_tf, campos) and every
+// rank recomputes dir per view: 12 R bytes per Gaussian on the wire instead of an all-reduce of 192.
+struct ShViewsArgs {
+    int N, n_skinned, B, K, R;
+    int64_t s_bone, s_cam, s_g;     // floats between consecutive views in bone_tf_all / campos_all / g_fdc_all
+    const float *xyz, *skin, *bone_tf_all, *campos_all, *g_fdc_all;
+    float *g_f_dc, *g_f_rest;
+};
+
+constexpr int kShvTile = 128;   // Gaussians per CTA
+
+// shared memory (floats): bones [R][B][13] | cameras [R][3] | skin tile [128][B] | output tile [128][3 (K-1)] (+1 pad per row)
+template <int DEG>
+__global__ void __launch_bounds__(kShvTile) sh_grad_from_views_kernel(ShViewsArgs a) {
+    constexpr int nb = (DEG + 1) * (DEG + 1);
+    extern __shared__ float sh_smem[];
+    float *bones_s = sh_smem, *cam_s = bones_s + (size_t)a.R * a.B * 13;
+    float *skin_s = cam_s + 3 * a.R + ((3 * a.R) & 1);
+    const int rs = (a.K - 1) * 3, rs_pad = rs | 1;            // odd row stride: conflict-free row-wise access
+    float *out_s = skin_s + (size_t)kShvTile * a.B;
+    const int tid = threadIdx.x, base = blockIdx.x * kShvTile, cnt = min(kShvTile, a.N - base);
+    for (int j = tid; j < a.R * a.B * 13; j += kShvTile) {
+        const int rb = j / 13, e = j - 13 * rb;
+        const int r = rb / a.B, b = rb - r * a.B;
+        bones_s[j] = a.bone_tf_all[(size_t)r * a.s_bone + 16 * b + (e < 12 ? e : 15)];
+    }
+    for (int j = tid; j < a.R * 3; j += kShvTile) cam_s[j] = a.campos_all[(size_t)(j / 3) * a.s_cam + j % 3];
+    // the tile's skin weights are one dense run: coalesced load, row-wise use
+    const int nsk = max(0, min(cnt, a.n_skinned - base));
+    for (int j = tid; j < nsk * a.B; j += kShvTile) skin_s[j] = a.skin[(size_t)base * a.B + j];
+    __syncthreads();
+    const int i = base + tid;
+    if (tid < cnt) {
+        const float x[3] = {a.xyz[3 * (size_t)i], a.xyz[3 * (size_t)i + 1], a.xyz[3 * (size_t)i + 2]};
+        const bool skinned = i < a.n_skinned;
+        float acc[nb][3];
+#pragma unroll
+        for (int k = 0; k < nb; ++k) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
+        for (int r = 0; r < a.R; ++r) {
+            PoseLocal p;
+            p.x[0] = x[0]; p.x[1] = x[1]; p.x[2] = x[2];
+            p.skinned = skinned;
+            float Ainv[9], ci[3], dir[3], basis[16];
+            if (skinned) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) p.A[k] = 0.f;
+                p.t[0] = p.t[1] = p.t[2] = 0.f; p.s = 0.f;
+                const float *w_row = skin_s + tid * a.B;
+                const float *bones = bones_s + (size_t)r * a.B * 13;
+                for (int b = 0; b < a.B; ++b) {
+                    const float w = w_row[b];
+                    if (w == 0.f) continue;
+                    const float *T = bones + 13 * b;
+                    p.A[0] += w * T[0]; p.A[1] += w * T[1]; p.A[2] += w * T[2]; p.t[0] += w * T[3];
+                    p.A[3] += w * T[4]; p.A[4] += w * T[5]; p.A[5] += w * T[6]; p.t[1] += w * T[7];
+                    p.A[6] += w * T[8]; p.A[7] += w * T[9]; p.A[8] += w * T[10]; p.t[2] += w * T[11];
+                    p.s += w * T[12];
+                }
+                mat3_inverse(p.A, Ainv);
+            }
+            view_dir(p, cam_s + 3 * r, Ainv, ci, dir);
+            sh_basis(DEG, dir[0], dir[1], dir[2], basis);
+            const float *g = a.g_fdc_all + (size_t)r * a.s_g + (size_t)i * 3;
+            const float go[3] = {g[0] / MB_SH_C0, g[1] / MB_SH_C0, g[2] / MB_SH_C0};
+#pragma unroll
+            for (int k = 0; k < nb; ++k)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[k][c] += basis[k] * go[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a.g_f_dc[3 * (size_t)i + c] = acc[0][c];
+        float *row = out_s + tid * rs_pad;
+#pragma unroll
+        for (int k = 1; k < nb; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) row[3 * (k - 1) + c] = acc[k][c];
+        for (int k = nb; k < a.K; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) row[3 * (k - 1) + c] = 0.f;
+    }
+    __syncthreads();
+    // the tile's f_rest gradients are one dense run in global memory: coalesced store
+    float *out = a.g_f_rest + (size_t)base * rs;
+    for (int j = tid; j < cnt * rs; j += kShvTile) {
+        const int rowi = j / rs, e = j - rowi * rs;
+        out[j] = out_s[rowi * rs_pad + e];
+    }
+}
+
 static int validate_pose(const mb_pose_inputs *in, const char *who) {
     MB_REQUIRE(in != nullptr, "%s: null inputs", who);
     MB_REQUIRE(in->num_points >= 0 && in->num_skinned >= 0 && in->num_skinned <= in->num_points, "%s: bad counts N=%d skinned=%d",
@@ -562,8 +629,7 @@ static PoseArgs pose_args(const mb_pose_inputs *in) {
 
 template <int DEG>
 static int launch_pose(PoseArgs a, bool backward, cudaStream_t s) {
-    a.stages = pose_stages();
-    const size_t smem = pose_smem_bytes(a.B, a.K, a.iso, backward, a.stages);
+    const size_t smem = pose_smem_bytes(a.B, a.K, a.iso, backward);
     const int ntiles = (a.N + kPoseThreads - 1) / kPoseThreads;
     int per_sm = (int)((size_t)(220 * 1024) / smem);
     if (per_sm < 1) {
@@ -624,11 +690,49 @@ extern "C" int mb_pose_backward(const mb_pose_inputs *in, const float *g_posed_x
     if (rc) return rc;
     if (in->num_points == 0) return MB_OK;
     MB_REQUIRE(g_posed_xyz && g_posed_cov6 && g_colors && g_opacity, "mb_pose_backward: null upstream gradient");
-    MB_REQUIRE(g_xyz && g_log_scale && g_quat && g_opacity_logit && g_f_dc && (in->sh_coeffs == 1 || g_f_rest),
-               "mb_pose_backward: null output");
+    // g_f_rest may be NULL: the SH gradient of one view is rank one, g_f_rest[k][c] = basis_k(dir) * g_f_dc[c] / basis_0, and
+    // can be rebuilt from g_f_dc by mb_sh_grad_from_views (what the data-parallel step exchanges instead of 45 floats)
+    MB_REQUIRE(g_xyz && g_log_scale && g_quat && g_opacity_logit && g_f_dc, "mb_pose_backward: null output");
     PoseArgs a = pose_args(in);
     a.g_posed_xyz = g_posed_xyz; a.g_cov6 = g_posed_cov6; a.g_colors = g_colors; a.g_opacity = g_opacity;
     a.g_xyz = g_xyz; a.g_log_scale = g_log_scale; a.g_quat = g_quat; a.g_opacity_logit = g_opacity_logit;
     a.g_f_dc = g_f_dc; a.g_f_rest = g_f_rest; a.g_skin = g_skin_wts;
     return launch_pose_deg(a, true, (cudaStream_t)stream);
+}
+
+
+extern "C" int mb_sh_grad_from_views(const float *xyz, int32_t num_points, const float *skin_wts, int32_t num_skinned, int32_t num_bones,
+                                     int32_t sh_degree, int32_t sh_coeffs, int32_t num_views, const float *bone_tf_all,
+                                     const float *campos_all, const float *g_f_dc_all, int64_t view_stride, float *g_f_dc,
+                                     float *g_f_rest, mb_stream_t stream) {
+    MB_REQUIRE(num_points >= 0 && num_views >= 1 && num_skinned >= 0 && num_skinned <= num_points, "mb_sh_grad_from_views: bad counts");
+    MB_REQUIRE(sh_degree >= 0 && sh_degree <= 3 && sh_coeffs >= (sh_degree + 1) * (sh_degree + 1) && sh_coeffs <= 16,
+               "mb_sh_grad_from_views: bad SH degree / coefficient count");
+    if (num_points == 0) return MB_OK;
+    MB_REQUIRE(xyz && campos_all && g_f_dc_all && g_f_dc && (sh_coeffs == 1 || g_f_rest), "mb_sh_grad_from_views: null pointer");
+    MB_REQUIRE(num_skinned == 0 || (skin_wts && bone_tf_all && num_bones > 0 && num_bones <= kMaxBones), "mb_sh_grad_from_views: skinning inputs missing");
+    const int nbones = num_skinned > 0 ? num_bones : 0;
+    ShViewsArgs a = {num_points, num_skinned, nbones, sh_coeffs, num_views,
+                     view_stride ? view_stride : (int64_t)nbones * 16, view_stride ? view_stride : 3,
+                     view_stride ? view_stride : (int64_t)num_points * 3,
+                     xyz, skin_wts, bone_tf_all, campos_all, g_f_dc_all, g_f_dc, g_f_rest};
+    const size_t smem = sizeof(float) * ((size_t)a.R * a.B * 13 + (size_t)a.R * 3 + 1 + (size_t)kShvTile * a.B +
+                                         (size_t)kShvTile * (((a.K - 1) * 3) | 1));
+    MB_REQUIRE(smem <= 200 * 1024, "mb_sh_grad_from_views: %d views x %d bones do not fit in shared memory", num_views, num_bones);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = (num_points + kShvTile - 1) / kShvTile;
+    KernelTimer kt("sh_grad_from_views", s);
+#define MB_LAUNCH_SHV(D)                                                                                             \
+    do {                                                                                                             \
+        if (smem > 48 * 1024) MB_CUDA(cudaFuncSetAttribute(sh_grad_from_views_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        sh_grad_from_views_kernel<D><<<grid, kShvTile, smem, s>>>(a);                                                    \
+    } while (0)
+    switch (sh_degree) {
+        case 0: MB_LAUNCH_SHV(0); break;
+        case 1: MB_LAUNCH_SHV(1); break;
+        case 2: MB_LAUNCH_SHV(2); break;
+        default: MB_LAUNCH_SHV(3); break;
+    }
+#undef MB_LAUNCH_SHV
+    return check_launch("sh_grad_from_views", false, s);
 }

@@ -679,12 +679,10 @@ extern "C" int mb_raster_forward_render(const mb_raster_inputs *in, void *geom, 
         if (rc) return rc;
         order = im.order_fwd;
     }
-    static int pad = -1;       // experiment switch: dynamic shared memory that only lowers the number of co-resident CTAs
-    if (pad < 0) pad = getenv("MB_FWD_SMEM_PAD") ? atoi(getenv("MB_FWD_SMEM_PAD")) : 0;
     {
         KernelTimer kt("blend_forward", s);
         if (blend_warps() == 4)
-            blend_forward_kernel<4><<<d.tiles * 2, 128, pad, s>>>(g.rec, b.gid_b, im.ranges, order, d.W, d.H, d.gx, in->background,
+            blend_forward_kernel<4><<<d.tiles * 2, 128, 0, s>>>(g.rec, b.gid_b, im.ranges, order, d.W, d.H, d.gx, in->background,
                                                                 out_color, im.final_T, im.n_contrib, im.tile_maxlast, b.ckpt);
         else if (blend_warps() == 2)
             blend_forward_kernel<2><<<d.tiles * 4, 64, 0, s>>>(g.rec, b.gid_b, im.ranges, order, d.W, d.H, d.gx, in->background,

@@ -4,7 +4,7 @@ The reference trains one view per optimizer step on one GPU and emulates larger 
 (``final_loss / accum_iter``, /root/reference/src/modules/hand_dynamic.py:248,259-277).  Here every rank holds the same
 Gaussians, renders its own view forward + backward, and the per-Gaussian parameter gradients -- which are plain sums
 over views -- are combined by ONE all-reduce of a single flat buffer per step (59 floats per Gaussian at SH degree 3:
-xyz 3 | f_dc 3 | f_rest 45 | opacity 1 | scaling 3 | rotation 4, the six Adam param groups of
+xyz 3 | opacity 1 | scaling 3 | rotation 4 | f_dc 3 | f_rest 45, the six Adam param groups of
 src/models/gaussian.py:133-140).  There is no exchange inside a frame.
 
 ``FlatGaussians`` owns the flat parameter / gradient buffers and hands out the six per-parameter views;
@@ -18,7 +18,8 @@ from typing import Callable, Dict, List, Optional, Sequence
 import torch
 import torch.distributed as dist
 
-PARAM_ORDER = ("xyz", "f_dc", "f_rest", "opacity_logit", "log_scale", "quat")
+# segment order of the flat buffers: the 11 non-SH floats first (one contiguous all-reduce range), the SH coefficients last
+PARAM_ORDER = ("xyz", "opacity_logit", "log_scale", "quat", "f_dc", "f_rest")
 
 
 def param_widths(sh_coeffs: int = 16, isotropic: bool = False) -> Dict[str, int]:
@@ -172,11 +173,13 @@ class SceneRenderer:
         return self._cams[view]
 
     def render(self, view: int, sink: Optional[Dict[str, torch.Tensor]] = None, cam_dev=None, bones_dev=None,
-               device_intrinsics: bool = False):
+               device_intrinsics: bool = False, compact_sh: bool = False):
         """Forward of one view through render_fused; returns the result dict (image is out['render'], HWC).
         cam_dev / bones_dev: the packed per-view inputs already on the device (``view_inputs_host`` layout).
         device_intrinsics: read tan(fov/2) from cam_dev[37:39] on the device instead of from the host camera, so that the
-        enqueued frame does not depend on which view ``cam_dev`` holds (CUDA-graph replay)."""
+        enqueued frame does not depend on which view ``cam_dev`` holds (CUDA-graph replay).
+        compact_sh: the backward does not write the f_rest gradient (45 of the 59 floats per Gaussian); it is rebuilt from the
+        f_dc gradients of all ranks' views by ``CompactGradExchange`` (the per-view SH gradient is rank one)."""
         from .cameras import Camera
         from .pose import bone_transforms
         from .render import render_fused
@@ -196,8 +199,67 @@ class SceneRenderer:
                 self._bone_tf = torch.eye(4, dtype=torch.float32, device=self.device).repeat(nb + 1, 1, 1)
             torch.bmm(bones_dev.view(-1, 4, 4), self.rest_inv, out=self._bone_tf[:nb])
             bone_tf = self._bone_tf
+        if compact_sh and sink is not None:
+            sink = dict(sink, f_rest=None)
+        self._last_campos = cam_dev[32:35]
         return render_fused(self.flat.leaves(), self.skin, bone_tf, dcam, self.bg, self.sh_degree, self.flat.isotropic,
                             self.n_hand, grad_sink=sink)
+
+
+class CompactGradExchange:
+    """The one exchange of the data-parallel step with 3.5x fewer bytes on the wire than all-reducing the flat buffer.
+
+    Of the 59 gradient floats per Gaussian, 48 belong to the SH coefficients, and for ONE view they are rank one:
+    g_f_dc[c] = basis_0 * go[c], g_f_rest[k][c] = basis_k(dir) * go[c] (go = colour gradient, dir = canonical-space view
+    direction, a function of the view's bone transforms and camera centre).  So every rank renders with ``compact_sh=True``
+    (its backward skips the 180-byte f_rest gradient), then: ONE all-gather of a per-rank record (g_f_dc, 12 B per Gaussian,
+    plus the view's bone transforms and camera centre); ONE all-reduce of the other 11 floats (the front of the flat
+    buffer); rebuild sum_r basis(dir_r) x go_r locally (``mb_sh_grad_from_views``).  Same result as ``all_reduce(flat.grad)`` up to fp32 summation order.
+    ``rebuild``: the reconstruction function (default: the CUDA kernel; the gloo test injects a CPU restatement)."""
+
+    def __init__(self, renderer: "SceneRenderer", group=None, rebuild=None):
+        self.r, self.group = renderer, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        flat = renderer.flat
+        n, dev = flat.n, flat.grad.device
+        self.nb = 0 if renderer.n_hand == 0 else renderer.rest_inv.shape[0] + 1
+        # one record per rank: DC gradients [N,3] | bone transforms [B,4,4] | camera centre [3] (padded to 4 floats)
+        self.rec = n * 3 + self.nb * 16 + 4
+        self.send = torch.zeros(self.rec, dtype=torch.float32, device=dev)
+        self.recv = torch.zeros(self.world, self.rec, dtype=torch.float32, device=dev)
+        # the non-SH gradients are the front of the flat buffer (PARAM_ORDER): one contiguous all-reduce range
+        w = param_widths(flat.sh_coeffs, flat.isotropic)
+        self.head = flat.grad[: n * (w["xyz"] + w["opacity_logit"] + w["log_scale"] + w["quat"])]
+        self.rebuild = rebuild
+        # a second communicator (own stream) for the all-reduce, so that it runs beside the all-gather and the rebuild
+        self.group2 = dist.new_group() if self.world > 1 and group is None else group
+
+    def __call__(self) -> None:
+        r, flat = self.r, self.r.flat
+        n = flat.n
+        pending = None
+        if self.world > 1:
+            pending = dist.all_reduce(self.head, group=self.group2, async_op=True)     # see below
+        self.send[: n * 3].copy_(flat.grads["f_dc"].reshape(-1))
+        if self.nb:
+            self.send[n * 3: n * 3 + self.nb * 16].copy_(r._bone_tf.reshape(-1))
+        self.send[n * 3 + self.nb * 16: n * 3 + self.nb * 16 + 3].copy_(r._last_campos.reshape(-1)[:3])
+        if self.world > 1:
+            # the all-reduce of the non-SH gradients (started above on its own communicator) runs beside the staging
+            # copies, the all-gather and the rebuild of the SH gradients
+            dist.all_gather_into_tensor(self.recv.view(-1), self.send, group=self.group)
+        else:
+            self.recv[0].copy_(self.send)
+        gfdc_all = self.recv[:, : n * 3].unflatten(1, (n, 3))
+        bone_all = self.recv[:, n * 3: n * 3 + self.nb * 16].unflatten(1, (self.nb, 4, 4)) if self.nb else None
+        campos_all = self.recv[:, n * 3 + self.nb * 16: n * 3 + self.nb * 16 + 3]
+        rebuild = self.rebuild
+        if rebuild is None:
+            from .pose import sh_grad_from_views as rebuild
+        rebuild(flat.params["xyz"], r.skin, r.n_hand, r.sh_degree, flat.sh_coeffs, bone_all, campos_all, gfdc_all,
+                flat.grads["f_dc"], flat.grads["f_rest"])
+        if pending is not None:
+            pending.wait()
 
 
 class GraphedStep:
@@ -211,7 +273,8 @@ class GraphedStep:
     hold the step's results.  ``check()`` (synchronises) raises if a replayed frame overflowed the reserved capacity.
     """
 
-    def __init__(self, renderer: SceneRenderer, loss_fn, target_like: torch.Tensor, view: int = 0, warmup: int = 3):
+    def __init__(self, renderer: SceneRenderer, loss_fn, target_like: torch.Tensor, view: int = 0, warmup: int = 3,
+                 compact_sh: bool = False):
         from . import rasterizer as rz
 
         if rz._Plan.mode != "reserve":
@@ -226,7 +289,8 @@ class GraphedStep:
         self.loss_fn = loss_fn
 
         def frame():
-            out = renderer.render(view, sink=renderer.flat.grads, cam_dev=self.cam, bones_dev=self.bones, device_intrinsics=True)
+            out = renderer.render(view, sink=renderer.flat.grads, cam_dev=self.cam, bones_dev=self.bones, device_intrinsics=True,
+                                  compact_sh=compact_sh)
             loss = loss_fn(out["render"], self.target)
             loss.backward()
             return loss.detach(), out["radii"]

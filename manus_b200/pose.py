@@ -91,9 +91,12 @@ class _PoseGaussians(torch.autograd.Function):
         sink = ctx.grad_sink
         if sink is not None:
             # write straight into caller-owned dense buffers (e.g. the flat all-reduce buffer): no autograd accumulation pass
-            g_xyz, g_ls, g_q, g_ol, g_fdc, g_fr = (sink[k] for k in ("xyz", "log_scale", "quat", "opacity_logit", "f_dc", "f_rest"))
+            # sink["f_rest"] may be None: the per-view SH gradient is rank one and can be rebuilt from g_f_dc (sh_grad_from_views)
+            g_xyz, g_ls, g_q, g_ol, g_fdc, g_fr = (sink.get(k) for k in ("xyz", "log_scale", "quat", "opacity_logit", "f_dc", "f_rest"))
             for g, ref in ((g_xyz, t[0]), (g_ls, t[1]), (g_q, t[2]), (g_ol, t[3]), (g_fdc, t[4]), (g_fr, t[5])):
-                if ref is not None and (g.numel() != ref.numel() or not g.is_contiguous() or g.dtype != torch.float32):
+                if g is None and ref is t[5]:
+                    continue
+                if ref is not None and (g is None or g.numel() != ref.numel() or not g.is_contiguous() or g.dtype != torch.float32):
                     raise RuntimeError("grad_sink tensors must be dense fp32 with the parameter's size")
         else:
             new = lambda ref: torch.empty_like(ref)
@@ -129,3 +132,28 @@ def pose_gaussians(xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts: 
         num_skinned = 0 if skin_wts is None else skin_wts.shape[0]
     return _PoseGaussians.apply(xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, bone_tf, campos, int(sh_degree),
                                 bool(isotropic), int(num_skinned), grad_sink)
+
+
+def sh_grad_from_views(xyz, skin_wts, num_skinned, sh_degree, sh_coeffs, bone_tf_all, campos_all, g_f_dc_all, out_f_dc, out_f_rest):
+    """SH-coefficient gradients of a sum over R views from the views' DC gradients (see mb_sh_grad_from_views):
+    bone_tf_all [R,B,4,4] (or None for static scenes), campos_all [R,3], g_f_dc_all [R,N,3] -> out_f_dc [N,1,3], out_f_rest [N,K-1,3].
+    The three per-view inputs may be views into one [R, stride] buffer (one gathered record per rank)."""
+    L = _lib.lib()
+    dev = xyz.device
+    R = g_f_dc_all.shape[0]
+    x = _f32c(xyz)
+    sk = _f32c(skin_wts) if num_skinned else None
+    B = 0 if sk is None else sk.shape[1]
+    stride = 0
+    if R > 1 and g_f_dc_all.stride(0) != g_f_dc_all[0].numel():
+        stride = g_f_dc_all.stride(0)          # strided record layout: every per-view array must share the stride
+        if campos_all.stride(0) != stride or (num_skinned and bone_tf_all.stride(0) != stride):
+            raise RuntimeError("strided per-view inputs must be views of one [R, stride] buffer")
+        bt, cp, gd = (bone_tf_all if num_skinned else None), campos_all, g_f_dc_all
+    else:
+        bt = _f32c(bone_tf_all) if num_skinned else None
+        cp, gd = _f32c(campos_all), _f32c(g_f_dc_all)
+    with torch.cuda.device(dev):
+        _lib.check(L.mb_sh_grad_from_views(ptr(x), x.shape[0], ptr(sk), int(num_skinned), B, int(sh_degree), int(sh_coeffs), R, ptr(bt),
+                                           ptr(cp), ptr(gd), int(stride), ptr(out_f_dc), ptr(out_f_rest) if out_f_rest is not None and out_f_rest.numel() else None,
+                                           torch.cuda.current_stream(dev).cuda_stream), "mb_sh_grad_from_views")

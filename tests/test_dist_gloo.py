@@ -132,3 +132,83 @@ def test_sharded_optimizer_step_equals_allreduce_then_full_step(tmp_path):
     _StubOpt(flat).step(grad_scale=1.0 / world)
     for r in range(world):
         np.testing.assert_allclose(np.load(tmp_path / f"param_{r}.npy"), flat.data.numpy(), rtol=1e-6, atol=1e-7)
+
+
+# ---- compact gradient exchange (manus_b200.dist.CompactGradExchange): host logic on CPU with a CPU restatement of the rebuild
+C0_SH = 0.28209479177387814
+
+
+def _rebuild_ref(xyz, skin, n_skinned, sh_degree, sh_coeffs, bone_all, campos_all, gfdc_all, out_f_dc, out_f_rest):
+    """sum_r basis(dir_r) x go_r with dir_r from the pinned pose oracle's definition (gaussian_utils.py:431-449)."""
+    from oracle import pose_ref
+
+    n = xyz.shape[0]
+    acc = torch.zeros(n, sh_coeffs, 3, dtype=torch.float64)
+    eye = torch.eye(sh_coeffs, dtype=torch.float64)
+    for r in range(gfdc_all.shape[0]):
+        campos = campos_all[r].double()
+        cam_inv = campos.expand(n, 3).clone()
+        if n_skinned:
+            tf = torch.einsum("nb,bij->nij", skin.double(), bone_all[r].double())
+            hom = torch.cat([campos, torch.ones(1, dtype=torch.float64)])
+            cam_inv[:n_skinned] = (torch.linalg.inv(tf) @ hom)[:, :3]
+        d = xyz.double() - cam_inv
+        d = d / d.norm(dim=1, keepdim=True)
+        basis = torch.stack([pose_ref.eval_sh(sh_degree, eye[k].expand(n, 1, sh_coeffs), d)[:, 0] for k in range(sh_coeffs)], 1)   # [n,K]
+        acc += basis[:, :, None] * (gfdc_all[r].double() / C0_SH)[:, None, :]
+    out_f_dc.copy_(acc[:, :1].float())
+    out_f_rest.copy_(acc[:, 1:].float())
+
+
+class _FakeRenderer:
+    def __init__(self, flat, rank):
+        g = torch.Generator().manual_seed(100 + rank)
+        self.flat, self.n_hand, self.sh_degree = flat, flat.n - 40, 3
+        w = torch.rand(self.n_hand, 21, generator=g) * (torch.rand(self.n_hand, 21, generator=g) < 0.2)
+        w[:, -1] += 0.1
+        gs = torch.Generator().manual_seed(7)                     # same skin weights / rest pose on every rank
+        w = torch.rand(self.n_hand, 21, generator=gs) * (torch.rand(self.n_hand, 21, generator=gs) < 0.2)
+        w[:, -1] += 0.1
+        self.skin = w / w.sum(1, keepdim=True)
+        self.rest_inv = torch.eye(4).repeat(20, 1, 1)
+        tf = torch.eye(4).repeat(21, 1, 1)
+        tf[:20, :3, :3] += 0.05 * torch.randn(20, 3, 3, generator=g)      # this rank's pose
+        tf[:20, :3, 3] = 0.02 * torch.randn(20, 3, generator=g)
+        self._bone_tf = tf
+        self._last_campos = torch.tensor([0.3, -0.2, 1.4]) + 0.1 * torch.randn(3, generator=g)
+
+
+def _compact_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from manus_b200.dist import CompactGradExchange
+
+        flat = make_flat()
+        flat.params["xyz"].mul_(0.05)
+        g = torch.Generator().manual_seed(rank)
+        flat.grad.copy_(torch.randn(flat.grad.shape, generator=g))        # f_rest part: stale values a compact backward leaves behind
+        r = _FakeRenderer(flat, rank)
+        torch.save(dict(grad=flat.grad.clone(), bone=r._bone_tf, campos=r._last_campos), os.path.join(out_dir, f"in_{rank}.pt"))
+        CompactGradExchange(r, rebuild=_rebuild_ref)()
+        np.save(os.path.join(out_dir, f"compact_{rank}.npy"), flat.grad.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_compact_exchange_equals_rebuilding_from_all_views(tmp_path):
+    world = 2
+    mp.spawn(_compact_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    ins = [torch.load(tmp_path / f"in_{r}.pt") for r in range(world)]
+    flat = make_flat()
+    flat.params["xyz"].mul_(0.05)
+    n = flat.n
+    exp = sum(i["grad"] for i in ins)                               # head and tail: plain sums
+    flat.grad.copy_(exp)
+    fake = _FakeRenderer(flat, 0)
+    gfdc_all = torch.stack([i["grad"][11 * n: 14 * n].reshape(n, 3) for i in ins])
+    _rebuild_ref(flat.params["xyz"], fake.skin, fake.n_hand, 3, 16, torch.stack([i["bone"] for i in ins]),
+                 torch.stack([i["campos"] for i in ins]), gfdc_all, flat.grads["f_dc"], flat.grads["f_rest"])
+    for r in range(world):
+        np.testing.assert_allclose(np.load(tmp_path / f"compact_{r}.npy"), flat.grad.numpy(), rtol=1e-6, atol=1e-6)
