@@ -521,16 +521,20 @@ struct ShViewsArgs {
 };
 
 constexpr int kShvTile = 128;   // Gaussians per CTA
+constexpr int kShvNz = 16;      // non-zero skin weights kept per Gaussian in compacted form
+constexpr int kShvNzStride = 2 * kShvNz + 1;   // odd: the per-thread rows do not collide on shared-memory banks
 
-// shared memory (floats): bones [R][B][13] | cameras [R][3] | skin tile [128][B] | output tile [128][3 (K-1)] (+1 pad per row)
+// shared memory (floats): bones [R][B][13] | cameras [R][3] | skin tile [128][B] | compacted weights [128][2 kShvNz + 1];
+// the output tile [128][3 (K-1)] (+1 pad per row) re-uses the skin / compacted-weight area once every thread is done with it
 template <int DEG>
-__global__ void __launch_bounds__(kShvTile) sh_grad_from_views_kernel(ShViewsArgs a) {
+__global__ void __launch_bounds__(kShvTile, 6) sh_grad_from_views_kernel(ShViewsArgs a) {
     constexpr int nb = (DEG + 1) * (DEG + 1);
     extern __shared__ float sh_smem[];
     float *bones_s = sh_smem, *cam_s = bones_s + (size_t)a.R * a.B * 13;
     float *skin_s = cam_s + 3 * a.R + ((3 * a.R) & 1);
     const int rs = (a.K - 1) * 3, rs_pad = rs | 1;            // odd row stride: conflict-free row-wise access
-    float *out_s = skin_s + (size_t)kShvTile * a.B;
+    float *nz_s = skin_s + (size_t)kShvTile * a.B;
+    float *out_s = skin_s;
     const int tid = threadIdx.x, base = blockIdx.x * kShvTile, cnt = min(kShvTile, a.N - base);
     for (int j = tid; j < a.R * a.B * 13; j += kShvTile) {
         const int rb = j / 13, e = j - 13 * rb;
@@ -543,13 +547,31 @@ __global__ void __launch_bounds__(kShvTile) sh_grad_from_views_kernel(ShViewsArg
     for (int j = tid; j < nsk * a.B; j += kShvTile) skin_s[j] = a.skin[(size_t)base * a.B + j];
     __syncthreads();
     const int i = base + tid;
+    float acc[nb][3];
+#pragma unroll
+    for (int k = 0; k < nb; ++k) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
     if (tid < cnt) {
         const float x[3] = {a.xyz[3 * (size_t)i], a.xyz[3 * (size_t)i + 1], a.xyz[3 * (size_t)i + 2]};
         const bool skinned = i < a.n_skinned;
-        float acc[nb][3];
-#pragma unroll
-        for (int k = 0; k < nb; ++k) acc[k][0] = acc[k][1] = acc[k][2] = 0.f;
+        // the weight row is sparse (a few bones per Gaussian): compact it once into (weight, bone) pairs so that every view
+        // only walks the non-zero entries; rows with more than kShvNz non-zeros keep the full scan
+        const float *w_row = skin_s + tid * a.B;
+        float *nz = nz_s + tid * kShvNzStride;
+        int nnz = 0;
+        if (skinned) {
+            for (int b = 0; b < a.B; ++b) {
+                const float w = w_row[b];
+                if (w == 0.f) continue;
+                if (nnz == kShvNz) { nnz = -1; break; }
+                nz[2 * nnz] = w;
+                nz[2 * nnz + 1] = __int_as_float(b);
+                ++nnz;
+            }
+        }
         for (int r = 0; r < a.R; ++r) {
+            // this view's DC gradient: requested first, used last (its latency hides behind the blend)
+            const float *g = a.g_fdc_all + (size_t)r * a.s_g + (size_t)i * 3;
+            const float g0 = g[0], g1 = g[1], g2 = g[2];
             PoseLocal p;
             p.x[0] = x[0]; p.x[1] = x[1]; p.x[2] = x[2];
             p.skinned = skinned;
@@ -558,11 +580,11 @@ __global__ void __launch_bounds__(kShvTile) sh_grad_from_views_kernel(ShViewsArg
 #pragma unroll
                 for (int k = 0; k < 9; ++k) p.A[k] = 0.f;
                 p.t[0] = p.t[1] = p.t[2] = 0.f; p.s = 0.f;
-                const float *w_row = skin_s + tid * a.B;
                 const float *bones = bones_s + (size_t)r * a.B * 13;
-                for (int b = 0; b < a.B; ++b) {
-                    const float w = w_row[b];
-                    if (w == 0.f) continue;
+                const int n_e = nnz >= 0 ? nnz : a.B;
+                for (int e = 0; e < n_e; ++e) {
+                    const float w = nnz >= 0 ? nz[2 * e] : w_row[e];
+                    const int b = nnz >= 0 ? __float_as_int(nz[2 * e + 1]) : e;
                     const float *T = bones + 13 * b;
                     p.A[0] += w * T[0]; p.A[1] += w * T[1]; p.A[2] += w * T[2]; p.t[0] += w * T[3];
                     p.A[3] += w * T[4]; p.A[4] += w * T[5]; p.A[5] += w * T[6]; p.t[1] += w * T[7];
@@ -573,8 +595,8 @@ __global__ void __launch_bounds__(kShvTile) sh_grad_from_views_kernel(ShViewsArg
             }
             view_dir(p, cam_s + 3 * r, Ainv, ci, dir);
             sh_basis(DEG, dir[0], dir[1], dir[2], basis);
-            const float *g = a.g_fdc_all + (size_t)r * a.s_g + (size_t)i * 3;
-            const float go[3] = {g[0] / MB_SH_C0, g[1] / MB_SH_C0, g[2] / MB_SH_C0};
+            const float inv_c0 = 1.0f / MB_SH_C0;
+            const float go[3] = {g0 * inv_c0, g1 * inv_c0, g2 * inv_c0};
 #pragma unroll
             for (int k = 0; k < nb; ++k)
 #pragma unroll
@@ -582,6 +604,9 @@ __global__ void __launch_bounds__(kShvTile) sh_grad_from_views_kernel(ShViewsArg
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) a.g_f_dc[3 * (size_t)i + c] = acc[0][c];
+    }
+    __syncthreads();              // every thread of the tile is done with the skin / compacted-weight area: it becomes the output tile
+    if (tid < cnt) {
         float *row = out_s + tid * rs_pad;
 #pragma unroll
         for (int k = 1; k < nb; ++k)
@@ -716,8 +741,8 @@ extern "C" int mb_sh_grad_from_views(const float *xyz, int32_t num_points, const
                      view_stride ? view_stride : (int64_t)nbones * 16, view_stride ? view_stride : 3,
                      view_stride ? view_stride : (int64_t)num_points * 3,
                      xyz, skin_wts, bone_tf_all, campos_all, g_f_dc_all, g_f_dc, g_f_rest};
-    const size_t smem = sizeof(float) * ((size_t)a.R * a.B * 13 + (size_t)a.R * 3 + 1 + (size_t)kShvTile * a.B +
-                                         (size_t)kShvTile * (((a.K - 1) * 3) | 1));
+    const size_t work = (size_t)kShvTile * a.B + (size_t)kShvTile * kShvNzStride, outt = (size_t)kShvTile * (((a.K - 1) * 3) | 1);
+    const size_t smem = sizeof(float) * ((size_t)a.R * a.B * 13 + (size_t)a.R * 3 + 1 + (work > outt ? work : outt));
     MB_REQUIRE(smem <= 200 * 1024, "mb_sh_grad_from_views: %d views x %d bones do not fit in shared memory", num_views, num_bones);
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = (num_points + kShvTile - 1) / kShvTile;
