@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--plain-allreduce", action="store_true",
                     help="N > 1: all-reduce the whole flat gradient buffer instead of the compact exchange (rank-one SH gradients)")
+    ap.add_argument("--compact-exchange", action="store_true", help="use the compact exchange for any N > 1 (default: N <= 4)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python each step instead of replaying the captured CUDA graph")
     return ap.parse_args()
 
@@ -322,7 +323,10 @@ def main():
     loss_fn = lambda image, target: (image * target).sum()
     # N > 1: the backward skips the f_rest gradient and the ranks exchange the rank-one SH gradient factors instead of
     # all-reducing all 59 floats per Gaussian (manus_b200.dist.CompactGradExchange)
-    compact = world > 1 and not args.plain_allreduce
+    # measured on B200 / NVSwitch: compact wins at N = 2 (0.838 vs 0.948 ms/step); at N = 8 the rebuild over 8 views costs
+    # what the smaller collective saves (1.060 vs 1.066 ms/step) and the extra launches hurt the per-step-synchronised e2e
+    # loop, so the default switches to the plain all-reduce above 4 ranks
+    compact = world > 1 and not args.plain_allreduce and (world <= 4 or args.compact_exchange)
     from manus_b200.dist import CompactGradExchange
     exchange = CompactGradExchange(r) if compact else None
     graphed = None if args.no_graph else GraphedStep(r, loss_fn, G_dev, view=views[0], compact_sh=compact)
