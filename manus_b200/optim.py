@@ -46,6 +46,17 @@ class FlatAdam:
         self._seg_end = (C.c_int64 * len(ends))(*ends)
         self.numel = off
 
+    def rebind(self, flat: FlatGaussians, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor) -> None:
+        """After densification / pruning changed N: new flat buffers and the moments that were carried over
+        (manus_b200.densify.GaussianState); the step count and learning rates continue."""
+        self.flat, self.exp_avg, self.exp_avg_sq = flat, exp_avg, exp_avg_sq
+        ends, off = [], 0
+        for name in PARAM_ORDER:
+            off += flat.params[name].numel()
+            ends.append(off)
+        self._seg_end = (C.c_int64 * len(ends))(*ends)
+        self.numel = off
+
     def set_lr(self, name: str, lr: float) -> None:
         """e.g. the per-step exponential schedule of the xyz group (gaussian.py:142-146, update_learning_rate)."""
         self.lr[GROUP_OF.get(name, name)] = float(lr)
