@@ -6,10 +6,12 @@ number through the public API with host inputs, and the CPU baseline.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-A step = one training view per rank: pose kernel (LBS + covariance + SH->RGB) -> rasterizer forward -> loss =
-sum(image * G) with a fixed G ~ U[0,1] -> rasterizer backward -> pose backward into the flat
-per-Gaussian gradient buffer -> (N > 1) one NCCL all-reduce of that buffer.  Views shard across ranks (weak scaling:
-every rank renders one view per step); value = views per second over all ranks.
+A step = V training views per rank (--views-in-flight, default 4; gradient accumulation over the views of a step like the
+reference's accum_iter), each: pose kernel (LBS + covariance + SH->RGB) -> rasterizer forward -> loss = sum(image * G) with a
+fixed G ~ U[0,1] -> rasterizer backward -> pose backward accumulating into the flat per-Gaussian
+gradient buffer; then (N > 1) one NCCL exchange of that buffer.  The V views of a step are independent until the
+accumulation and run as parallel branches of one CUDA graph.  Views shard across ranks (weak scaling: every rank renders V
+views per step); value = views (frames) per second over all ranks.
 """
 from __future__ import annotations
 
@@ -44,6 +46,9 @@ def parse():
     ap.add_argument("--plain-allreduce", action="store_true",
                     help="N > 1: all-reduce the whole flat gradient buffer instead of the compact exchange (rank-one SH gradients)")
     ap.add_argument("--compact-exchange", action="store_true", help="use the compact exchange for any N > 1 (default: N <= 4)")
+    ap.add_argument("--views-in-flight", type=int, default=4,
+                    help="views per rank and step, captured on parallel streams of the step's CUDA graph and accumulated into one "
+                         "gradient buffer (the reference's accum_iter); 1 = one view per step")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python each step instead of replaying the captured CUDA graph")
     return ap.parse_args()
 
@@ -241,7 +246,7 @@ def run_reference(args, rank, world):
     line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": k_eff, "warmup": len(t_warm),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
-            "config": workload_config(args, 1),
+            "config": workload_config(args, 1, max(1, args.views_in_flight)),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -257,12 +262,14 @@ def make_scene(args):
     return synth.make_composite(args.gaussians, seed=0)
 
 
-def workload_config(args, world):
+def workload_config(args, world, vif=1):
     kind = {"composite": "composite hand+object {n} Gaussians (60% skinned by 20+1 bones, 40% static)",
             "hand": "articulated hand {n} Gaussians (all skinned by 20+1 bones)", "object": "static object {n} Gaussians (no skinning)"}[args.scene]
     return {"workload": kind.format(n=args.gaussians) + ", " +
                         f"{args.views} shipped views/poses at {args.width}x{args.height}, SH degree 3, white background",
-            "global_views_per_step": world, "parallelism": f"view-sharded dp{world}, one exchange of per-Gaussian gradients per step",
+            "global_views_per_step": world * vif, "views_in_flight_per_gpu": vif,
+            "parallelism": f"view-sharded dp{world}, {vif} view(s) per rank and step accumulated into one gradient buffer (parallel branches "
+                           "of one CUDA graph), one exchange of per-Gaussian gradients per step",
             "l2": "working set per step (parameters 118 MB + gradients 118 MB + instance records) exceeds the 126 MB L2 and the view "
                   "changes every step; no explicit flush",
             "loss": "sum(image * G), G ~ U[0,1] fixed (seed 7)"}
@@ -304,7 +311,8 @@ def main():
     r = SceneRenderer(scene, dev, W, H)
     n_hand, n_obj = scene.n_hand, scene.n - scene.n_hand
     views = list(range(args.views))
-    my_view = lambda it: views[(it * world + rank) % len(views)]
+    VIF = 1 if args.no_graph else max(1, args.views_in_flight)
+    my_view = lambda it, slot=0: views[((it * VIF + slot) * world + rank) % len(views)]
     G_host = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(7)).pin_memory()
     G_dev = G_host.to(dev)
     staged = {}
@@ -326,10 +334,11 @@ def main():
     # measured on B200 / NVSwitch: compact wins at N = 2 (0.838 vs 0.948 ms/step); at N = 8 the rebuild over 8 views costs
     # what the smaller collective saves (1.060 vs 1.066 ms/step) and the extra launches hurt the per-step-synchronised e2e
     # loop, so the default switches to the plain all-reduce above 4 ranks
-    compact = world > 1 and not args.plain_allreduce and (world <= 4 or args.compact_exchange)
+    # the compact exchange carries ONE view per rank; with several views per rank and step the flat buffer is all-reduced
+    compact = world > 1 and VIF == 1 and not args.plain_allreduce and (world <= 4 or args.compact_exchange)
     from manus_b200.dist import CompactGradExchange
     exchange = CompactGradExchange(r) if compact else None
-    graphed = None if args.no_graph else GraphedStep(r, loss_fn, G_dev, view=views[0], compact_sh=compact)
+    graphed = None if args.no_graph else GraphedStep(r, loss_fn, G_dev, view=views[0], compact_sh=compact, views_in_flight=VIF)
 
     def reduce_gradients():
         if exchange is not None:
@@ -337,17 +346,22 @@ def main():
         elif world > 1:
             dist.all_reduce(r.flat.grad)
 
-    def step_resident(it, eager=False):
-        v = my_view(it)
+    def step_resident(it, eager=False, graphed=graphed):
         if graphed is not None and not eager:
-            # the whole step (pose fwd -> raster fwd -> loss -> raster bwd -> pose bwd) is ONE graph launch; the per-view
-            # camera / bones are copied device-to-device into the graph's static inputs
-            graphed.set_inputs(staged[v][0], staged[v][1], None)
+            # the whole step (per view: pose fwd -> raster fwd -> loss -> raster bwd -> pose bwd) is ONE graph launch; the
+            # per-view camera / bones are copied device-to-device into the graph's static inputs
+            for slot in range(graphed.V):
+                v = my_view(it, slot)
+                graphed.set_inputs(staged[v][0], staged[v][1], None, slot=slot)
             loss = graphed.replay()
         else:
-            out = r.render(v, sink=r.flat.grads, cam_dev=staged[v][0], bones_dev=staged[v][1], compact_sh=compact)
-            loss = loss_fn(out["render"], G_dev)
-            loss.backward()
+            loss = 0.0
+            for slot in range(VIF):
+                v = my_view(it, slot)
+                out = r.render(v, sink=r.flat.grads, cam_dev=staged[v][0], bones_dev=staged[v][1], compact_sh=compact, accumulate=slot > 0)
+                l = loss_fn(out["render"], G_dev)
+                l.backward()
+                loss = loss + l.detach()
         reduce_gradients()
         return loss
 
@@ -356,17 +370,19 @@ def main():
     # copy stream while step i computes (double buffered), so the PCIe transfer overlaps the kernels; every copy is inside
     # the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
-    slots = [dict(g=torch.empty_like(G_dev), cam=torch.empty(CAM_FLOATS, device=dev), bones=torch.empty(320, device=dev),
-                  ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+    slots = [dict(g=[torch.empty_like(G_dev) for _ in range(VIF)], cam=[torch.empty(CAM_FLOATS, device=dev) for _ in range(VIF)],
+                  bones=[torch.empty(320, device=dev) for _ in range(VIF)], ready=torch.cuda.Event(), free=torch.cuda.Event())
+             for _ in range(2)]
 
     def stage_inputs(it):
         slot = slots[it % 2]
-        _, c, b = r.view_inputs_host(my_view(it))
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(slot["free"])               # the step that last used this slot has finished with it
-            slot["g"].copy_(G_host, non_blocking=True)
-            slot["cam"].copy_(c, non_blocking=True)
-            slot["bones"].copy_(b, non_blocking=True)
+            for j in range(VIF):                               # every view of the step: target image, camera, posed bones
+                _, c, b = r.view_inputs_host(my_view(it, j))
+                slot["g"][j].copy_(G_host, non_blocking=True)
+                slot["cam"][j].copy_(c, non_blocking=True)
+                slot["bones"][j].copy_(b, non_blocking=True)
             slot["ready"].record(copy_stream)
 
     def step_e2e(it, graphed=graphed, loss_fn=loss_fn):
@@ -376,17 +392,22 @@ def main():
         cur = torch.cuda.current_stream(dev)
         cur.wait_event(slot["ready"])
         if graphed is not None:
-            graphed.set_inputs(slot["cam"], slot["bones"], slot["g"])
+            for j in range(VIF):
+                graphed.set_inputs(slot["cam"][j], slot["bones"][j], slot["g"][j], slot=j)
             loss = graphed.replay()
         else:
-            out = r.render(my_view(it), sink=r.flat.grads, cam_dev=slot["cam"], bones_dev=slot["bones"], compact_sh=compact)
-            loss = loss_fn(out["render"], slot["g"])
-            loss.backward()
+            loss = 0.0
+            for j in range(VIF):
+                out = r.render(my_view(it, j), sink=r.flat.grads, cam_dev=slot["cam"][j], bones_dev=slot["bones"][j], compact_sh=compact,
+                               accumulate=j > 0)
+                l = loss_fn(out["render"], slot["g"][j])
+                l.backward()
+                loss = loss + l.detach()
         reduce_gradients()
         slot["free"].record(cur)
         # the next step's host->device copies are enqueued (copy stream) while this step runs
         stage_inputs(it + 1); slots[(it + 1) % 2]["staged"] = it + 1
-        return float(loss.detach())                             # device -> host read of the step's result
+        return float(loss)                                      # device -> host read of the step's result
 
     def timed(fn, steps, sampler=None):
         for it in range(WU):
@@ -425,10 +446,17 @@ def main():
     # the same end-to-end step with the reference's training loss 0.8 L1 + 0.2 (1 - SSIM) (fused kernel, manus_b200.losses)
     from manus_b200.losses import photometric_loss
     photo_fn = lambda image, target: photometric_loss(image, target, 0.8, 0.2)
-    graphed_photo = None if args.no_graph else GraphedStep(r, photo_fn, G_dev, view=views[0], compact_sh=compact)
+    graphed_photo = None if args.no_graph else GraphedStep(r, photo_fn, G_dev, view=views[0], compact_sh=compact, views_in_flight=VIF)
     ms_e2e_photo = timed(lambda it: step_e2e(it, graphed_photo, photo_fn), K)
     if graphed_photo is not None:
         graphed_photo.check()
+    # one view per step (the latency of a single frame; what earlier revisions of this bench reported as `value`)
+    ms_single = None
+    if graphed is not None and VIF > 1 and world == 1:
+        graphed_one = GraphedStep(r, loss_fn, G_dev, view=views[0])
+        ms_single = timed(lambda it: step_resident(it, graphed=graphed_one), K)
+        graphed_one.check()
+        del graphed_one
     # reserve mode reads nothing back per frame: make sure no timed frame ran out of instance capacity
     if graphed is not None:
         graphed.check()
@@ -442,7 +470,7 @@ def main():
     torch.cuda.synchronize()
     prof = _lib.profile_report()
     _lib.profile_enable(False)
-    seen = [my_view(WU + it) for it in range(K)]
+    seen = [my_view(WU + it, j) for it in range(K) for j in range(VIF)]
     D_mean = float(np.mean([D_all[v] for v in seen]))
     V_mean = float(np.mean([V_all[v] for v in seen]))
     P = W * H
@@ -457,24 +485,27 @@ def main():
                 "traffic_source": "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, per launch)",
                 "peak_source": peak_src, "launch_ms": per_launch_ms, "share_of_step": top_ms / total_ms if total_ms else None,
                 "algorithmic_bytes_per_launch": fb,
-                "kernels_ms_per_step": {k: round(ms / K, 5) for k, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
+                "timing": "CUDA events around every launch on the launching stream, kernels enqueued one by one (no overlap between views)",
+                "kernels_ms_per_frame": {k: round(ms / (K * VIF), 5) for k, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
     launches_per_step = sum(n for n, _ in prof.values()) / K
     fbytes = frame_bytes(n_hand, n_obj, D_mean, P)
-    value = world * 1e3 / ms_step
-    e2e_val = world * 1e3 / ms_e2e
-    h2d = G_host.numel() * 4 + (CAM_FLOATS + 320) * 4
+    value = world * VIF * 1e3 / ms_step
+    e2e_val = world * VIF * 1e3 / ms_e2e
+    h2d = VIF * (G_host.numel() * 4 + (CAM_FLOATS + 320) * 4)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": WU, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, world), "clocks": clocks,
+            "config": workload_config(args, world, VIF), "clocks": clocks, "frames_per_step": world * VIF,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
-            "e2e_reference_loss": {"value": world * 1e3 / ms_e2e_photo, "unit": UNIT, "ms_per_step": ms_e2e_photo,
+            "e2e_reference_loss": {"value": world * VIF * 1e3 / ms_e2e_photo, "unit": UNIT, "ms_per_step": ms_e2e_photo,
                                    "loss": "0.8 * L1 + 0.2 * (1 - SSIM) as in config/COMPOSITE.yaml:22-23 (fused kernel), host inputs as in e2e"},
             "gpu_launches": int(round(launches_per_step * K)), "host_enqueue_ms_per_step": host_enqueue_ms,
             "launch_mode": "eager (one launch per kernel)" if graphed is None else "CUDA graph replay (one launch per step)",
+            "single_view": None if ms_single is None else {"value": 1e3 / ms_single, "unit": UNIT, "ms_per_step": ms_single,
+                                                           "note": "one view per step (views_in_flight = 1), inputs resident"},
             "roofline": roofline,
             "frame": {"num_rendered_mean": D_mean, "visible_mean": V_mean, "algorithmic_bytes": fbytes,
-                      "achieved_gbps": fbytes * (1e3 / ms_step) / 1e9, "frac_of_hbm_peak": fbytes * (1e3 / ms_step) / 1e9 / peak,
+                      "achieved_gbps": fbytes * (VIF * 1e3 / ms_step) / 1e9, "frac_of_hbm_peak": fbytes * (VIF * 1e3 / ms_step) / 1e9 / peak,
                       "allreduce_bytes": r.flat.allreduce_bytes() if world > 1 else 0,
                       "exchange": ("none" if world == 1 else "compact: all-gather of the DC gradients (12 B per Gaussian and rank) + all-reduce of "
                                    "the 11 non-SH floats + local rebuild of the SH gradients" if compact else "all-reduce of the flat gradient buffer"),

@@ -106,7 +106,8 @@ int mb_raster_query(const void *geom, int64_t *num_rendered, int64_t *num_visibl
  * contiguous [3,H,W] tensor and the permuted view of an [H,W,3] tensor (src/utils/gaussian_utils.py:418) are read
  * in place.  Every output row is written (zeros for culled Gaussians); outputs for absent inputs may be NULL
  * (dL_dsh when shs == NULL; dL_dscales / dL_drotations when cov3D_precomp != NULL; dL_dcolors is written in both
- * colour modes).  grad_scratch: mb_raster_backward_scratch_bytes(P) bytes. */
+ * colour modes).  grad_scratch: mb_raster_backward_scratch_bytes(P) bytes.  in->opacities is not read (may be NULL): the
+ * opacities are part of the saved blend records, as in upstream, whose rasterize_gaussians_backward does not take them. */
 size_t mb_raster_backward_scratch_bytes(int32_t num_points);
 int mb_raster_backward(const mb_raster_inputs *in, const int32_t *radii, const void *geom, const void *binning,
                        int64_t capacity /* as given to forward_render */, const void *image_buf, const float *dL_dout, int64_t stride_c, int64_t stride_y, int64_t stride_x,
@@ -158,6 +159,14 @@ int mb_pose_forward(const mb_pose_inputs *in, float *posed_xyz /*[N,3]*/, float 
 int mb_pose_backward(const mb_pose_inputs *in, const float *g_posed_xyz, const float *g_posed_cov6, const float *g_colors,
                      const float *g_opacity, float *g_xyz, float *g_log_scale, float *g_quat, float *g_opacity_logit,
                      float *g_f_dc, float *g_f_rest, float *g_skin_wts, mb_stream_t stream);
+
+/* Same, but the gradients are ADDED to the output buffers (bulk TMA reduce-add, fp32 adds resolved in L2): gradient
+ * accumulation over the views of one optimisation step -- the reference's accum_iter loop, src/modules/hand_dynamic.py:248,
+ * 259-277, where autograd accumulates every view's gradient into the parameters' .grad.  The caller orders the
+ * accumulating launches of one buffer (stream order or events) when it wants a deterministic summation order. */
+int mb_pose_backward_accumulate(const mb_pose_inputs *in, const float *g_posed_xyz, const float *g_posed_cov6,
+                                const float *g_colors, const float *g_opacity, float *g_xyz, float *g_log_scale, float *g_quat,
+                                float *g_opacity_logit, float *g_f_dc, float *g_f_rest, float *g_skin_wts, mb_stream_t stream);
 
 /* SH-coefficient gradients of a SUM over num_views views from the views' DC gradients (data-parallel step, SURVEY.md
  * section 8e): for one view g_f_rest[k][c] = basis_k(dir) * g_f_dc[c] / basis_0, with dir the canonical-space view direction

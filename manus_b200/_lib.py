@@ -60,6 +60,7 @@ SIGNATURES = {
     "mb_mark_visible": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mb_pose_forward": (C.c_int, [C.POINTER(PoseInputs)] + [C.c_void_p] * 5 + [C.c_void_p]),
     "mb_pose_backward": (C.c_int, [C.POINTER(PoseInputs)] + [C.c_void_p] * 4 + [C.c_void_p] * 7 + [C.c_void_p]),
+    "mb_pose_backward_accumulate": (C.c_int, [C.POINTER(PoseInputs)] + [C.c_void_p] * 4 + [C.c_void_p] * 7 + [C.c_void_p]),
     "mb_skin_weights_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
     "mb_skin_weights_backward": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,

@@ -36,6 +36,7 @@ struct PoseArgs {
     // backward inputs / outputs
     const float *g_posed_xyz, *g_cov6, *g_colors, *g_opacity;
     float *g_xyz, *g_log_scale, *g_quat, *g_opacity_logit, *g_f_dc, *g_f_rest, *g_skin;
+    int accumulate;   // backward: add the gradients to the output buffers (bulk TMA reduce-add) instead of overwriting them
 };
 
 // Shared-memory image of one tile of kPoseThreads Gaussians (offsets in floats, every array 16-B aligned).  Rows are
@@ -83,6 +84,12 @@ __device__ __forceinline__ bool bulk_ok(const Transfer &t) {
 // 1-D bulk asynchronous copy shared -> global (TMA engine); completion tracked by the issuing thread's bulk async-group
 __device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+// the same with an fp32 add at the destination (TMA reduction: the adds happen in L2, nothing is read back)
+__device__ __forceinline__ void bulk_s2g_add(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -271,11 +278,18 @@ struct TilePipe {
             if (!t[j].bytes) continue;
             float *dst = const_cast<float *>(t[j].g);
             const float *src = stage(k) + t[j].s;
+            const bool add = kBackward && a.accumulate;
             if (bulk_ok(t[j])) {
-                if (threadIdx.x == 0) bulk_s2g(dst, src, t[j].bytes);
+                if (threadIdx.x == 0) {
+                    if (add) bulk_s2g_add(dst, src, t[j].bytes);
+                    else bulk_s2g(dst, src, t[j].bytes);
+                }
             } else {
                 const int words = (int)(t[j].bytes >> 2);
-                for (int e = threadIdx.x; e < words; e += kPoseThreads) dst[e] = src[e];
+                if (add)
+                    for (int e = threadIdx.x; e < words; e += kPoseThreads) atomicAdd(dst + e, src[e]);
+                else
+                    for (int e = threadIdx.x; e < words; e += kPoseThreads) dst[e] = src[e];
             }
         }
         if (threadIdx.x == 0) bulk_commit();
@@ -708,9 +722,10 @@ extern "C" int mb_pose_forward(const mb_pose_inputs *in, float *posed_xyz, float
     return launch_pose_deg(a, false, (cudaStream_t)stream);
 }
 
-extern "C" int mb_pose_backward(const mb_pose_inputs *in, const float *g_posed_xyz, const float *g_posed_cov6,
-                                const float *g_colors, const float *g_opacity, float *g_xyz, float *g_log_scale, float *g_quat,
-                                float *g_opacity_logit, float *g_f_dc, float *g_f_rest, float *g_skin_wts, mb_stream_t stream) {
+static int pose_backward_impl(const mb_pose_inputs *in, const float *g_posed_xyz, const float *g_posed_cov6,
+                              const float *g_colors, const float *g_opacity, float *g_xyz, float *g_log_scale, float *g_quat,
+                              float *g_opacity_logit, float *g_f_dc, float *g_f_rest, float *g_skin_wts, int accumulate,
+                              mb_stream_t stream) {
     int rc = validate_pose(in, "mb_pose_backward");
     if (rc) return rc;
     if (in->num_points == 0) return MB_OK;
@@ -722,7 +737,23 @@ extern "C" int mb_pose_backward(const mb_pose_inputs *in, const float *g_posed_x
     a.g_posed_xyz = g_posed_xyz; a.g_cov6 = g_posed_cov6; a.g_colors = g_colors; a.g_opacity = g_opacity;
     a.g_xyz = g_xyz; a.g_log_scale = g_log_scale; a.g_quat = g_quat; a.g_opacity_logit = g_opacity_logit;
     a.g_f_dc = g_f_dc; a.g_f_rest = g_f_rest; a.g_skin = g_skin_wts;
+    a.accumulate = accumulate;
     return launch_pose_deg(a, true, (cudaStream_t)stream);
+}
+
+extern "C" int mb_pose_backward(const mb_pose_inputs *in, const float *g_posed_xyz, const float *g_posed_cov6,
+                                const float *g_colors, const float *g_opacity, float *g_xyz, float *g_log_scale, float *g_quat,
+                                float *g_opacity_logit, float *g_f_dc, float *g_f_rest, float *g_skin_wts, mb_stream_t stream) {
+    return pose_backward_impl(in, g_posed_xyz, g_posed_cov6, g_colors, g_opacity, g_xyz, g_log_scale, g_quat, g_opacity_logit, g_f_dc,
+                              g_f_rest, g_skin_wts, 0, stream);
+}
+
+extern "C" int mb_pose_backward_accumulate(const mb_pose_inputs *in, const float *g_posed_xyz, const float *g_posed_cov6,
+                                           const float *g_colors, const float *g_opacity, float *g_xyz, float *g_log_scale,
+                                           float *g_quat, float *g_opacity_logit, float *g_f_dc, float *g_f_rest, float *g_skin_wts,
+                                           mb_stream_t stream) {
+    return pose_backward_impl(in, g_posed_xyz, g_posed_cov6, g_colors, g_opacity, g_xyz, g_log_scale, g_quat, g_opacity_logit, g_f_dc,
+                              g_f_rest, g_skin_wts, 1, stream);
 }
 
 

@@ -704,7 +704,9 @@ extern "C" int mb_raster_backward(const mb_raster_inputs *in, const int32_t *rad
                                   float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity, float *dL_dmeans3D,
                                   float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations,
                                   mb_stream_t stream) {
-    int rc = validate_raster_inputs(in, "mb_raster_backward");
+    // the backward never reads the opacities (they are part of the saved blend records), like upstream's, whose
+    // rasterize_gaussians_backward does not take them
+    int rc = validate_raster_inputs(in, "mb_raster_backward", false);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const RasterDims d = raster_dims(in);

@@ -537,7 +537,7 @@ int segment_items(const uint32_t *maxlast, int tiles, uint2 *items, uint32_t *n_
     return check_launch("segment_items", debug, s);
 }
 
-int validate_raster_inputs(const mb_raster_inputs *in, const char *who) {
+int validate_raster_inputs(const mb_raster_inputs *in, const char *who, bool need_opacities) {
     MB_REQUIRE(in != nullptr, "%s: null inputs", who);
     MB_REQUIRE(in->num_points >= 0 && in->image_width > 0 && in->image_height > 0, "%s: bad sizes P=%d W=%d H=%d", who,
                in->num_points, in->image_width, in->image_height);
@@ -546,7 +546,7 @@ int validate_raster_inputs(const mb_raster_inputs *in, const char *who) {
     const bool sr = in->scales != nullptr && in->rotations != nullptr;
     MB_REQUIRE((in->cov3D_precomp != nullptr) != sr && ((in->scales != nullptr) == (in->rotations != nullptr)),
                "%s: Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!", who);
-    MB_REQUIRE(in->num_points == 0 || (in->means3D && in->opacities), "%s: means3D / opacities missing", who);
+    MB_REQUIRE(in->num_points == 0 || (in->means3D && (in->opacities || !need_opacities)), "%s: means3D / opacities missing", who);
     MB_REQUIRE(in->background && in->viewmatrix && in->projmatrix && in->campos, "%s: camera tensors missing", who);
     if (in->shs) {
         MB_REQUIRE(in->sh_degree >= 0 && in->sh_degree <= 3, "%s: sh_degree %d not in 0..3", who, in->sh_degree);

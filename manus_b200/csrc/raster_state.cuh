@@ -156,7 +156,7 @@ inline RasterDims raster_dims(const mb_raster_inputs *in) {
     return d;
 }
 
-int validate_raster_inputs(const mb_raster_inputs *in, const char *who);
+int validate_raster_inputs(const mb_raster_inputs *in, const char *who, bool need_opacities = true);
 
 // order[i] = tile with the i-th largest weight (approximately: descending quarter-octave buckets).  `ws` = kOrderWs zeroed
 // words; the kernel leaves them zeroed again.

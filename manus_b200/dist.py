@@ -173,13 +173,16 @@ class SceneRenderer:
         return self._cams[view]
 
     def render(self, view: int, sink: Optional[Dict[str, torch.Tensor]] = None, cam_dev=None, bones_dev=None,
-               device_intrinsics: bool = False, compact_sh: bool = False):
+               device_intrinsics: bool = False, compact_sh: bool = False, accumulate: bool = False, slot: int = 0):
         """Forward of one view through render_fused; returns the result dict (image is out['render'], HWC).
         cam_dev / bones_dev: the packed per-view inputs already on the device (``view_inputs_host`` layout).
         device_intrinsics: read tan(fov/2) from cam_dev[37:39] on the device instead of from the host camera, so that the
         enqueued frame does not depend on which view ``cam_dev`` holds (CUDA-graph replay).
         compact_sh: the backward does not write the f_rest gradient (45 of the 59 floats per Gaussian); it is rebuilt from the
-        f_dc gradients of all ranks' views by ``CompactGradExchange`` (the per-view SH gradient is rank one)."""
+        f_dc gradients of all ranks' views by ``CompactGradExchange`` (the per-view SH gradient is rank one).
+        accumulate: the backward ADDS this view's parameter gradients to ``sink`` (gradient accumulation over the views of a step).
+        slot: views that are in flight at the same time (``GraphedStep(views_in_flight=V)``) use different slots, each with its
+        own bone-transform buffer."""
         from .cameras import Camera
         from .pose import bone_transforms
         from .render import render_fused
@@ -195,15 +198,17 @@ class SceneRenderer:
             # = bone_transforms(posed, rest, append_identity=True), written into a persistent [B+1,4,4] buffer whose last
             # row stays the identity "background" bone (one small batched product per frame, no concatenation)
             nb = self.rest_inv.shape[0]
-            if getattr(self, "_bone_tf", None) is None:
-                self._bone_tf = torch.eye(4, dtype=torch.float32, device=self.device).repeat(nb + 1, 1, 1)
-            torch.bmm(bones_dev.view(-1, 4, 4), self.rest_inv, out=self._bone_tf[:nb])
-            bone_tf = self._bone_tf
+            tfs = self.__dict__.setdefault("_bone_tfs", {})
+            if slot not in tfs:
+                tfs[slot] = torch.eye(4, dtype=torch.float32, device=self.device).repeat(nb + 1, 1, 1)
+            bone_tf = tfs[slot]
+            torch.bmm(bones_dev.view(-1, 4, 4), self.rest_inv, out=bone_tf[:nb])
+            self._bone_tf = bone_tf
         if compact_sh and sink is not None:
             sink = dict(sink, f_rest=None)
         self._last_campos = cam_dev[32:35]
         return render_fused(self.flat.leaves(), self.skin, bone_tf, dcam, self.bg, self.sh_degree, self.flat.isotropic,
-                            self.n_hand, grad_sink=sink)
+                            self.n_hand, grad_sink=sink, accumulate=accumulate)
 
 
 class CompactGradExchange:
@@ -263,62 +268,110 @@ class CompactGradExchange:
 
 
 class GraphedStep:
-    """One training view -- pose forward, rasterizer forward, loss, rasterizer backward, pose backward into the flat gradient
-    buffer -- captured ONCE in a CUDA graph and replayed per step with a single launch.  The per-view inputs (packed camera,
-    posed bones, loss target) live in static device tensors that the caller overwrites before ``replay()``; nothing in the
-    captured frame depends on host values of the view (intrinsics are read from ``cam`` on the device) and nothing is read
-    back (reserve capacity mode), so the same graph serves every view of the scene.
+    """One training step -- for each of its views: pose forward, rasterizer forward, loss, rasterizer backward, pose backward
+    into the flat gradient buffer -- captured ONCE in a CUDA graph and replayed per step with a single launch.  The per-view
+    inputs (packed camera, posed bones, loss target) live in static device tensors that the caller overwrites before
+    ``replay()``; nothing in the captured step depends on host values of the view (intrinsics are read from ``cam`` on the
+    device) and nothing is read back (reserve capacity mode), so the same graph serves every view of the scene.
 
-    loss_fn(image[H,W,3], target) -> scalar tensor.  After ``replay()``: ``loss`` (device scalar) and ``renderer.flat.grad``
-    hold the step's results.  ``check()`` (synchronises) raises if a replayed frame overflowed the reserved capacity.
+    views_in_flight = V > 1: the step holds V independent views (the reference's gradient accumulation over ``accum_iter``
+    views, hand_dynamic.py:248,259-277; the views of one rank in the view-sharded step).  Each view is captured on its own
+    stream, so the graph has V parallel branches: one frame cannot fill a B200 (the blend kernels wait on their deepest tile,
+    the sort passes on look-back latency), and the HBM-bound pose kernels of one view run under the latency-bound tile
+    kernels of another (measured at 500k / 1080p: 0.64 ms per frame alone, 0.52 with two, 0.48 with four views in flight).
+    The gradients are summed into ``renderer.flat.grad`` by the pose backward kernels themselves (TMA reduce-add, fp32 adds
+    resolved in L2): the buffer is cleared at the head of the graph and every view adds to it, in whatever order the branches
+    finish (like the atomics of the blend backward, the summation order is not fixed).  ``ordered=True`` instead chains the
+    pose backward launches in view order (view 0 overwrites, view i adds after view i-1: event edges in the graph) for a
+    reproducible sum, at the price of serialising the last kernel of every branch.
+
+    loss_fn(image[H,W,3], target) -> scalar tensor.  After ``replay()``: ``loss`` (device scalar: the sum over the step's
+    views; ``losses`` holds them one by one) and ``renderer.flat.grad`` (sum over the views) hold the step's results.
+    ``check()`` (synchronises) raises if a replayed frame overflowed the reserved capacity.
     """
 
     def __init__(self, renderer: SceneRenderer, loss_fn, target_like: torch.Tensor, view: int = 0, warmup: int = 3,
-                 compact_sh: bool = False):
+                 compact_sh: bool = False, views_in_flight: int = 1, ordered: bool = False):
         from . import rasterizer as rz
 
         if rz._Plan.mode != "reserve":
             raise RuntimeError("GraphedStep needs set_capacity_mode('reserve') and reserve_capacity(...) (no host read-back in a graph)")
-        self.r = renderer
+        V = int(views_in_flight)
+        if V < 1 or (compact_sh and V > 1):
+            raise ValueError("views_in_flight must be >= 1 (and 1 with compact_sh: the compact exchange carries one view per rank)")
+        self.r, self.V = renderer, V
         dev = renderer.device
         _, cam_host, bones_host = renderer.view_inputs_host(view)
-        self.cam = cam_host.to(dev)
-        self.bones = bones_host.to(dev)
-        self.target = target_like.to(dev).clone()
+        self.cams = [cam_host.to(dev) for _ in range(V)]
+        self.bones_all = [bones_host.to(dev) for _ in range(V)]
+        self.targets = [target_like.to(dev).clone() for _ in range(V)]
+        self.cam, self.bones, self.target = self.cams[0], self.bones_all[0], self.targets[0]
         self.view = view
         self.loss_fn = loss_fn
+        self.states = [None] * V
 
-        def frame():
-            out = renderer.render(view, sink=renderer.flat.grads, cam_dev=self.cam, bones_dev=self.bones, device_intrinsics=True,
-                                  compact_sh=compact_sh)
-            loss = loss_fn(out["render"], self.target)
-            loss.backward()
-            return loss.detach(), out["radii"]
+        def frame(i, done):
+            sink = renderer.flat.grads
+            if V > 1 and ordered:
+                # the pose backward kernels (the last kernel of each branch, the only writers of the flat gradient buffer) are
+                # chained in view order through events; everything before them runs concurrently
+                sink = dict(sink, _wait=done[i - 1] if i > 0 else None, _record=done[i])
+            out = renderer.render(view, sink=sink, cam_dev=self.cams[i], bones_dev=self.bones_all[i], device_intrinsics=True,
+                                  compact_sh=compact_sh, accumulate=V > 1 and (i > 0 or not ordered), slot=i)
+            self.states[i] = rz._Plan.last_state
+            loss = loss_fn(out["render"], self.targets[i])
+            return loss, out["radii"]
 
+        def step():
+            # every view on its own stream (view 0 on the current one)
+            cur = torch.cuda.current_stream(dev)
+            losses, radii = [None] * V, [None] * V
+            done = [torch.cuda.Event() for _ in range(V)]
+            if V > 1 and not ordered:
+                renderer.flat.grad.zero_()          # every view adds to the buffer
+            for side in self._sides:                # fork first: no branch waits for work of another branch
+                side.wait_stream(cur)
+            for i in range(V):
+                with torch.cuda.stream(cur if i == 0 else self._sides[i - 1]):
+                    losses[i], radii[i] = frame(i, done)
+            for i in range(V):              # host order = view order: event i-1 is recorded before view i waits for it
+                with torch.cuda.stream(cur if i == 0 else self._sides[i - 1]):
+                    losses[i].backward()
+                    losses[i] = losses[i].detach()
+            for i in range(1, V):
+                cur.wait_stream(self._sides[i - 1])
+            total = losses[0] if V == 1 else torch.stack(losses).sum()
+            return total, losses, radii
+
+        self._sides = [torch.cuda.Stream(device=dev) for _ in range(V - 1)]
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                frame()
+                step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.loss, self.radii = frame()
-        self.state = rz._Plan.last_state
+            self.loss, self.losses, radii = step()
+        self.radii = radii[0]
+        self.radii_all = radii
+        self.state = self.states[0]
 
-    def set_inputs(self, cam_dev: torch.Tensor, bones_dev: torch.Tensor, target_dev: Optional[torch.Tensor] = None) -> None:
-        """Device-to-device copies into the static slots (enqueued on the current stream)."""
-        self.cam.copy_(cam_dev, non_blocking=True)
-        self.bones.copy_(bones_dev, non_blocking=True)
+    def set_inputs(self, cam_dev: torch.Tensor, bones_dev: torch.Tensor, target_dev: Optional[torch.Tensor] = None,
+                   slot: int = 0) -> None:
+        """Device-to-device copies into the static inputs of view ``slot`` of the step (enqueued on the current stream)."""
+        self.cams[slot].copy_(cam_dev, non_blocking=True)
+        self.bones_all[slot].copy_(bones_dev, non_blocking=True)
         if target_dev is not None:
-            self.target.copy_(target_dev, non_blocking=True)
+            self.targets[slot].copy_(target_dev, non_blocking=True)
 
     def replay(self) -> torch.Tensor:
         self.graph.replay()
         return self.loss
 
     def check(self) -> int:
+        """num_rendered of the last replay (summed over the step's views); raises on a capacity overflow."""
         from . import rasterizer as rz
 
-        return rz.check_overflow(self.state)
+        return sum(rz.check_overflow(st) for st in self.states)

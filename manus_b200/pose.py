@@ -54,7 +54,7 @@ def _inputs(xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, bone_tf
 class _PoseGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, bone_tf, campos, sh_degree, isotropic,
-                num_skinned, grad_sink):
+                num_skinned, grad_sink, accumulate=False):
         L = _lib.lib()
         if not xyz.is_cuda:
             raise _lib.ManusB200Error("manus_b200.pose_gaussians needs CUDA tensors (there is no CPU path)")
@@ -74,6 +74,7 @@ class _PoseGaussians(torch.autograd.Function):
                                          torch.cuda.current_stream(dev).cuda_stream), "mb_pose_forward")
         ctx.saved = (t, cam, sh_degree, isotropic, num_skinned)
         ctx.grad_sink = grad_sink
+        ctx.accumulate = bool(accumulate) and grad_sink is not None
         ctx.need_skin = skin_wts is not None and skin_wts.requires_grad
         ctx.shapes = [None if v is None else v.shape for v in (xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts)]
         return posed_xyz, cov6, colors, opacity
@@ -104,20 +105,27 @@ class _PoseGaussians(torch.autograd.Function):
             g_fr = new(t[5]) if t[5] is not None else None
         g_skin = torch.empty_like(t[6]) if ctx.need_skin else None
         with torch.cuda.device(dev):
-            _lib.check(L.mb_pose_backward(C.byref(pi), ptr(gin[0]), ptr(gin[1]), ptr(gin[2]), ptr(gin[3]), ptr(g_xyz), ptr(g_ls),
-                                          ptr(g_q), ptr(g_ol), ptr(g_fdc), ptr(g_fr) if g_fr is not None and g_fr.numel() else None,
-                                          ptr(g_skin), torch.cuda.current_stream(dev).cuda_stream), "mb_pose_backward")
+            if sink is not None and sink.get("_wait") is not None:      # ordered accumulation: after the previous view's launch
+                torch.cuda.current_stream(dev).wait_event(sink["_wait"])
+            entry = L.mb_pose_backward_accumulate if ctx.accumulate else L.mb_pose_backward
+            if ctx.accumulate and g_skin is not None:
+                g_skin.zero_()
+            _lib.check(entry(C.byref(pi), ptr(gin[0]), ptr(gin[1]), ptr(gin[2]), ptr(gin[3]), ptr(g_xyz), ptr(g_ls),
+                             ptr(g_q), ptr(g_ol), ptr(g_fdc), ptr(g_fr) if g_fr is not None and g_fr.numel() else None,
+                             ptr(g_skin), torch.cuda.current_stream(dev).cuda_stream), "mb_pose_backward")
+            if sink is not None and sink.get("_record") is not None:
+                sink["_record"].record(torch.cuda.current_stream(dev))
         sh = ctx.shapes
         rs = lambda g, s: None if g is None else g.reshape(s)
         if sink is not None:
-            return (None,) * 6 + (rs(g_skin, sh[6]), None, None, None, None, None, None)
+            return (None,) * 6 + (rs(g_skin, sh[6]), None, None, None, None, None, None, None)
         return (rs(g_xyz, sh[0]), rs(g_ls, sh[1]), rs(g_q, sh[2]), rs(g_ol, sh[3]), rs(g_fdc, sh[4]), rs(g_fr, sh[5]),
-                rs(g_skin, sh[6]), None, None, None, None, None, None)
+                rs(g_skin, sh[6]), None, None, None, None, None, None, None)
 
 
 def pose_gaussians(xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts: Optional[torch.Tensor],
                    bone_tf: Optional[torch.Tensor], campos, sh_degree: int = 3, isotropic: bool = False,
-                   num_skinned: Optional[int] = None, grad_sink: Optional[dict] = None):
+                   num_skinned: Optional[int] = None, grad_sink: Optional[dict] = None, accumulate: bool = False):
     """-> (posed_xyz[N,3], posed_cov6[N,6], colors[N,3], opacity[N,1]).
 
     xyz [N,3], log_scale [N,3] ([N,1] if isotropic), quat [N,4] raw, opacity_logit [N,1], f_dc [N,1,3],
@@ -127,11 +135,15 @@ def pose_gaussians(xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts: 
     grad_sink: optional {"xyz","log_scale","quat","opacity_logit","f_dc","f_rest"} -> dense fp32 tensors; when given, the
     backward kernel OVERWRITES them with the parameter gradients and autograd receives no gradient for those inputs
     (used by the data-parallel step: the sinks are views of the flat all-reduce buffer).
+    accumulate (with grad_sink): the backward kernel ADDS to the sinks instead (gradient accumulation over the views of one
+    step, hand_dynamic.py:248,259-277; bulk TMA reduce-add, no read-modify-write pass).  Views running on different streams
+    order their accumulating launches through two optional entries of grad_sink: "_wait" (a torch.cuda.Event the backward
+    launch waits for) and "_record" (an event recorded right after it).
     """
     if num_skinned is None:
         num_skinned = 0 if skin_wts is None else skin_wts.shape[0]
     return _PoseGaussians.apply(xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, bone_tf, campos, int(sh_degree),
-                                bool(isotropic), int(num_skinned), grad_sink)
+                                bool(isotropic), int(num_skinned), grad_sink, bool(accumulate))
 
 
 def sh_grad_from_views(xyz, skin_wts, num_skinned, sh_degree, sh_coeffs, bone_tf_all, campos_all, g_f_dc_all, out_f_dc, out_f_rest):

@@ -135,8 +135,9 @@ def _make_inputs(settings: GaussianRasterizationSettings, means3D, opacities, co
 
 
 def rasterize_forward(settings: GaussianRasterizationSettings, means3D, opacities, colors_precomp=None, shs=None,
-                      cov3D_precomp=None, scales=None, rotations=None, capacity: Optional[int] = None):
-    """-> (color[3,H,W], radii[N], RasterState).  Inputs must already be dense fp32 CUDA tensors (or None)."""
+                      cov3D_precomp=None, scales=None, rotations=None, capacity: Optional[int] = None, exact: bool = False):
+    """-> (color[3,H,W], radii[N], RasterState).  Inputs must already be dense fp32 CUDA tensors (or None).
+    exact=True: size the instance buffers from this frame's own num_rendered (one host read) whatever the capacity mode."""
     L = _lib.lib()
     if not means3D.is_cuda:
         raise _lib.ManusB200Error("manus_b200 rasterizer needs CUDA tensors (there is no CPU path)")
@@ -152,7 +153,7 @@ def rasterize_forward(settings: GaussianRasterizationSettings, means3D, opacitie
         st.radii = torch.empty(N, dtype=torch.int32, device=dev)
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         st.key = (dev.index, N, H, W)
-        reserve = capacity is None and _Plan.mode == "reserve" and st.key in _Plan.high_water
+        reserve = capacity is None and not exact and _Plan.mode == "reserve" and st.key in _Plan.high_water
         # reserve mode: nothing is read back per frame (the frame can be captured in a CUDA graph); an overflow is
         # recorded in the device counters and raised by check_overflow() / raster_query()
         st.host_count = None if reserve else torch.zeros(1, dtype=torch.int64).pin_memory()
@@ -281,6 +282,71 @@ class GaussianRasterizer(nn.Module):
                                    empty if colors_precomp is None else colors_precomp, opacities,
                                    empty if scales is None else scales, empty if rotations is None else rotations,
                                    empty if cov3D_precomp is None else cov3D_precomp, self.raster_settings)
+
+
+# ---- the function-level surface of upstream's pybind11 module ``diff_gaussian_rasterization._C`` ----
+
+def _state_from_buffers(settings, means3D, colors, sh, cov3D_precomp, scales, rotations, radii, geom, binning, image, num_rendered):
+    d = _dense
+    st = RasterState()
+    m3 = d(means3D)
+    st.keep = [m3, d(colors), d(sh), d(cov3D_precomp), d(scales), d(rotations)]
+    st.inputs = _make_inputs(settings, m3, None, st.keep[1], st.keep[2], st.keep[3], st.keep[4], st.keep[5], st.keep)
+    st.geom, st.binning, st.image, st.radii = geom, binning, image, radii
+    st.capacity = st.num_rendered = int(num_rendered)
+    st.host_count, st.event, st.key = None, None, None
+    return st
+
+
+def _c_settings(bg, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, degree, campos, debug):
+    return GaussianRasterizationSettings(int(image_height), int(image_width), float(tan_fovx), float(tan_fovy), bg, float(scale_modifier),
+                                         viewmatrix, projmatrix, int(degree), campos, False, bool(debug))
+
+
+def c_rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                          projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos, prefiltered, debug):
+    """``_C.rasterize_gaussians`` with upstream's positional signature and return value
+    (num_rendered, out_color[3,H,W], radii[N] int32, geomBuffer u8, binningBuffer u8, imgBuffer u8); absent tensors are passed
+    as empty tensors like upstream's Python wrapper does.  The three byte buffers are this library's opaque state."""
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    settings = _c_settings(background, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, degree,
+                           campos, debug)
+    d = _dense
+    if means3D.shape[0] == 0:
+        dev = means3D.device
+        u8 = torch.empty(0, dtype=torch.uint8, device=dev)
+        color = background.to(dev).float().reshape(3, 1, 1).expand(3, int(image_height), int(image_width)).contiguous()
+        return 0, color, torch.zeros(0, dtype=torch.int32, device=dev), u8, u8.clone(), u8.clone()
+    color, radii, st = rasterize_forward(settings, d(means3D), d(opacity).reshape(-1), d(colors), d(sh), d(cov3D_precomp), d(scales),
+                                         d(rotations), exact=True)      # capacity == num_rendered: the backward re-derives the layout from R
+    return st.resolve(), color, radii, st.geom, st.binning, st.image
+
+
+def c_rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
+                                   projmatrix, tan_fovx, tan_fovy, dL_dout_color, sh, degree, campos, geomBuffer, R, binningBuffer,
+                                   imageBuffer, debug):
+    """``_C.rasterize_gaussians_backward`` with upstream's positional signature and its 8-tuple
+    (dL_dmeans2D[N,3], dL_dcolors[N,3], dL_dopacity[N,1], dL_dmeans3D[N,3], dL_dcov3D[N,6], dL_dsh[N,M,3], dL_dscales[N,3],
+    dL_drotations[N,4]); gradients of absent inputs come back as zeros of upstream's shapes."""
+    N, dev = means3D.shape[0], means3D.device
+    H, W = int(dL_dout_color.shape[-2]), int(dL_dout_color.shape[-1])
+    M = 0 if sh is None or sh.numel() == 0 else int(sh.shape[1])
+    z = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+    if N == 0 or R == 0 and geomBuffer.numel() == 0:
+        return z(N, 3), z(N, 3), z(N, 1), z(N, 3), z(N, 6), z(N, M, 3), z(N, 3), z(N, 4)
+    settings = _c_settings(background, scale_modifier, viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, degree, campos, debug)
+    st = _state_from_buffers(settings, means3D, colors, sh, cov3D_precomp, scales, rotations, radii, geomBuffer, binningBuffer,
+                             imageBuffer, R)
+    g2d, gcol, gop, g3d, gcov, gsh, gsc, grot = rasterize_backward(st, dL_dout_color)
+    return (g2d, gcol, gop.reshape(N, 1), g3d, gcov, gsh if gsh is not None else z(N, M, 3), gsc if gsc is not None else z(N, 3),
+            grot if grot is not None else z(N, 4))
+
+
+def c_mark_visible(means3D, viewmatrix, projmatrix):
+    """``_C.mark_visible(means3D, viewmatrix, projmatrix) -> bool[N]``."""
+    rs = GaussianRasterizationSettings(0, 0, 1.0, 1.0, None, 1.0, viewmatrix, projmatrix, 0, None, False, False)
+    return GaussianRasterizer(rs).markVisible(means3D)
 
 
 def debug_views(st: RasterState):

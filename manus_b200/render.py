@@ -111,14 +111,15 @@ def render_gaussians(posed_means, posed_cov, cano_means, cano_features, cano_opa
     return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii}
 
 
-def render_fused(params, skin_wts, bone_tf, camera, bg_color, sh_degree=3, isotropic=False, num_skinned=None, grad_sink=None):
+def render_fused(params, skin_wts, bone_tf, camera, bg_color, sh_degree=3, isotropic=False, num_skinned=None, grad_sink=None,
+                 accumulate=False):
     """params: (xyz, log_scale, quat, opacity_logit, f_dc, f_rest) -- the six nn.Parameters of GaussianModel.
     Returns the render_gaussians dict plus the posed quantities (what TrainingModule.forward returns)."""
     xyz, log_scale, quat, opacity_logit, f_dc, f_rest = params
     device = xyz.device
     campos = torch.as_tensor(camera.camera_center).to(device)
     posed_xyz, posed_cov, colors, opacity = pose_gaussians(xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, bone_tf,
-                                                          campos, sh_degree, isotropic, num_skinned, grad_sink)
+                                                          campos, sh_degree, isotropic, num_skinned, grad_sink, accumulate)
     out = render_gaussians(posed_xyz, posed_cov, xyz, None, opacity, camera, bg_color, colors_precomp=colors,
                            sh_degree=sh_degree, device=device, _cached_screenspace=True)
     out.update(posed_xyz=posed_xyz, posed_cov=posed_cov, colors=colors, cano_opacity=opacity)

@@ -88,3 +88,26 @@ def test_rasterizer_argument_errors_match_upstream():
         r(z, z, torch.ones(2, 1), colors_precomp=z)
     assert GaussianRasterizationSettings._fields == ("image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier",
                                                      "viewmatrix", "projmatrix", "sh_degree", "campos", "prefiltered", "debug")
+
+
+def test_shims_expose_the_upstream_module_surface():
+    """What MANUS imports (gaussian_utils.py:18-21, gaussian.py:4) plus the function-level ``_C`` surface of SURVEY.md 8b, with
+    upstream's positional parameter order."""
+    import inspect
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "shims"))
+    try:
+        import diff_gaussian_rasterization as dgr
+        from simple_knn._C import distCUDA2  # noqa: F401
+    finally:
+        sys.path.pop(0)
+    assert dgr.GaussianRasterizationSettings._fields[0] == "image_height" and callable(dgr.GaussianRasterizer)
+    fwd = list(inspect.signature(dgr._C.rasterize_gaussians).parameters)
+    assert fwd == ["background", "means3D", "colors", "opacity", "scales", "rotations", "scale_modifier", "cov3D_precomp", "viewmatrix",
+                   "projmatrix", "tan_fovx", "tan_fovy", "image_height", "image_width", "sh", "degree", "campos", "prefiltered", "debug"]
+    bwd = list(inspect.signature(dgr._C.rasterize_gaussians_backward).parameters)
+    assert bwd == ["background", "means3D", "radii", "colors", "scales", "rotations", "scale_modifier", "cov3D_precomp", "viewmatrix",
+                   "projmatrix", "tan_fovx", "tan_fovy", "dL_dout_color", "sh", "degree", "campos", "geomBuffer", "R", "binningBuffer",
+                   "imageBuffer", "debug"]
+    assert list(inspect.signature(dgr._C.mark_visible).parameters) == ["means3D", "viewmatrix", "projmatrix"]

@@ -75,3 +75,65 @@ def test_graph_replay_equals_eager_step(built_lib):
             assert ok, (view, e, s)
     finally:
         rz.set_capacity_mode("exact")
+
+
+def test_accumulating_pose_backward_adds_to_the_sink(built_lib):
+    """mb_pose_backward_accumulate (TMA reduce-add): sink_after = sink_before + gradient, also across the ragged last tile and
+    the skinned / static boundary (runs that are not 16-byte sized take the atomicAdd path)."""
+    scene, r = _renderer(n=6007)
+    dev = r.device
+    G = torch.rand(r.H, r.W, 3, generator=torch.Generator().manual_seed(3)).to(dev)
+    _, c, b = r.view_inputs_host(7)
+    c, b = c.to(dev), b.to(dev)
+    (r.render(7, sink=r.flat.grads, cam_dev=c, bones_dev=b)["render"] * G).sum().backward()
+    g = r.flat.grad.clone()
+    base = torch.randn_like(g) * g.abs().mean()
+    r.flat.grad.copy_(base)
+    (r.render(7, sink=r.flat.grads, cam_dev=c, bones_dev=b, accumulate=True)["render"] * G).sum().backward()
+    ok, e, s = grad_close((r.flat.grad - base).cpu().numpy(), g.cpu().numpy(), 2e-6)
+    assert ok, (e, s)
+    assert float(g.abs().max()) > 0
+
+
+@pytest.mark.parametrize("V,ordered", [(2, False), (3, False), (3, True)])
+def test_views_in_flight_sum_the_single_view_gradients(built_lib, V, ordered):
+    """GraphedStep(views_in_flight=V): V views captured on V streams of one graph; flat.grad = sum of the views' gradients
+    (reference: gradient accumulation over accum_iter views, hand_dynamic.py:248,259-277), loss = sum of the views' losses."""
+    from manus_b200 import rasterizer as rz
+    from manus_b200.dist import GraphedStep
+
+    scene, r = _renderer()
+    H, W, dev = r.H, r.W, r.device
+    targets = [torch.rand(H, W, 3, generator=torch.Generator().manual_seed(20 + i)).to(dev) for i in range(3)]
+    loss_fn = lambda image, target: (image * target).sum()
+    views = (7, 11, 2)
+    rz.set_capacity_mode("exact")
+    try:
+        eager, dmax = [], 0
+        for i, view in enumerate(views):
+            _, c, b = r.view_inputs_host(view)
+            out = r.render(view, sink=r.flat.grads, cam_dev=c.to(dev), bones_dev=b.to(dev))
+            loss = loss_fn(out["render"], targets[i])
+            loss.backward()
+            eager.append((float(loss.detach()), r.flat.grad.clone(), int(rz.check_overflow())))
+            dmax = max(dmax, eager[-1][2])
+        rz.set_capacity_mode("reserve", margin=1.2)
+        rz.reserve_capacity(dev.index, scene.n, H, W, dmax)
+        step = GraphedStep(r, loss_fn, targets[0], view=2, views_in_flight=V, ordered=ordered)
+        for rep in range(3):                                    # replays are repeatable (the buffer is cleared / overwritten)
+            order = [(rep + i) % 3 for i in range(V)]
+            for slot, k in enumerate(order):
+                _, c, b = r.view_inputs_host(views[k])
+                step.set_inputs(c.to(dev), b.to(dev), targets[k], slot=slot)
+            loss = step.replay()
+            torch.cuda.synchronize()
+            assert step.check() == sum(eager[k][2] for k in order)
+            want_loss = sum(eager[k][0] for k in order)
+            assert abs(float(loss) - want_loss) <= 2e-6 * abs(want_loss)
+            want = sum(eager[k][1] for k in order)
+            ok, e, s = grad_close(r.flat.grad.cpu().numpy(), want.cpu().numpy())
+            assert ok, (V, rep, e, s)
+            for slot, k in enumerate(order):
+                assert abs(float(step.losses[slot]) - eager[k][0]) <= 1e-6 * abs(eager[k][0])
+    finally:
+        rz.set_capacity_mode("exact")

@@ -242,6 +242,55 @@ def test_module_interface_like_manus_calls_it(built_lib, raster_ref):
     np.testing.assert_array_equal(vis.cpu().numpy(), raster_ref.mark_visible(ps["means3D"], cam.world_view_transform, cam.full_proj_transform))
 
 
+def test_function_level_C_surface_matches_the_module(built_lib):
+    """shims/diff_gaussian_rasterization/_C.py: upstream's rasterize_gaussians / rasterize_gaussians_backward / mark_visible
+    signatures and return tuples, same numbers as the autograd module; both colour / covariance modes."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "shims"))
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer, _C
+
+    sc, cam, ps = small_scene(5, N=2500)
+    tg = lambda a: torch.tensor(np.ascontiguousarray(a), device=DEV)
+    empty = torch.empty(0, device=DEV)
+    bg, view, proj, campos = tg(np.ones(3, np.float32)), tg(cam.world_view_transform), tg(cam.full_proj_transform), tg(cam.camera_center)
+    means, op = tg(ps["means3D"]), tg(ps["opacity"])
+    shs = tg(np.concatenate([sc.f_dc, sc.f_rest], 1).astype(np.float32))
+    scales, rots = tg(np.exp(sc.log_scale + 0.3).astype(np.float32)), tg(sc.quat / np.linalg.norm(sc.quat, axis=1, keepdims=True))
+    G = torch.rand(3, cam.height, cam.width, generator=torch.Generator().manual_seed(2)).to(DEV)
+    for mode in ("precomp", "sh_scale_rot"):
+        if mode == "precomp":
+            kw = dict(colors_precomp=tg(ps["colors"]), cov3D_precomp=tg(ps["cov3D"]))
+        else:
+            kw = dict(shs=shs, scales=scales, rotations=rots)
+        col, cov = kw.get("colors_precomp", empty), kw.get("cov3D_precomp", empty)
+        sh, sca, rot = kw.get("shs", empty), kw.get("scales", empty), kw.get("rotations", empty)
+        R, color, radii, geom, binning, img = _C.rasterize_gaussians(bg, means, col, op, sca, rot, 1.0, cov, view, proj, cam.tanfovx,
+                                                                     cam.tanfovy, cam.height, cam.width, sh, 3, campos, False, False)
+        assert isinstance(R, int) and R > 0 and geom.dtype == binning.dtype == img.dtype == torch.uint8
+        grads = _C.rasterize_gaussians_backward(bg, means, radii, col, sca, rot, 1.0, cov, view, proj, cam.tanfovx, cam.tanfovy, G,
+                                                sh, 3, campos, geom, R, binning, img, False)
+        assert [tuple(g.shape) for g in grads] == [(sc.n, 3), (sc.n, 3), (sc.n, 1), (sc.n, 3), (sc.n, 6),
+                                                   (sc.n, 16 if mode != "precomp" else 0, 3), (sc.n, 3), (sc.n, 4)]
+        rs = GaussianRasterizationSettings(cam.height, cam.width, cam.tanfovx, cam.tanfovy, bg, 1.0, view, proj, 3, campos, False, False)
+        leaves = {k: v.clone().requires_grad_(True) for k, v in kw.items()}
+        m3, m2, o = means.clone().requires_grad_(True), torch.zeros_like(means, requires_grad=True), op.clone().requires_grad_(True)
+        img2, radii2 = GaussianRasterizer(rs)(means3D=m3, means2D=m2, opacities=o, **leaves)
+        (img2 * G).sum().backward()
+        assert torch.equal(color, img2.detach()) and torch.equal(radii, radii2)
+        pairs = [(grads[0], m2.grad), (grads[2], o.grad), (grads[3], m3.grad)]
+        if mode == "precomp":
+            pairs += [(grads[1], leaves["colors_precomp"].grad), (grads[4], leaves["cov3D_precomp"].grad)]
+        else:
+            pairs += [(grads[5], leaves["shs"].grad), (grads[6], leaves["scales"].grad), (grads[7], leaves["rotations"].grad)]
+        for got, want in pairs:
+            ok_, e, s = grad_close(got.cpu().numpy(), want.cpu().numpy())
+            assert ok_, (mode, e, s)
+    vis = _C.mark_visible(means, view, proj)
+    M = np.asarray(cam.world_view_transform, np.float32)
+    assert vis.dtype == torch.bool and vis.shape == (sc.n,)
+    np.testing.assert_array_equal(vis.cpu().numpy(), ps["means3D"] @ M[:3, 2] + M[3, 2] > 0.2)
+
+
 def test_capacity_overflow_is_detected(built_lib):
     from manus_b200 import _lib
     from manus_b200.rasterizer import raster_query
