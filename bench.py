@@ -311,7 +311,7 @@ def main():
     r = SceneRenderer(scene, dev, W, H)
     n_hand, n_obj = scene.n_hand, scene.n - scene.n_hand
     views = list(range(args.views))
-    VIF = 1 if args.no_graph else max(1, args.views_in_flight)
+    VIF = max(1, args.views_in_flight)      # with --no-graph the views of a step are enqueued one after the other
     my_view = lambda it, slot=0: views[((it * VIF + slot) * world + rank) % len(views)]
     G_host = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(7)).pin_memory()
     G_dev = G_host.to(dev)

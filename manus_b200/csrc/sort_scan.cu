@@ -82,6 +82,19 @@ __global__ void __launch_bounds__(kSortThreads, MB_SORT_MINBLOCKS) radix_pass_ke
     if (chunk >= nchunks) return;
     const int64_t chunk_base = chunk * kSortChunk;
     const int nvalid = (int)(n - chunk_base < kSortChunk ? n - chunk_base : kSortChunk);
+    // every key has the same digit (e.g. the exponent byte of the depths of one hand-sized scene): the stable pass is the
+    // identity -- copy the chunk, no ranking and no look-back
+    if (__syncthreads_or(hist[tid] == (uint32_t)n)) {
+#pragma unroll
+        for (int r = 0; r < kSortItems; ++r) {
+            const int e = r * kSortThreads + tid;
+            if (e < nvalid) {
+                if (keys_out) keys_out[chunk_base + e] = keys_in[chunk_base + e];
+                vals_out[chunk_base + e] = vals_in[chunk_base + e];
+            }
+        }
+        return;
+    }
     // stable rank of every key among the keys of its warp's 512-element slice with the same digit
     const int wbase = warp * (32 * kSortItems);
     uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];

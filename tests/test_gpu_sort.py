@@ -61,3 +61,22 @@ def test_sort_float_depth_keys(built_lib):
     ko, vo = run_sort(built_lib, torch.tensor(k.view(np.int32), device="cuda"), torch.arange(d.size, dtype=torch.int32, device="cuda"), 32)
     assert np.all(np.diff(ko.view(np.float32)) >= 0)
     np.testing.assert_array_equal(vo, np.argsort(d, kind="stable").astype(np.uint32))
+
+
+@pytest.mark.parametrize("n", [4097, 70_001])
+def test_sort_with_constant_digits(built_lib, n):
+    """Passes whose digit is the same for every key (the exponent byte of the depths of a hand-sized scene) take the
+    identity fast path; a pass that is constant except for ONE key must not."""
+    rng = np.random.default_rng(n)
+    v = np.arange(n, dtype=np.uint32)
+    for keys in ((np.uint32(0x3F) << 24) | rng.integers(0, 1 << 16, n).astype(np.uint32),         # digits 2 and 3 constant
+                 rng.uniform(1.0, 1.9, n).astype(np.float32).view(np.uint32),                     # digit 3 constant
+                 np.full(n, 0x12345678, np.uint32)):                                               # everything constant
+        for odd in (False, True):
+            k = keys.copy()
+            if odd:
+                k[n // 2] = 0xFFFFFFFF                   # a culled Gaussian's key
+            ko, vo = run_sort(built_lib, torch.tensor(k.view(np.int32), device="cuda"), torch.tensor(v.view(np.int32), device="cuda"), 32)
+            order = np.argsort(k, kind="stable")
+            np.testing.assert_array_equal(ko, k[order])
+            np.testing.assert_array_equal(vo, v[order])
