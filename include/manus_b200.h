@@ -116,6 +116,14 @@ int mb_raster_backward(const mb_raster_inputs *in, const int32_t *radii, const v
                        float *dL_dsh /*[P,M,3]*/, float *dL_dscales /*[P,3]*/, float *dL_drotations /*[P,4]*/,
                        mb_stream_t stream);
 
+/* The tile half of the backward only: fills grad_scratch with one 12-float accumulator row per Gaussian (dL/d(screen xy) 2 |
+ * dL/dconic 3 | dL/dopacity 1 | dL/dcolour 3 | 3 unused).  mb_pose_backward_from_raster consumes the rows: on the fused path the
+ * projection backward runs inside the pose backward kernel and dL_dmeans3D / dL_dcov3D / dL_dcolors / dL_dopacity never touch
+ * HBM. */
+int mb_raster_backward_blend(const mb_raster_inputs *in, const int32_t *radii, const void *geom, const void *binning,
+                             int64_t capacity, const void *image_buf, const float *dL_dout, int64_t stride_c, int64_t stride_y,
+                             int64_t stride_x, void *grad_scratch, size_t scratch_bytes, mb_stream_t stream);
+
 /* Diagnostics for tests: byte offsets of named arrays inside the opaque buffers of a forward with these sizes.
  * out[0..3]: image buffer -> final_T f32[H*W], n_contrib u32[H*W], tile ranges u32[tiles][2], deepest last contributor u32[tiles];
  * out[4..5]: binning buffer -> gaussian id per sorted instance u32[num_rendered], tile id per sorted instance u32[num_rendered];
@@ -159,6 +167,16 @@ int mb_pose_forward(const mb_pose_inputs *in, float *posed_xyz /*[N,3]*/, float 
 int mb_pose_backward(const mb_pose_inputs *in, const float *g_posed_xyz, const float *g_posed_cov6, const float *g_colors,
                      const float *g_opacity, float *g_xyz, float *g_log_scale, float *g_quat, float *g_opacity_logit,
                      float *g_f_dc, float *g_f_rest, float *g_skin_wts, mb_stream_t stream);
+
+/* Pose backward fused with the rasterizer's projection backward (the part of RasterizeGaussiansBackwardCUDA after the tile
+ * pass): `raster` is the mb_raster_inputs of the forward that rendered THIS pose's outputs
+ * (colors_precomp / cov3D_precomp mode, scale_modifier 1), radii its radii, grad_scratch the rows written by
+ * mb_raster_backward_blend.  Writes dL_dmeans2D [N,3] (the screen-space gradient MANUS's densification reads,
+ * src/models/gaussian.py:335-338) and the parameter gradients; accumulate != 0 adds to them like mb_pose_backward_accumulate. */
+int mb_pose_backward_from_raster(const mb_pose_inputs *in, const struct mb_raster_inputs *raster, const int32_t *radii,
+                                 const void *grad_scratch, float *dL_dmeans2D, float *g_xyz, float *g_log_scale, float *g_quat,
+                                 float *g_opacity_logit, float *g_f_dc, float *g_f_rest, float *g_skin_wts, int32_t accumulate,
+                                 mb_stream_t stream);
 
 /* Same, but the gradients are ADDED to the output buffers (bulk TMA reduce-add, fp32 adds resolved in L2): gradient
  * accumulation over the views of one optimisation step -- the reference's accum_iter loop, src/modules/hand_dynamic.py:248,

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "project_bwd.cuh"
 
 namespace mb {
 
@@ -37,7 +38,19 @@ struct PoseArgs {
     const float *g_posed_xyz, *g_cov6, *g_colors, *g_opacity;
     float *g_xyz, *g_log_scale, *g_quat, *g_opacity_logit, *g_f_dc, *g_f_rest, *g_skin;
     int accumulate;   // backward: add the gradients to the output buffers (bulk TMA reduce-add) instead of overwriting them
+    // backward fused with the rasterizer's projection backward (mb_pose_backward_from_raster): the upstream gradients are
+    // derived in the kernel from the blend backward's accumulator rows instead of being read from the four g_* arrays
+    const float *acc;          // [N,12]: dL/d(mean2D xy), dL/dconic xyz, dL/dopacity, dL/dcolour rgb, 3 unused; nullptr = not fused
+    const int32_t *radii;      // [N]
+    const float *view, *proj;  // [16] each
+    const float *tanfov_dev;   // optional [2] in device memory (replaces tanx / tany)
+    float tanx, tany;
+    int W, H;
+    float *g_means2D;          // [N,3] out: (acc[0], acc[1], 0)
 };
+
+constexpr int kAccRow = 12;          // floats per accumulator row (kAccStride of raster_blend.cu)
+constexpr int kCamFloats = 40;       // view 16 | proj 16 | tanx, tany, focx, focy | pad (fused backward only)
 
 // Shared-memory image of one tile of kPoseThreads Gaussians (offsets in floats, every array 16-B aligned).  Rows are
 // dense: the wide rows have odd word counts in the shipped configurations (45 = 15 SH coefficients x 3, 21 bones), so
@@ -67,8 +80,8 @@ __host__ __device__ inline TileLayout tile_layout(int K, int B, int iso, bool ba
 }
 
 inline size_t pose_smem_bytes(int B, int K, int iso, bool backward) {
-    // bones (13 floats each) + camera + 2 mbarriers, then the tile stage
-    return sizeof(float) * ((size_t)kMaxBones * 13 + 8) + sizeof(float) * (size_t)tile_layout(K, B, iso, backward).floats;
+    // bones (13 floats each) + camera centre + 2 mbarriers + camera matrices, then the tile stage
+    return sizeof(float) * ((size_t)kMaxBones * 13 + 8 + kCamFloats) + sizeof(float) * (size_t)tile_layout(K, B, iso, backward).floats;
 }
 
 struct Transfer {   // one dense array of a tile: global <-> shared
@@ -182,7 +195,7 @@ __device__ __forceinline__ float view_dir(const PoseLocal &p, const float *cam, 
 // tile is brought in by a handful of 1-D bulk (TMA) copies into the stage that is not being computed on, and written
 // back the same way; runs that are not 16-B sized / aligned (last tile, skinned/static boundary, odd tensor offsets) take
 // a cooperative load / store path through the same shared-memory image.
-template <bool kBackward>
+template <bool kBackward, bool kFused = false>
 struct TilePipe {
     const PoseArgs &a;
     TileLayout L;
@@ -203,7 +216,12 @@ struct TilePipe {
         t[n++] = {a.quat + (size_t)base * 4, L.quat, (uint32_t)(cnt * 16)};
         t[n++] = {a.opacity_logit + base, L.opac, (uint32_t)(cnt * 4)};
         t[n++] = {a.f_dc + (size_t)base * 3, L.fdc, (uint32_t)(cnt * 12)};
-        if (kBackward) {
+        if (kBackward && kFused) {
+            // fused with the rasterizer: the tile's accumulator rows (12 floats each) and radii land in the region of the four
+            // upstream-gradient arrays (13 floats per Gaussian) and are transposed in place (run_tiles)
+            t[n++] = {a.acc + (size_t)base * kAccRow, L.gpx, (uint32_t)(cnt * kAccRow * 4)};
+            t[n++] = {reinterpret_cast<const float *>(a.radii) + base, L.gpx + kPoseThreads * kAccRow, (uint32_t)(cnt * 4)};
+        } else if (kBackward) {
             t[n++] = {a.g_posed_xyz + (size_t)base * 3, L.gpx, (uint32_t)(cnt * 12)};
             t[n++] = {a.g_cov6 + (size_t)base * 6, L.gcov, (uint32_t)(cnt * 24)};
             t[n++] = {a.g_colors + (size_t)base * 3, L.gcol, (uint32_t)(cnt * 12)};
@@ -296,11 +314,21 @@ struct TilePipe {
     }
 };
 
-template <bool kBackward, typename Body>
+template <bool kBackward, bool kFused = false, typename Body>
 __device__ __forceinline__ void run_tiles(const PoseArgs &a, float *smem, Body body) {
     float *bones_s = smem, *cam_s = bones_s + kMaxBones * 13;
     uint64_t *bar = reinterpret_cast<uint64_t *>(cam_s + 4);
-    TilePipe<kBackward> pipe{a, tile_layout(a.K, a.B, a.iso, kBackward), cam_s + 8, bar};
+    float *rcam_s = cam_s + 8;      // fused backward: view | proj | tanx, tany, focx, focy
+    TilePipe<kBackward, kFused> pipe{a, tile_layout(a.K, a.B, a.iso, kBackward), rcam_s + kCamFloats, bar};
+    if (kBackward && kFused) {
+        if (threadIdx.x < 16) rcam_s[threadIdx.x] = a.view[threadIdx.x];
+        else if (threadIdx.x < 32) rcam_s[threadIdx.x] = a.proj[threadIdx.x - 16];
+        else if (threadIdx.x == 32) {
+            const float tx = a.tanfov_dev ? a.tanfov_dev[0] : a.tanx, ty = a.tanfov_dev ? a.tanfov_dev[1] : a.tany;
+            rcam_s[32] = tx; rcam_s[33] = ty;
+            rcam_s[34] = a.W / (2.0f * tx); rcam_s[35] = a.H / (2.0f * ty);
+        }
+    }
     for (int j = threadIdx.x; j < a.B * 13; j += kPoseThreads) {
         const int b = j / 13, e = j - 13 * b;
         bones_s[j] = a.bone_tf[16 * b + (e < 12 ? e : 15)];
@@ -324,6 +352,25 @@ __device__ __forceinline__ void run_tiles(const PoseArgs &a, float *smem, Body b
         __syncthreads();
         pipe.acquire(tile, 0, phase);
         const int row = threadIdx.x, i = tile * kPoseThreads + row;
+        if (kBackward && kFused) {
+            // rows of the accumulator (array of structures) -> the per-array slots the body reads: every thread takes its
+            // row into registers, then writes (mean2D grad xy, radius | conic grad | colour grad | opacity grad)
+            float *st = pipe.stage(0);
+            float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+            int rad = 0;
+            if (i < a.N) {
+                const float4 *rp = reinterpret_cast<const float4 *>(st + pipe.L.gpx + kAccRow * row);
+                r0 = rp[0]; r1 = rp[1]; r2 = rp[2];
+                rad = reinterpret_cast<const int *>(st + pipe.L.gpx + kPoseThreads * kAccRow)[row];
+            }
+            __syncthreads();
+            if (i < a.N) {
+                st[pipe.L.gpx + 3 * row] = r0.x; st[pipe.L.gpx + 3 * row + 1] = r0.y; st[pipe.L.gpx + 3 * row + 2] = __int_as_float(rad);
+                st[pipe.L.gcov + 6 * row] = r0.z; st[pipe.L.gcov + 6 * row + 1] = r0.w; st[pipe.L.gcov + 6 * row + 2] = r1.x;
+                st[pipe.L.gop + row] = r1.y;
+                st[pipe.L.gcol + 3 * row] = r1.z; st[pipe.L.gcol + 3 * row + 1] = r1.w; st[pipe.L.gcol + 3 * row + 2] = r2.x;
+            }
+        }
 #ifndef MB_POSE_NOCOMPUTE   // experiment switch (tools/pose_bench.py): data movement only
         if (i < a.N) body(pipe.L, pipe.stage(0), i, row, bones_s, cam_s);
 #endif
@@ -397,18 +444,54 @@ __global__ void __launch_bounds__(kPoseThreads) pose_forward_kernel(PoseArgs a) 
     });
 }
 
-template <int DEG>
-__global__ void __launch_bounds__(kPoseThreads) pose_backward_kernel(PoseArgs a) {
+// kFused: upstream gradients from the rasterizer's accumulator rows (mb_pose_backward_from_raster)
+template <int DEG, bool kFused>
+__global__ void __launch_bounds__(kPoseThreads, kFused ? 4 : 1) pose_backward_kernel(PoseArgs a) {
     extern __shared__ __align__(128) float smem[];
     constexpr int nb = (DEG + 1) * (DEG + 1);
-    run_tiles<true>(a, smem, [&](const TileLayout &L, float *st, int i, int row, const float *bones_s, const float *cam_s) {
+    run_tiles<true, kFused>(a, smem, [&](const TileLayout &L, float *st, int i, int row, const float *bones_s, const float *cam_s) {
         PoseLocal p;
         pose_common(a, L, st, i, row, bones_s, p);
         float gx[3] = {0.f, 0.f, 0.f}, dA[9], dt[3] = {0.f, 0.f, 0.f}, ds = 0.f;
 #pragma unroll
         for (int k = 0; k < 9; ++k) dA[k] = 0.f;
+        float Bm[9], dB[9], dL[9];
+        if (p.skinned) mat3_mul(p.A, p.L, Bm);
+        else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) Bm[k] = p.L[k];
+        }
+        // upstream gradients of the posed mean and covariance: from the rasterizer's arrays, or (fused) from its accumulator row
+        float gp[3], g6[6];
+        if (kFused) {
+            const float g2x = st[L.gpx + 3 * row], g2y = st[L.gpx + 3 * row + 1];
+            const int rad = __float_as_int(st[L.gpx + 3 * row + 2]);
+            gp[0] = gp[1] = gp[2] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) g6[k] = 0.f;
+            if (rad > 0) {
+                // the posed mean and covariance exactly as pose_forward_kernel wrote them for the rasterizer's forward
+                float pm[3], c6[6];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) pm[r] = p.A[3 * r] * p.x[0] + p.A[3 * r + 1] * p.x[1] + p.A[3 * r + 2] * p.x[2] + p.t[r];
+                c6[0] = Bm[0] * Bm[0] + Bm[1] * Bm[1] + Bm[2] * Bm[2];
+                c6[1] = Bm[0] * Bm[3] + Bm[1] * Bm[4] + Bm[2] * Bm[5];
+                c6[2] = Bm[0] * Bm[6] + Bm[1] * Bm[7] + Bm[2] * Bm[8];
+                c6[3] = Bm[3] * Bm[3] + Bm[4] * Bm[4] + Bm[5] * Bm[5];
+                c6[4] = Bm[3] * Bm[6] + Bm[4] * Bm[7] + Bm[5] * Bm[8];
+                c6[5] = Bm[6] * Bm[6] + Bm[7] * Bm[7] + Bm[8] * Bm[8];
+                const float *rc = cam_s + 8;
+                project_backward(rc, rc + 16, rc[32], rc[33], rc[34], rc[35], pm[0], pm[1], pm[2], c6, st[L.gcov + 6 * row],
+                                 st[L.gcov + 6 * row + 1], st[L.gcov + 6 * row + 2], g2x, g2y, gp, g6);
+            }
+            a.g_means2D[3 * (size_t)i] = g2x; a.g_means2D[3 * (size_t)i + 1] = g2y; a.g_means2D[3 * (size_t)i + 2] = 0.f;
+        } else {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) gp[r] = st[L.gpx + 3 * row + r];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) g6[k] = st[L.gcov + 6 * row + k];
+        }
         // ---- mean: x' = A x + t
-        const float gp[3] = {st[L.gpx + 3 * row], st[L.gpx + 3 * row + 1], st[L.gpx + 3 * row + 2]};
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             gx[r] = p.A[r] * gp[0] + p.A[3 + r] * gp[1] + p.A[6 + r] * gp[2];
@@ -417,14 +500,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_backward_kernel(PoseArgs a)
             for (int c = 0; c < 3; ++c) dA[3 * r + c] = gp[r] * p.x[c];
         }
         // ---- covariance: Sigma' = Bm Bm^T, Bm = A L ; Gs = symmetrised dL/dSigma'
-        const float *g6 = st + L.gcov + 6 * row;
         const float Gs[9] = {g6[0], 0.5f * g6[1], 0.5f * g6[2], 0.5f * g6[1], g6[3], 0.5f * g6[4], 0.5f * g6[2], 0.5f * g6[4], g6[5]};
-        float Bm[9], dB[9], dL[9];
-        if (p.skinned) mat3_mul(p.A, p.L, Bm);
-        else {
-#pragma unroll
-            for (int k = 0; k < 9; ++k) Bm[k] = p.L[k];
-        }
         mat3_mul(Gs, Bm, dB);
 #pragma unroll
         for (int k = 0; k < 9; ++k) dB[k] *= 2.f;
@@ -684,13 +760,16 @@ static int launch_pose(PoseArgs a, bool backward, cudaStream_t s) {
     MB_CUDA(cudaGetDevice(&dev));
     int &cur = limit[backward ? 1 : 0][dev & 15];
     if (cur < (int)smem) {
-        if (backward) MB_CUDA(cudaFuncSetAttribute(pose_backward_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else MB_CUDA(cudaFuncSetAttribute(pose_forward_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (backward) {
+            MB_CUDA(cudaFuncSetAttribute(pose_backward_kernel<DEG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MB_CUDA(cudaFuncSetAttribute(pose_backward_kernel<DEG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        } else MB_CUDA(cudaFuncSetAttribute(pose_forward_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cur = (int)smem;
     }
     if (backward) {
         KernelTimer kt("pose_backward", s);
-        pose_backward_kernel<DEG><<<grid, kPoseThreads, smem, s>>>(a);
+        if (a.acc) pose_backward_kernel<DEG, true><<<grid, kPoseThreads, smem, s>>>(a);
+        else pose_backward_kernel<DEG, false><<<grid, kPoseThreads, smem, s>>>(a);
     } else {
         KernelTimer kt("pose_forward", s);
         pose_forward_kernel<DEG><<<grid, kPoseThreads, smem, s>>>(a);
@@ -746,6 +825,31 @@ extern "C" int mb_pose_backward(const mb_pose_inputs *in, const float *g_posed_x
                                 float *g_opacity_logit, float *g_f_dc, float *g_f_rest, float *g_skin_wts, mb_stream_t stream) {
     return pose_backward_impl(in, g_posed_xyz, g_posed_cov6, g_colors, g_opacity, g_xyz, g_log_scale, g_quat, g_opacity_logit, g_f_dc,
                               g_f_rest, g_skin_wts, 0, stream);
+}
+
+extern "C" int mb_pose_backward_from_raster(const mb_pose_inputs *in, const mb_raster_inputs *raster, const int32_t *radii,
+                                           const void *grad_scratch, float *dL_dmeans2D, float *g_xyz, float *g_log_scale,
+                                           float *g_quat, float *g_opacity_logit, float *g_f_dc, float *g_f_rest, float *g_skin_wts,
+                                           int32_t accumulate, mb_stream_t stream) {
+    int rc = validate_pose(in, "mb_pose_backward_from_raster");
+    if (rc) return rc;
+    MB_REQUIRE(raster != nullptr && raster->num_points == in->num_points, "mb_pose_backward_from_raster: raster inputs missing or of another size");
+    if (in->num_points == 0) return MB_OK;
+    MB_REQUIRE(raster->viewmatrix && raster->projmatrix && raster->image_width > 0 && raster->image_height > 0 &&
+                   (raster->tanfov_dev || (raster->tanfovx > 0.f && raster->tanfovy > 0.f)),
+               "mb_pose_backward_from_raster: camera missing");
+    MB_REQUIRE(raster->colors_precomp && raster->cov3D_precomp && raster->scale_modifier == 1.0f,
+               "mb_pose_backward_from_raster: the rasterizer must have run on this pose's colours and covariances (scale_modifier 1)");
+    MB_REQUIRE(radii && grad_scratch && dL_dmeans2D, "mb_pose_backward_from_raster: null radii / accumulator / dL_dmeans2D");
+    MB_REQUIRE(g_xyz && g_log_scale && g_quat && g_opacity_logit && g_f_dc, "mb_pose_backward_from_raster: null output");
+    PoseArgs a = pose_args(in);
+    a.g_xyz = g_xyz; a.g_log_scale = g_log_scale; a.g_quat = g_quat; a.g_opacity_logit = g_opacity_logit;
+    a.g_f_dc = g_f_dc; a.g_f_rest = g_f_rest; a.g_skin = g_skin_wts;
+    a.accumulate = accumulate;
+    a.acc = reinterpret_cast<const float *>(grad_scratch); a.radii = radii; a.g_means2D = dL_dmeans2D;
+    a.view = raster->viewmatrix; a.proj = raster->projmatrix; a.tanfov_dev = raster->tanfov_dev;
+    a.tanx = raster->tanfovx; a.tany = raster->tanfovy; a.W = raster->image_width; a.H = raster->image_height;
+    return launch_pose_deg(a, true, (cudaStream_t)stream);
 }
 
 extern "C" int mb_pose_backward_accumulate(const mb_pose_inputs *in, const float *g_posed_xyz, const float *g_posed_cov6,

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 
 #include "raster_state.cuh"
+#include "project_bwd.cuh"
 
 namespace mb {
 
@@ -479,71 +480,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBwdArgs a) 
         const float gx = ac[2], gy = ac[3], gz = ac[4];
         gop = ac[5]; gc[0] = ac[6]; gc[1] = ac[7]; gc[2] = ac[8];
         const float *c6 = a.cov3D + 6 * (size_t)i;
-        // cov2D backward (A.4)
-        const float t0 = v[0] * mx + v[4] * my + v[8] * mz + v[12];
-        const float t1 = v[1] * mx + v[5] * my + v[9] * mz + v[13];
-        const float tz = v[2] * mx + v[6] * my + v[10] * mz + v[14];
-        const float limx = 1.3f * a.tanx, limy = 1.3f * a.tany;
-        const float rx = t0 / tz, ry = t1 / tz;
-        const float xm = (rx < -limx || rx > limx) ? 0.f : 1.f, ym = (ry < -limy || ry > limy) ? 0.f : 1.f;
-        const float tx = fminf(limx, fmaxf(-limx, rx)) * tz, ty = fminf(limy, fmaxf(-limy, ry)) * tz;
-        const float J00 = a.focx / tz, J02 = -(a.focx * tx) / (tz * tz);
-        const float J11 = a.focy / tz, J12 = -(a.focy * ty) / (tz * tz);
-        float M0[3], M1[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            M0[k] = J00 * v[4 * k + 0] + J02 * v[4 * k + 2];
-            M1[k] = J11 * v[4 * k + 1] + J12 * v[4 * k + 2];
-        }
-        const float S[9] = {c6[0], c6[1], c6[2], c6[1], c6[3], c6[4], c6[2], c6[4], c6[5]};
-        float SM0[3], SM1[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            SM0[k] = S[3 * k] * M0[0] + S[3 * k + 1] * M0[1] + S[3 * k + 2] * M0[2];
-            SM1[k] = S[3 * k] * M1[0] + S[3 * k + 1] * M1[1] + S[3 * k + 2] * M1[2];
-        }
-        const float ca = M0[0] * SM0[0] + M0[1] * SM0[1] + M0[2] * SM0[2] + kLowPass;
-        const float cb = M0[0] * SM1[0] + M0[1] * SM1[1] + M0[2] * SM1[2];
-        const float cc = M1[0] * SM1[0] + M1[1] * SM1[1] + M1[2] * SM1[2] + kLowPass;
-        const float denom = ca * cc - cb * cb;
-        const float d2 = 1.0f / (denom * denom + 0.0000001f);
-        float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
-        if (d2 != 0.f) {
-            dL_da = d2 * (-cc * cc * gx + 2.f * cb * cc * gy + (denom - ca * cc) * gz);
-            dL_dc = d2 * (-ca * ca * gz + 2.f * ca * cb * gy + (denom - ca * cc) * gx);
-            dL_db = d2 * 2.f * (cb * cc * gx - (denom + 2.f * cb * cb) * gy + ca * cb * gz);
-            gcov[0] = M0[0] * M0[0] * dL_da + M0[0] * M1[0] * dL_db + M1[0] * M1[0] * dL_dc;
-            gcov[3] = M0[1] * M0[1] * dL_da + M0[1] * M1[1] * dL_db + M1[1] * M1[1] * dL_dc;
-            gcov[5] = M0[2] * M0[2] * dL_da + M0[2] * M1[2] * dL_db + M1[2] * M1[2] * dL_dc;
-            gcov[1] = 2.f * M0[0] * M0[1] * dL_da + (M0[0] * M1[1] + M0[1] * M1[0]) * dL_db + 2.f * M1[0] * M1[1] * dL_dc;
-            gcov[2] = 2.f * M0[0] * M0[2] * dL_da + (M0[0] * M1[2] + M0[2] * M1[0]) * dL_db + 2.f * M1[0] * M1[2] * dL_dc;
-            gcov[4] = 2.f * M0[2] * M0[1] * dL_da + (M0[1] * M1[2] + M0[2] * M1[1]) * dL_db + 2.f * M1[1] * M1[2] * dL_dc;
-        }
-        float dM0[3], dM1[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            dM0[k] = 2.f * SM0[k] * dL_da + SM1[k] * dL_db;
-            dM1[k] = 2.f * SM1[k] * dL_dc + SM0[k] * dL_db;
-        }
-        const float dJ00 = v[0] * dM0[0] + v[4] * dM0[1] + v[8] * dM0[2];
-        const float dJ02 = v[2] * dM0[0] + v[6] * dM0[1] + v[10] * dM0[2];
-        const float dJ11 = v[1] * dM1[0] + v[5] * dM1[1] + v[9] * dM1[2];
-        const float dJ12 = v[2] * dM1[0] + v[6] * dM1[1] + v[10] * dM1[2];
-        const float itz = 1.f / tz, tz2 = itz * itz, tz3 = tz2 * itz;
-        const float dtx = xm * -a.focx * tz2 * dJ02, dty = ym * -a.focy * tz2 * dJ12;
-        const float dtz = -a.focx * tz2 * dJ00 - a.focy * tz2 * dJ11 + (2.f * a.focx * tx) * tz3 * dJ02 + (2.f * a.focy * ty) * tz3 * dJ12;
-        gmean[0] = v[0] * dtx + v[1] * dty + v[2] * dtz;
-        gmean[1] = v[4] * dtx + v[5] * dty + v[6] * dtz;
-        gmean[2] = v[8] * dtx + v[9] * dty + v[10] * dtz;
-        // projection backward
-        const float hx = p[0] * mx + p[4] * my + p[8] * mz + p[12];
-        const float hy = p[1] * mx + p[5] * my + p[9] * mz + p[13];
-        const float hw = p[3] * mx + p[7] * my + p[11] * mz + p[15];
-        const float mw = 1.0f / (hw + 0.0000001f);
-        const float mul1 = hx * mw * mw, mul2 = hy * mw * mw;
-        gmean[0] += (p[0] * mw - p[3] * mul1) * g2x + (p[1] * mw - p[3] * mul2) * g2y;
-        gmean[1] += (p[4] * mw - p[7] * mul1) * g2x + (p[5] * mw - p[7] * mul2) * g2y;
-        gmean[2] += (p[8] * mw - p[11] * mul1) * g2x + (p[9] * mw - p[11] * mul2) * g2y;
+        project_backward(v, p, a.tanx, a.tany, a.focx, a.focy, mx, my, mz, c6, gx, gy, gz, g2x, g2y, gmean, gcov);
 
         if (kSH) {
             float dx = mx - cam[32], dy = my - cam[33], dz = mz - cam[34];
@@ -698,12 +635,12 @@ extern "C" size_t mb_raster_backward_scratch_bytes(int32_t num_points) {
     return align_up((size_t)(num_points > 0 ? num_points : 1) * kAccStride * sizeof(float));
 }
 
-extern "C" int mb_raster_backward(const mb_raster_inputs *in, const int32_t *radii, const void *geom, const void *binning,
-                                  int64_t capacity, const void *image_buf, const float *dL_dout, int64_t stride_c,
-                                  int64_t stride_y, int64_t stride_x, void *grad_scratch, size_t scratch_bytes,
-                                  float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity, float *dL_dmeans3D,
-                                  float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations,
-                                  mb_stream_t stream) {
+static int raster_backward_impl(const mb_raster_inputs *in, const int32_t *radii, const void *geom, const void *binning,
+                                int64_t capacity, const void *image_buf, const float *dL_dout, int64_t stride_c,
+                                int64_t stride_y, int64_t stride_x, void *grad_scratch, size_t scratch_bytes,
+                                float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity, float *dL_dmeans3D,
+                                float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations, bool blend_only,
+                                mb_stream_t stream) {
     // the backward never reads the opacities (they are part of the saved blend records), like upstream's, whose
     // rasterize_gaussians_backward does not take them
     int rc = validate_raster_inputs(in, "mb_raster_backward", false);
@@ -712,9 +649,11 @@ extern "C" int mb_raster_backward(const mb_raster_inputs *in, const int32_t *rad
     const RasterDims d = raster_dims(in);
     if (d.P == 0) return MB_OK;
     MB_REQUIRE(radii && geom && binning && image_buf && dL_dout && grad_scratch, "mb_raster_backward: null buffer");
-    MB_REQUIRE(dL_dmeans2D && dL_dcolors && dL_dopacity && dL_dmeans3D && dL_dcov3D, "mb_raster_backward: null output");
-    MB_REQUIRE(!in->shs || dL_dsh, "mb_raster_backward: dL_dsh required when shs is given");
-    MB_REQUIRE(in->cov3D_precomp || (dL_dscales && dL_drotations), "mb_raster_backward: dL_dscales / dL_drotations required");
+    if (!blend_only) {
+        MB_REQUIRE(dL_dmeans2D && dL_dcolors && dL_dopacity && dL_dmeans3D && dL_dcov3D, "mb_raster_backward: null output");
+        MB_REQUIRE(!in->shs || dL_dsh, "mb_raster_backward: dL_dsh required when shs is given");
+        MB_REQUIRE(in->cov3D_precomp || (dL_dscales && dL_drotations), "mb_raster_backward: dL_dscales / dL_drotations required");
+    }
     if (scratch_bytes < mb_raster_backward_scratch_bytes(d.P)) {
         set_error("mb_raster_backward: scratch too small");
         return MB_ERR_WORKSPACE;
@@ -750,6 +689,7 @@ extern "C" int mb_raster_backward(const mb_raster_inputs *in, const int32_t *rad
         rc = check_launch("blend_backward", dbg, s);
         if (rc) return rc;
     }
+    if (blend_only) return MB_OK;      // the accumulator rows are consumed by mb_pose_backward_from_raster
     PreBwdArgs a;
     a.P = d.P; a.W = d.W; a.H = d.H; a.deg = in->sh_degree; a.M = in->sh_coeffs;
     a.tanx = in->tanfovx; a.tany = in->tanfovy; a.focx = d.focx; a.focy = d.focy; a.scale_mod = in->scale_modifier;
@@ -767,6 +707,25 @@ extern "C" int mb_raster_backward(const mb_raster_inputs *in, const int32_t *rad
     else if (sr) preprocess_backward_kernel<false, true><<<grid, 256, 0, s>>>(a);
     else preprocess_backward_kernel<false, false><<<grid, 256, 0, s>>>(a);
     return check_launch("preprocess_backward", dbg, s);
+}
+
+extern "C" int mb_raster_backward(const mb_raster_inputs *in, const int32_t *radii, const void *geom, const void *binning,
+                                  int64_t capacity, const void *image_buf, const float *dL_dout, int64_t stride_c,
+                                  int64_t stride_y, int64_t stride_x, void *grad_scratch, size_t scratch_bytes,
+                                  float *dL_dmeans2D, float *dL_dcolors, float *dL_dopacity, float *dL_dmeans3D,
+                                  float *dL_dcov3D, float *dL_dsh, float *dL_dscales, float *dL_drotations,
+                                  mb_stream_t stream) {
+    return raster_backward_impl(in, radii, geom, binning, capacity, image_buf, dL_dout, stride_c, stride_y, stride_x, grad_scratch,
+                                scratch_bytes, dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales,
+                                dL_drotations, false, stream);
+}
+
+extern "C" int mb_raster_backward_blend(const mb_raster_inputs *in, const int32_t *radii, const void *geom, const void *binning,
+                                        int64_t capacity, const void *image_buf, const float *dL_dout, int64_t stride_c,
+                                        int64_t stride_y, int64_t stride_x, void *grad_scratch, size_t scratch_bytes,
+                                        mb_stream_t stream) {
+    return raster_backward_impl(in, radii, geom, binning, capacity, image_buf, dL_dout, stride_c, stride_y, stride_x, grad_scratch,
+                                scratch_bytes, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, true, stream);
 }
 
 #ifdef MB_TRACE_CTA

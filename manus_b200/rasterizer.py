@@ -211,6 +211,23 @@ def rasterize_backward(st: RasterState, grad_color: torch.Tensor):
     return g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rot
 
 
+def rasterize_backward_blend(st: RasterState, grad_color: torch.Tensor) -> torch.Tensor:
+    """The tile half of the backward only (mb_raster_backward_blend): returns the accumulator rows ([N,12] fp32, as bytes)
+    that ``manus_b200.pose.pose_backward_from_raster`` consumes.  grad_color: [3,H,W] with any strides."""
+    L = _lib.lib()
+    ri = st.inputs
+    dev = st.geom.device
+    if grad_color.dtype != torch.float32:
+        grad_color = grad_color.float()
+    sc, sy, sx = grad_color.stride()
+    with torch.cuda.device(dev):
+        scratch = torch.empty(L.mb_raster_backward_scratch_bytes(ri.num_points), dtype=torch.uint8, device=dev)
+        _lib.check(L.mb_raster_backward_blend(C.byref(ri), ptr(st.radii), ptr(st.geom), ptr(st.binning), st.capacity, ptr(st.image),
+                                              ptr(grad_color), sc, sy, sx, ptr(scratch), scratch.numel(),
+                                              torch.cuda.current_stream(dev).cuda_stream), "mb_raster_backward_blend")
+    return scratch
+
+
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):

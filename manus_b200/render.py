@@ -111,13 +111,113 @@ def render_gaussians(posed_means, posed_cov, cano_means, cano_features, cano_opa
     return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii}
 
 
+class _RenderFused(torch.autograd.Function):
+    """pose forward + rasterizer forward as ONE autograd node, so that the backward can keep the rasterizer's per-Gaussian
+    gradients out of HBM: tile backward (accumulator rows) -> pose backward with the projection backward inside
+    (mb_pose_backward_from_raster).  Same results as pose_gaussians + GaussianRasterizer up to fp32 contraction order."""
+
+    @staticmethod
+    def forward(ctx, xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, screenspace, bone_tf, campos, settings, sh_degree,
+                isotropic, num_skinned, grad_sink, accumulate):
+        import ctypes as C
+
+        from . import _lib
+        from ._lib import ptr
+        from .pose import _f32c, _inputs
+        from .rasterizer import rasterize_forward
+
+        L = _lib.lib()
+        if not xyz.is_cuda:
+            raise _lib.ManusB200Error("manus_b200.render_fused needs CUDA tensors (there is no CPU path)")
+        dev = xyz.device
+        t = [_f32c(v) for v in (xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, bone_tf)]
+        cam = _f32c(campos).reshape(-1)[:3].contiguous()
+        N = t[0].shape[0]
+        if t[6] is not None and (t[6].shape[0] != num_skinned or t[7] is None or t[7].shape[0] != t[6].shape[1]):
+            raise RuntimeError(f"skin_wts {tuple(t[6].shape)} does not match num_skinned={num_skinned} / bone_tf "
+                               f"{None if t[7] is None else tuple(t[7].shape)}")   # hand_dynamic.py:104
+        pi = _inputs(*t, cam, sh_degree, isotropic, num_skinned)
+        new = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        posed_xyz, cov6, colors, opacity = new(N, 3), new(N, 6), new(N, 3), new(N, 1)
+        with torch.cuda.device(dev):
+            _lib.check(L.mb_pose_forward(C.byref(pi), ptr(posed_xyz), ptr(cov6), ptr(colors), ptr(opacity), None,
+                                         torch.cuda.current_stream(dev).cuda_stream), "mb_pose_forward")
+        color, radii, st = rasterize_forward(settings, posed_xyz, opacity.reshape(-1), colors_precomp=colors, cov3D_precomp=cov6)
+        ctx.saved = (t, cam, sh_degree, isotropic, num_skinned, st)
+        ctx.grad_sink, ctx.accumulate = grad_sink, bool(accumulate) and grad_sink is not None
+        ctx.need_skin = skin_wts is not None and skin_wts.requires_grad
+        ctx.shapes = [None if v is None else v.shape for v in (xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, screenspace)]
+        ctx.mark_non_differentiable(radii, posed_xyz, cov6, colors, opacity)
+        ctx.set_materialize_grads(False)
+        return color, radii, posed_xyz, cov6, colors, opacity
+
+    @staticmethod
+    def backward(ctx, g_color, *_unused):
+        import ctypes as C
+
+        from . import _lib
+        from ._lib import ptr
+        from .pose import _inputs
+        from .rasterizer import rasterize_backward_blend
+
+        L = _lib.lib()
+        t, cam, sh_degree, isotropic, num_skinned, st = ctx.saved
+        if g_color is None:
+            return (None,) * 16
+        if st.host_count is not None:
+            st.resolve()
+        dev = t[0].device
+        N = t[0].shape[0]
+        scratch = rasterize_backward_blend(st, g_color)
+        pi = _inputs(*t, cam, sh_degree, isotropic, num_skinned)
+        sink = ctx.grad_sink
+        if sink is not None:
+            g = [sink.get(k) for k in ("xyz", "log_scale", "quat", "opacity_logit", "f_dc", "f_rest")]
+            for k, (gk, ref) in enumerate(zip(g, t[:6])):
+                if gk is None and k == 5:
+                    continue                     # compact exchange: the f_rest gradient is rebuilt from g_f_dc
+                if ref is not None and (gk is None or gk.numel() != ref.numel() or not gk.is_contiguous() or gk.dtype != torch.float32):
+                    raise RuntimeError("grad_sink tensors must be dense fp32 with the parameter's size")
+        else:
+            g = [None if ref is None else torch.empty_like(ref) for ref in t[:6]]
+        g_skin = None
+        if ctx.need_skin:
+            g_skin = torch.zeros_like(t[6]) if ctx.accumulate else torch.empty_like(t[6])
+        g_means2D = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            if sink is not None and sink.get("_wait") is not None:
+                torch.cuda.current_stream(dev).wait_event(sink["_wait"])
+            _lib.check(L.mb_pose_backward_from_raster(C.byref(pi), C.byref(st.inputs), ptr(st.radii), ptr(scratch), ptr(g_means2D),
+                                                      ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(g[3]), ptr(g[4]),
+                                                      ptr(g[5]) if g[5] is not None and g[5].numel() else None, ptr(g_skin),
+                                                      int(ctx.accumulate), torch.cuda.current_stream(dev).cuda_stream),
+                       "mb_pose_backward_from_raster")
+            if sink is not None and sink.get("_record") is not None:
+                sink["_record"].record(torch.cuda.current_stream(dev))
+        sh = ctx.shapes
+        rs = lambda v, s: None if v is None else v.reshape(s)
+        ctx.saved = None
+        head = (None,) * 6 if sink is not None else tuple(rs(gk, s) for gk, s in zip(g, sh[:6]))
+        return head + (rs(g_skin, sh[6]), rs(g_means2D, sh[7])) + (None,) * 8
+
+
 def render_fused(params, skin_wts, bone_tf, camera, bg_color, sh_degree=3, isotropic=False, num_skinned=None, grad_sink=None,
-                 accumulate=False):
+                 accumulate=False, fuse_backward=False):
     """params: (xyz, log_scale, quat, opacity_logit, f_dc, f_rest) -- the six nn.Parameters of GaussianModel.
     Returns the render_gaussians dict plus the posed quantities (what TrainingModule.forward returns)."""
     xyz, log_scale, quat, opacity_logit, f_dc, f_rest = params
     device = xyz.device
     campos = torch.as_tensor(camera.camera_center).to(device)
+    if fuse_backward:
+        # one autograd node for pose + rasterizer: the backward runs the projection backward inside the pose backward kernel
+        if num_skinned is None:
+            num_skinned = 0 if skin_wts is None else skin_wts.shape[0]
+        screenspace = _screenspace_leaf(xyz)
+        image, radii, posed_xyz, posed_cov, colors, opacity = _RenderFused.apply(
+            xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, screenspace, bone_tf, campos,
+            _settings(camera, bg_color, sh_degree, device), int(sh_degree), bool(isotropic), int(num_skinned), grad_sink, accumulate)
+        return {"render": torch.permute(image, (1, 2, 0)), "viewspace_points": screenspace, "visibility_filter": radii > 0, "radii": radii,
+                "posed_xyz": posed_xyz, "posed_cov": posed_cov, "colors": colors, "cano_opacity": opacity}
     posed_xyz, posed_cov, colors, opacity = pose_gaussians(xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, bone_tf,
                                                           campos, sh_degree, isotropic, num_skinned, grad_sink, accumulate)
     out = render_gaussians(posed_xyz, posed_cov, xyz, None, opacity, camera, bg_color, colors_precomp=colors,

@@ -137,3 +137,49 @@ def test_views_in_flight_sum_the_single_view_gradients(built_lib, V, ordered):
                 assert abs(float(step.losses[slot]) - eager[k][0]) <= 1e-6 * abs(eager[k][0])
     finally:
         rz.set_capacity_mode("exact")
+
+
+@pytest.mark.parametrize("n", [6007, 4096])
+def test_fused_projection_and_pose_backward_matches_the_two_kernel_path(built_lib, n):
+    """render_fused(fuse_backward=True): ONE autograd node whose backward feeds the blend backward's accumulator rows straight
+    into the pose backward kernel (mb_raster_backward_blend + mb_pose_backward_from_raster) -- same image, same screen-space
+    gradient, same parameter gradients as mb_raster_backward + mb_pose_backward; overwrite, accumulate and autograd-leaf modes."""
+    from manus_b200.render import render_fused
+
+    scene, r = _renderer(n=n)
+    dev = r.device
+    G = torch.rand(r.H, r.W, 3, generator=torch.Generator().manual_seed(11)).to(dev)
+    _, c, b = r.view_inputs_host(11)
+    c, b = c.to(dev), b.to(dev)
+    res = {}
+    for fused in (False, True):
+        out = r.render(11, sink=r.flat.grads, cam_dev=c, bones_dev=b, fuse_backward=fused)
+        (out["render"] * G).sum().backward()
+        res[fused] = (out["render"].detach().clone(), r.flat.grad.clone(), out["viewspace_points"].grad.clone(), out["radii"].clone())
+    assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][3], res[False][3])
+    ok, e, s = grad_close(res[True][2].cpu().numpy(), res[False][2].cpu().numpy(), 4e-6)    # float atomics: order noise only
+    assert ok, (e, s)
+    assert float(res[False][2][:, :2].abs().max()) > 0 and float(res[True][2][:, 2].abs().max()) == 0
+    ok, e, s = grad_close(res[True][1].cpu().numpy(), res[False][1].cpu().numpy(), 5e-6)
+    assert ok, (e, s)
+    # accumulate on top of a random buffer
+    base = torch.randn_like(r.flat.grad) * res[False][1].abs().mean()
+    r.flat.grad.copy_(base)
+    out = r.render(11, sink=r.flat.grads, cam_dev=c, bones_dev=b, fuse_backward=True, accumulate=True)
+    (out["render"] * G).sum().backward()
+    ok, e, s = grad_close((r.flat.grad - base).cpu().numpy(), res[False][1].cpu().numpy(), 1e-5)
+    assert ok, (e, s)
+    # without a sink the gradients go to the autograd leaves (and to skin_wts when it requires grad)
+    grads = {}
+    for fused in (False, True):
+        leaves = r.flat.leaves()
+        skin = r.skin.clone().requires_grad_(True)
+        from manus_b200.cameras import Camera
+        cam = r._cams[11][0]
+        dcam = Camera(cam.width, cam.height, cam.fovx, cam.fovy, c[0:16].view(4, 4), c[16:32].view(4, 4), c[32:35], None)
+        out = render_fused(leaves, skin, r._bone_tf, dcam, r.bg, 3, False, r.n_hand, fuse_backward=fused)
+        (out["render"] * G).sum().backward()
+        grads[fused] = [l.grad.clone() for l in leaves] + [skin.grad.clone()]
+    for got, want in zip(grads[True], grads[False]):
+        ok, e, s = grad_close(got.cpu().numpy(), want.cpu().numpy(), 5e-6)
+        assert ok, (e, s)
