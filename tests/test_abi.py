@@ -111,3 +111,39 @@ def test_shims_expose_the_upstream_module_surface():
                    "projmatrix", "tan_fovx", "tan_fovy", "dL_dout_color", "sh", "degree", "campos", "geomBuffer", "R", "binningBuffer",
                    "imageBuffer", "debug"]
     assert list(inspect.signature(dgr._C.mark_visible).parameters) == ["means3D", "viewmatrix", "projmatrix"]
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The header is plain C: compile a probe with gcc that prints sizeof / offsetof of the two input structs and compare with
+    the ctypes mirrors in manus_b200/_lib.py (field names, order, offsets, total size)."""
+    import shutil
+    import subprocess
+
+    from manus_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    pairs = (("mb_raster_inputs", _lib.RasterInputs), ("mb_pose_inputs", _lib.PoseInputs))
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "manus_b200.h"', "int main(void) {"]
+    for cname, cls in pairs:
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {field} %zu\\n", offsetof({cname}, {field}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    want = []
+    for cname, cls in pairs:
+        want.append(f"{cname} size {ctypes.sizeof(cls)}")
+        want += [f"{cname} {field} {getattr(cls, field).offset}" for field, _ in cls._fields_]
+    assert [g for g in got if g] == want
+    # and the header declares no field the mirrors lack
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "manus_b200.h")).read(), flags=re.S)
+    for cname, cls in pairs:
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), text, flags=re.S).group(1)
+        names = re.findall(r"(\w+)\s*(?=[;,])", body)
+        assert sorted(set(names)) == sorted(f for f, _ in cls._fields_), (cname, names)
