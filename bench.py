@@ -554,6 +554,10 @@ def main():
         line["cpu_baseline"] = {"value": 1.0 / cb["total_s"], "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "one full 1080p frame of the same scene (view 0): pose fwd+bwd in PyTorch-CPU + raster "
                                           "fwd+bwd in C (oracle/), all host threads", "breakdown_s": {k: round(v, 4) for k, v in cb.items() if k != "D"}}
+    # north_star asks for the reference's own CUDA rasterizer on one GPU next to this number: it is a third-party submodule
+    # cloned at install time (setup_env.sh:6-13), absent from the reference tree and from this image (no network)
+    line["reference_cuda_rasterizer"] = {"value": None, "unavailable": "diff-gaussian-rasterization / simple-knn sources are not part of "
+                                         "the reference checkout and cannot be fetched here; the reference arm is the CPU port (cpu_baseline)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
