@@ -295,7 +295,10 @@ class GraphedStep:
 
     loss_fn(image[H,W,3], target) -> scalar tensor.  After ``replay()``: ``loss`` (device scalar: the sum over the step's
     views; ``losses`` holds them one by one) and ``renderer.flat.grad`` (sum over the views) hold the step's results.
-    ``check()`` (synchronises) raises if a replayed frame overflowed the reserved capacity.
+    ``check()`` (synchronises) raises if a replayed frame overflowed the reserved capacity.  ``radii_all[i]`` are view i's
+    radii; the views' screen-space gradients (``viewspace_points.grad``, the densification statistic of
+    src/models/gaussian.py:335-338) are not kept by the captured step yet -- a densification iteration renders its views
+    through ``SceneRenderer.render`` (every ~100th step in the reference's schedule).
     """
 
     def __init__(self, renderer: SceneRenderer, loss_fn, target_like: torch.Tensor, view: int = 0, warmup: int = 3,
