@@ -297,8 +297,9 @@ class GraphedStep:
     views; ``losses`` holds them one by one) and ``renderer.flat.grad`` (sum over the views) hold the step's results.
     ``check()`` (synchronises) raises if a replayed frame overflowed the reserved capacity.  ``radii_all[i]`` are view i's
     radii; the views' screen-space gradients (``viewspace_points.grad``, the densification statistic of
-    src/models/gaussian.py:335-338) are not kept by the captured step yet -- a densification iteration renders its views
-    through ``SceneRenderer.render`` (every ~100th step in the reference's schedule).
+    src/models/gaussian.py:335-338, which the reference accumulates every step while ``global_step < densify_until_step``,
+    src/utils/gaussian_utils.py:466-473) are not kept by the captured step yet: steps of the densification phase go through
+    ``SceneRenderer.render`` (whose result dict carries ``viewspace_points``), the captured step serves the steps after it.
     """
 
     def __init__(self, renderer: SceneRenderer, loss_fn, target_like: torch.Tensor, view: int = 0, warmup: int = 3,
