@@ -298,8 +298,7 @@ class GraphedStep:
     ``check()`` (synchronises) raises if a replayed frame overflowed the reserved capacity.  ``radii_all[i]`` are view i's
     radii; the views' screen-space gradients (``viewspace_points.grad``, the densification statistic of
     src/models/gaussian.py:335-338, which the reference accumulates every step while ``global_step < densify_until_step``,
-    src/utils/gaussian_utils.py:466-473) are not kept by the captured step yet: steps of the densification phase go through
-    ``SceneRenderer.render`` (whose result dict carries ``viewspace_points``), the captured step serves the steps after it.
+    src/utils/gaussian_utils.py:466-473) are in ``viewspace[i].grad`` after a replay.
     """
 
     def __init__(self, renderer: SceneRenderer, loss_fn, target_like: torch.Tensor, view: int = 0, warmup: int = 3,
@@ -321,6 +320,7 @@ class GraphedStep:
         self.view = view
         self.loss_fn = loss_fn
         self.states = [None] * V
+        self.viewspace = [None] * V      # per view: the screen-space leaf; .grad is rewritten by every replay
 
         def frame(i, done):
             sink = renderer.flat.grads
@@ -331,6 +331,7 @@ class GraphedStep:
             out = renderer.render(view, sink=sink, cam_dev=self.cams[i], bones_dev=self.bones_all[i], device_intrinsics=True,
                                   compact_sh=compact_sh, accumulate=V > 1 and (i > 0 or not ordered), slot=i)
             self.states[i] = rz._Plan.last_state
+            self.viewspace[i] = out["viewspace_points"]
             loss = loss_fn(out["render"], self.targets[i])
             return loss, out["radii"]
 
