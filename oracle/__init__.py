@@ -13,7 +13,8 @@ Parity status
 * image losses (``loss_ref.py``) and the skin-weight lookup (``skin_ref.py``): PINNED against the reference's own
   ``loss_utils`` / ``skinning_weights_from_voxel_grid`` through ``tests/golden/loss_golden.npz`` / ``skin_golden.npz``
   (``tests/golden/make_golden_loss.py``, ``make_golden_skin.py``).
-* contact distance (``knn_ref.contact_dist``): unpinned (the reference loop is a taichi kernel), cross-checked with a k-d tree.
+* contact distance (``knn_ref.contact_dist``): the reference loop is a taichi kernel (cannot run here); cross-checked with a k-d
+  tree and pinned through the reference's pure-torch ``get_contact_map`` (tests/golden/contact_golden.npz).
 * rasterizer (R2/R3) and ``distCUDA2`` (K1): **parity unpinned** -- the Inria
   ``diff-gaussian-rasterization`` / ``simple-knn`` sources are not present in
   ``/root/reference`` (cloned un-pinned at install time, ``setup_env.sh:4-13``);

@@ -38,3 +38,20 @@ def test_contact_composite_size_vs_kdtree(built_lib):
     dk, ik = cKDTree(b.astype(np.float64)).query(a.astype(np.float64), workers=-1)
     np.testing.assert_allclose(d.cpu().numpy(), dk, rtol=3e-6, atol=1e-9)
     assert (i.cpu().numpy() == ik).mean() > 0.9999
+
+
+def test_contact_against_the_reference_get_contact_map(built_lib):
+    """Golden from the reference's own get_contact_map (tests/golden/make_golden_contact.py).  The kernel is exact; the
+    reference's torch.cdist values carry up to 6e-5 of their own error (see test_oracle_knn_contact.py)."""
+    import os
+
+    from manus_b200.knn import get_contact_dist, get_contact_map
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "contact_golden.npz"))
+    a, b = torch.tensor(g["pt1"], device="cuda"), torch.tensor(g["pt2"], device="cuda")
+    cm = get_contact_map(a, b, chunk=1024).cpu().numpy()
+    np.testing.assert_allclose(cm, g["dist64"], rtol=3e-6, atol=1e-9)
+    np.testing.assert_allclose(cm, g["contact_map"], rtol=0, atol=1e-4)
+    d, i = get_contact_dist(a, b)
+    np.testing.assert_array_equal(d.cpu().numpy(), cm)
+    assert (i.cpu().numpy().astype(np.int64) == g["idx64"]).mean() > 0.999
