@@ -28,16 +28,16 @@ def main(out=None):
         d = json.loads(line)
         f = d["frame"]
         top = d["roofline"]
-        rows.append(f"| {name} | {d['value']:.0f} | {d['ms_per_step']:.3f} | {d['e2e']['value']:.0f} | {f['num_rendered_mean'] / 1e6:.2f} M | "
+        rows.append(f"| {name} | {d['value']:.0f} | {d['ms_per_step'] / d.get('frames_per_step', 1):.3f} | {d['e2e']['value']:.0f} | {f['num_rendered_mean'] / 1e6:.2f} M | "
                     f"{f['algorithmic_bytes'] / 1e9:.2f} GB | {f['achieved_gbps']:.0f} GB/s ({100 * f['frac_of_hbm_peak']:.0f} %) | "
                     f"{top['kernel']} {top['launch_ms'] * 1e3:.0f} us |")
         print(rows[-1], flush=True)
-    txt = ("| configuration | frames/s (resident) | ms/step | frames/s (e2e, host inputs) | instances D | algorithmic bytes/frame | achieved (of HBM peak) | dominant kernel |\n"
+    txt = ("| configuration | frames/s (resident) | ms/frame | frames/s (e2e, host inputs) | instances D | algorithmic bytes/frame | achieved (of HBM peak) | dominant kernel |\n"
            "|---|---|---|---|---|---|---|---|\n" + "\n".join(rows) + "\n")
     if out:
         with open(out, "w") as fh:
             fh.write("# One-GPU sweep over BASELINE.json's configurations (fwd+bwd, `python tools/sweep.py`)\n\n"
-                     "100 timed steps after 5 warm-up steps each, CUDA-graph replay, 50 shipped views cycled; algorithmic bytes per SURVEY.md section 8d\n"
+                     "100 timed steps after 5 warm-up steps each, CUDA-graph replay with bench.py's default views in flight, 50 shipped views cycled; algorithmic bytes per SURVEY.md section 8d\n"
                      "with the measured instance count.\n\n" + txt)
     print(txt)
 
