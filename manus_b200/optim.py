@@ -12,8 +12,10 @@ reduce-scatter(grad) -> Adam on the rank's shard -> all-gather(param): the same 
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Optional, Tuple
+import math
+from typing import Callable, Dict, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -79,6 +81,29 @@ class FlatAdam:
             _lib.check(L.mb_fused_adam(ptr(self.flat.data), ptr(g), ptr(self.exp_avg), ptr(self.exp_avg_sq), int(begin), int(end),
                                        len(PARAM_ORDER), self._seg_end, lrs, self.step_count, self.betas[0], self.betas[1], self.eps,
                                        float(grad_scale), torch.cuda.current_stream(dev).cuda_stream), "mb_fused_adam")
+
+
+def get_expon_lr_func(lr_init: float, lr_final: float, lr_delay_steps: int = 0, lr_delay_mult: float = 1.0,
+                      max_steps: int = 1000000) -> Callable[[int], float]:
+    """The xyz group's per-step learning rate (/root/reference/src/utils/gaussian_utils.py:212-247, used through
+    ``xyz_scheduler_args`` at src/models/gaussian.py:143-146 and ``update_learning_rate`` :505-511): log-linear interpolation
+    from lr_init (step 0) to lr_final (max_steps), optionally eased in over lr_delay_steps by
+    lr_delay_mult + (1 - lr_delay_mult) sin(pi/2 clip(step / lr_delay_steps)); 0 for negative steps or when both ends are 0.
+    Host arithmetic in float64 like the reference; feed the result to ``FlatAdam.set_lr("xyz", lr)`` before each step."""
+    log_init, log_final = (math.log(lr_init), math.log(lr_final)) if lr_init > 0.0 and lr_final > 0.0 else (None, None)
+
+    def lr_at(step: int) -> float:
+        if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+            return 0.0
+        delay = 1.0
+        if lr_delay_steps > 0:
+            delay = lr_delay_mult + (1.0 - lr_delay_mult) * math.sin(0.5 * math.pi * min(max(step / lr_delay_steps, 0.0), 1.0))
+        t = min(max(step / max_steps, 0.0), 1.0)
+        if log_init is None:      # one end is 0: the reference's log() gives -inf and exp() 0 (or NaN at the 0-weighted end)
+            return delay * float(np.exp(np.log(np.float64(lr_init)) * (1 - t) + np.log(np.float64(lr_final)) * t))
+        return delay * math.exp(log_init * (1.0 - t) + log_final * t)
+
+    return lr_at
 
 
 def shard_range(numel: int, rank: int, world_size: int, align: int = 4) -> Tuple[int, int]:
