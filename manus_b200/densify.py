@@ -42,6 +42,35 @@ def build_rotation(r: torch.Tensor) -> torch.Tensor:
     return R
 
 
+SH_C0 = 0.28209479177387814
+
+
+def initialize_parameters(points, points_colors, sh_degree: int = 3, isotropic: bool = False, dist2: Optional[torch.Tensor] = None,
+                          device=None) -> Dict[str, torch.Tensor]:
+    """``GaussianModel.initialize_parameters`` (/root/reference/src/models/gaussian.py:99-127), the one caller of ``distCUDA2``
+    (:110): xyz = points; f_dc = RGB2SH(colours) (sh_utils.py:123-124), f_rest = 0; log-scales = log(sqrt(clamp_min(mean squared
+    distance to the 3 nearest neighbours, 1e-7))) in every axis (one column when isotropic); identity quaternions (1, 0, 0, 0);
+    opacity logit = inverse_sigmoid(0.1).  Returns the six parameters under the names ``FlatGaussians`` uses.
+    ``dist2``: the 3-NN statistic when the caller already has it; otherwise ``manus_b200.knn.distCUDA2`` computes it (CUDA)."""
+    xyz = torch.as_tensor(points).float()
+    if device is not None:
+        xyz = xyz.to(device)
+    n, dev = xyz.shape[0], xyz.device
+    colors = torch.as_tensor(points_colors).float().to(dev)
+    if dist2 is None:
+        from .knn import distCUDA2
+
+        dist2 = distCUDA2(xyz)
+    dist2 = torch.clamp_min(torch.as_tensor(dist2).float().to(dev), 0.0000001)
+    log_scale = torch.log(torch.sqrt(dist2))[..., None].repeat(1, 1 if isotropic else 3)
+    quat = torch.zeros((n, 4), device=dev)
+    quat[:, 0] = 1
+    k = (sh_degree + 1) ** 2
+    return {"xyz": xyz, "opacity_logit": inverse_sigmoid(0.1 * torch.ones((n, 1), dtype=torch.float, device=dev)),
+            "log_scale": log_scale, "quat": quat, "f_dc": ((colors - 0.5) / SH_C0).reshape(n, 1, 3).contiguous(),
+            "f_rest": torch.zeros((n, k - 1, 3), device=dev)}
+
+
 def _segments(flat: FlatGaussians, buf: torch.Tensor) -> Dict[str, torch.Tensor]:
     """Per-parameter views of a flat buffer laid out like ``flat.data``."""
     out, off = {}, 0

@@ -60,6 +60,16 @@ class FlatGaussians:
             fg.params[name].copy_(torch.as_tensor(getattr(scene, name)).reshape(fg.params[name].shape))
         return fg
 
+    @classmethod
+    def from_params(cls, params: Dict[str, torch.Tensor], device=None):
+        """From the six tensors keyed like PARAM_ORDER, e.g. ``manus_b200.densify.initialize_parameters(points, colours)``
+        (the reference's GaussianModel.initialize_parameters, src/models/gaussian.py:99-127)."""
+        device = params["xyz"].device if device is None else device
+        fg = cls(params["xyz"].shape[0], device, sh_coeffs=1 + params["f_rest"].shape[1], isotropic=params["log_scale"].shape[1] == 1)
+        for name in PARAM_ORDER:
+            fg.params[name].copy_(torch.as_tensor(params[name]).reshape(fg.params[name].shape))
+        return fg
+
     def leaves(self) -> List[torch.Tensor]:
         """The six parameters as autograd leaves, in the order pose_gaussians takes them
         (xyz, log_scale, quat, opacity_logit, f_dc, f_rest)."""

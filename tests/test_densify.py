@@ -64,3 +64,29 @@ def test_prune_keeps_layout_and_step_count():
     st.prune_points(mask)
     assert st.n == int((~mask).sum()) and st.opt.numel == st.flat.data.numel() == st.opt.exp_avg.numel()
     assert st.opt.step_count == 7 and torch.equal(st.flat.params["quat"], before)
+
+
+def test_initialize_parameters_matches_the_reference():
+    """tests/golden/init_golden.npz: GaussianModel.initialize_parameters (gaussian.py:99-127) run here with the exact 3-NN
+    statistic standing in for the absent distCUDA2; bit-exact (same torch operations on the same inputs)."""
+    import os
+
+    import numpy as np
+
+    from manus_b200.densify import initialize_parameters
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "init_golden.npz"))
+    assert float(g["dist2"].min()) == 0.0                                  # coincident points exercise the 1e-7 clamp
+    for iso in (False, True):
+        got = initialize_parameters(g["points"], g["colors"], sh_degree=3, isotropic=iso, dist2=torch.tensor(g["dist2"]))
+        pre = "iso" if iso else "aniso"
+        for k, v in got.items():
+            want = g[f"{pre}_{k}"]
+            assert tuple(v.shape) == want.shape, (k, v.shape, want.shape)
+            np.testing.assert_array_equal(v.numpy(), want, err_msg=k)
+    flat_shapes = {k: tuple(v.shape) for k, v in got.items()}
+    assert flat_shapes["log_scale"] == (700, 1) and flat_shapes["f_rest"] == (700, 15, 3)
+    flat = FlatGaussians.from_params(got)                                    # the flat buffers the render path works on
+    assert flat.isotropic and flat.n == 700 and flat.data.numel() == 700 * (3 + 1 + 1 + 4 + 3 + 45)
+    for k, v in got.items():
+        assert torch.equal(flat.params[k], v)
