@@ -4,12 +4,15 @@ GaussianModel parameters (one pose kernel + the rasterizer; nothing else runs pe
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 
 import torch
 
-from .pose import pose_gaussians
-from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+from . import _lib
+from ._lib import ptr
+from .pose import _f32c, _inputs, pose_gaussians
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, rasterize_backward_blend, rasterize_forward
 
 
 def _scalar(v) -> float:
@@ -119,13 +122,6 @@ class _RenderFused(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, screenspace, bone_tf, campos, settings, sh_degree,
                 isotropic, num_skinned, grad_sink, accumulate):
-        import ctypes as C
-
-        from . import _lib
-        from ._lib import ptr
-        from .pose import _f32c, _inputs
-        from .rasterizer import rasterize_forward
-
         L = _lib.lib()
         if not xyz.is_cuda:
             raise _lib.ManusB200Error("manus_b200.render_fused needs CUDA tensors (there is no CPU path)")
@@ -153,13 +149,6 @@ class _RenderFused(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_color, *_unused):
-        import ctypes as C
-
-        from . import _lib
-        from ._lib import ptr
-        from .pose import _inputs
-        from .rasterizer import rasterize_backward_blend
-
         L = _lib.lib()
         t, cam, sh_degree, isotropic, num_skinned, st = ctx.saved
         if g_color is None:
