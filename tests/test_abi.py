@@ -147,3 +147,21 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), text, flags=re.S).group(1)
         names = re.findall(r"(\w+)\s*(?=[;,])", body)
         assert sorted(set(names)) == sorted(f for f, _ in cls._fields_), (cname, names)
+
+
+def test_fused_render_refuses_cpu_tensors(built_lib):
+    """There is no CPU path: the fused pose + rasterizer node raises on CPU tensors instead of computing anything."""
+    import types
+
+    import torch
+
+    from manus_b200 import _lib
+    from manus_b200.render import render_fused
+
+    cam = types.SimpleNamespace(camera_center=torch.zeros(3), height=16, width=16, fovx=0.5, fovy=0.5,
+                                world_view_transform=torch.eye(4), full_proj_transform=torch.eye(4))
+    params = [torch.zeros(4, 3, requires_grad=True), torch.zeros(4, 3), torch.zeros(4, 4), torch.zeros(4, 1), torch.zeros(4, 1, 3),
+              torch.zeros(4, 15, 3)]
+    for fused in (True, False):
+        with pytest.raises(_lib.ManusB200Error, match="no CPU path"):
+            render_fused(params, None, None, cam, torch.ones(3), fuse_backward=fused)
