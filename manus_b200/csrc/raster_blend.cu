@@ -407,7 +407,8 @@ __global__ void __launch_bounds__(kWarps * 32, MB_BWD_WARPS_PER_SM / kWarps) ble
                 const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
                 const bool cand = (pos < last_rel) && (power <= 0.0f) && !(power < rc.y);
                 if (!__any_sync(0xffffffffu, cand)) continue;
-                const float G = expf(power);
+                // non-candidate lanes get G = 0 (not exp of a possibly huge positive power): their partials are exact zeros
+                const float G = cand ? expf(power) : 0.f;
                 const float alpha = fminf(kAlphaMax, rb.y * G);
                 const bool active = cand && (alpha >= kAlphaMin);
                 // Branch-free update: a lane for which this Gaussian does not contribute keeps its state (selects) and its

@@ -131,7 +131,10 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {   // `a` i
                     const float cut = -logf(255.0f * op) - 1e-4f;
                     // half extents of the bounding box of { power >= cut }: dx^2 <= 2|cut| cov2D.xx, dy^2 <= 2|cut| cov2D.yy
                     // (NaN when no pixel can pass the alpha gate: such a record never survives the tile kernels' box test)
-                    const float ex = sqrtf(-2.0f * cut * ca) * 1.0001f + 0.01f, ey = sqrtf(-2.0f * cut * cc) * 1.0001f + 0.01f;
+                    float ex = sqrtf(-2.0f * cut * ca) * 1.0001f + 0.01f, ey = sqrtf(-2.0f * cut * cc) * 1.0001f + 0.01f;
+                    // an indefinite 2-D covariance (det < 0: only possible with a non-PSD cov3D_precomp) has no bounded
+                    // { power >= cut } set: keep upstream's whole rectangle and let the per-pixel gates decide
+                    if (det < 0.0f && cut <= 0.0f) ex = ey = 1.0e9f;
                     // Instances are only emitted for the tiles of upstream's rectangle that this box reaches: in the others
                     // every pixel fails the alpha >= 1/255 gate, so dropping them changes neither image nor gradients
                     // (it only shortens the lists; radii and visibility stay upstream's).
