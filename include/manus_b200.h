@@ -116,8 +116,10 @@ int mb_raster_backward(const mb_raster_inputs *in, const int32_t *radii, const v
                        float *dL_dsh /*[P,M,3]*/, float *dL_dscales /*[P,3]*/, float *dL_drotations /*[P,4]*/,
                        mb_stream_t stream);
 
-/* The tile half of the backward only: fills grad_scratch with one 12-float accumulator row per Gaussian (dL/d(screen xy) 2 |
- * dL/dconic 3 | dL/dopacity 1 | dL/dcolour 3 | 3 unused).  mb_pose_backward_from_raster consumes the rows: on the fused path the
+/* The tile half of the backward only: fills grad_scratch with one 12-float accumulator row per Gaussian: the pixel sums of
+ * q = G dL/dalpha times (dx, dy, dx^2, dx dy, dy^2), d = mean2D - pixel (5) | sum q = dL/dopacity (1) | dL/dcolour (3) | 3 unused;
+ * dL/dmean2D and dL/dconic follow from the five moments once per Gaussian (csrc/project_bwd.cuh).
+ * mb_pose_backward_from_raster consumes the rows: on the fused path the
  * projection backward runs inside the pose backward kernel and dL_dmeans3D / dL_dcov3D / dL_dcolors / dL_dopacity never touch
  * HBM. */
 int mb_raster_backward_blend(const mb_raster_inputs *in, const int32_t *radii, const void *geom, const void *binning,

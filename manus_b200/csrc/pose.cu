@@ -40,13 +40,13 @@ struct PoseArgs {
     int accumulate;   // backward: add the gradients to the output buffers (bulk TMA reduce-add) instead of overwriting them
     // backward fused with the rasterizer's projection backward (mb_pose_backward_from_raster): the upstream gradients are
     // derived in the kernel from the blend backward's accumulator rows instead of being read from the four g_* arrays
-    const float *acc;          // [N,12]: dL/d(mean2D xy), dL/dconic xyz, dL/dopacity, dL/dcolour rgb, 3 unused; nullptr = not fused
+    const float *acc;          // [N,12]: five moments of the blend backward (project_bwd.cuh), dL/dopacity, dL/dcolour rgb, 3 unused; nullptr = not fused
     const int32_t *radii;      // [N]
     const float *view, *proj;  // [16] each
     const float *tanfov_dev;   // optional [2] in device memory (replaces tanx / tany)
     float tanx, tany;
     int W, H;
-    float *g_means2D;          // [N,3] out: (acc[0], acc[1], 0)
+    float *g_means2D;          // [N,3] out: (dL/dmean2D x, y, 0)
 };
 
 constexpr int kAccRow = 12;          // floats per accumulator row (kAccStride of raster_blend.cu)
@@ -354,7 +354,7 @@ __device__ __forceinline__ void run_tiles(const PoseArgs &a, float *smem, Body b
         const int row = threadIdx.x, i = tile * kPoseThreads + row;
         if (kBackward && kFused) {
             // rows of the accumulator (array of structures) -> the per-array slots the body reads: every thread takes its
-            // row into registers, then writes (mean2D grad xy, radius | conic grad | colour grad | opacity grad)
+            // row into registers, then writes (moments m0 m1, radius | moments m2 m3 m4 | colour grad | opacity grad)
             float *st = pipe.stage(0);
             float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
             int rad = 0;
@@ -464,13 +464,14 @@ __global__ void __launch_bounds__(kPoseThreads, kFused ? 4 : 1) pose_backward_ke
         // upstream gradients of the posed mean and covariance: from the rasterizer's arrays, or (fused) from its accumulator row
         float gp[3], g6[6];
         if (kFused) {
-            const float g2x = st[L.gpx + 3 * row], g2y = st[L.gpx + 3 * row + 1];
+            const float m[5] = {st[L.gpx + 3 * row], st[L.gpx + 3 * row + 1], st[L.gcov + 6 * row], st[L.gcov + 6 * row + 1], st[L.gcov + 6 * row + 2]};
             const int rad = __float_as_int(st[L.gpx + 3 * row + 2]);
+            float g2[2] = {0.f, 0.f};
             gp[0] = gp[1] = gp[2] = 0.f;
 #pragma unroll
             for (int k = 0; k < 6; ++k) g6[k] = 0.f;
             if (rad > 0) {
-                // the posed mean and covariance exactly as pose_forward_kernel wrote them for the rasterizer's forward
+                // the posed mean, covariance and opacity exactly as pose_forward_kernel wrote them for the rasterizer's forward
                 float pm[3], c6[6];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) pm[r] = p.A[3 * r] * p.x[0] + p.A[3 * r + 1] * p.x[1] + p.A[3 * r + 2] * p.x[2] + p.t[r];
@@ -480,11 +481,11 @@ __global__ void __launch_bounds__(kPoseThreads, kFused ? 4 : 1) pose_backward_ke
                 c6[3] = Bm[3] * Bm[3] + Bm[4] * Bm[4] + Bm[5] * Bm[5];
                 c6[4] = Bm[3] * Bm[6] + Bm[4] * Bm[7] + Bm[5] * Bm[8];
                 c6[5] = Bm[6] * Bm[6] + Bm[7] * Bm[7] + Bm[8] * Bm[8];
+                const float op = 1.0f / (1.0f + expf(-st[L.opac + row]));
                 const float *rc = cam_s + 8;
-                project_backward(rc, rc + 16, rc[32], rc[33], rc[34], rc[35], pm[0], pm[1], pm[2], c6, st[L.gcov + 6 * row],
-                                 st[L.gcov + 6 * row + 1], st[L.gcov + 6 * row + 2], g2x, g2y, gp, g6);
+                project_backward(rc, rc + 16, rc[32], rc[33], rc[34], rc[35], a.W, a.H, pm[0], pm[1], pm[2], c6, op, m, g2, gp, g6);
             }
-            a.g_means2D[3 * (size_t)i] = g2x; a.g_means2D[3 * (size_t)i + 1] = g2y; a.g_means2D[3 * (size_t)i + 2] = 0.f;
+            a.g_means2D[3 * (size_t)i] = g2[0]; a.g_means2D[3 * (size_t)i + 1] = g2[1]; a.g_means2D[3 * (size_t)i + 2] = 0.f;
         } else {
 #pragma unroll
             for (int r = 0; r < 3; ++r) gp[r] = st[L.gpx + 3 * row + r];

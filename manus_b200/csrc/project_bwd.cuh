@@ -7,11 +7,16 @@
 namespace mb {
 
 // v = viewmatrix[16], p = projmatrix[16] (column-major as upstream reads them); (mx, my, mz) world-space mean; c6 = 3-D
-// covariance (xx,xy,xz,yy,yz,zz); (gx, gy, gz) = dL/dconic; (g2x, g2y) = dL/d(NDC-scaled screen xy).
-// Writes gmean[3] = dL/dmean3D and gcov[6] = dL/dcov3D.
+// covariance (xx,xy,xz,yy,yz,zz); opacity as the forward used it; W, H image size.
+// m[5] = the blend backward's moments of q = G dL/dalpha over the Gaussian's pixels, d = mean2D - pixel:
+//   sum q dx, sum q dy, sum q dx^2, sum q dx dy, sum q dy^2.   With dL/dG = opacity dL/dalpha and
+//   dG/dd = -G (conic.x dx + conic.y dy, conic.z dy + conic.y dx) they give (A.4)
+//   dL/dmean2D = -opacity (conic.x m0 + conic.y m1, conic.z m1 + conic.y m0) * (W/2, H/2)   [NDC-scaled, upstream's ddelx_dx]
+//   dL/dconic  = -0.5 opacity (m2, m3, m4).
+// Writes g2[2] = dL/dmean2D, gmean[3] = dL/dmean3D and gcov[6] = dL/dcov3D.
 __device__ __forceinline__ void project_backward(const float *v, const float *p, float tanx, float tany, float focx, float focy,
-                                                 float mx, float my, float mz, const float *c6, float gx, float gy, float gz,
-                                                 float g2x, float g2y, float *gmean, float *gcov) {
+                                                 int W, int H, float mx, float my, float mz, const float *c6, float opacity,
+                                                 const float *m, float *g2, float *gmean, float *gcov) {
     // cov2D backward (A.4)
     const float t0 = v[0] * mx + v[4] * my + v[8] * mz + v[12];
     const float t1 = v[1] * mx + v[5] * my + v[9] * mz + v[13];
@@ -39,6 +44,13 @@ __device__ __forceinline__ void project_backward(const float *v, const float *p,
     const float cb = M0[0] * SM1[0] + M0[1] * SM1[1] + M0[2] * SM1[2];
     const float cc = M1[0] * SM1[0] + M1[1] * SM1[1] + M1[2] * SM1[2] + kLowPass;
     const float denom = ca * cc - cb * cb;
+    // the conic of the forward (A.1 step 6) and the per-Gaussian part of the blend backward
+    const float di = 1.0f / denom;
+    const float conx = cc * di, cony = -cb * di, conz = ca * di;
+    const float g2x = -opacity * (conx * m[0] + cony * m[1]) * (0.5f * W);
+    const float g2y = -opacity * (conz * m[1] + cony * m[0]) * (0.5f * H);
+    const float gx = -0.5f * opacity * m[2], gy = -0.5f * opacity * m[3], gz = -0.5f * opacity * m[4];
+    g2[0] = g2x; g2[1] = g2y;
     const float d2 = 1.0f / (denom * denom + 0.0000001f);
     float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
 #pragma unroll

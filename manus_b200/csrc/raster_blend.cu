@@ -21,7 +21,10 @@
 namespace mb {
 
 constexpr int kAccStride = 12;              // floats per Gaussian in the gradient accumulator
-// accumulator slots: 0,1 mean2D.xy | 2,3,4 conic (x,y,w) | 5 opacity | 6,7,8 colour
+// accumulator slots: moments of q = G * dL/dalpha over the pixels, d = mean2D - pixel:
+//   0 sum q dx | 1 sum q dy | 2 sum q dx^2 | 3 sum q dx dy | 4 sum q dy^2 | 5 sum q (= dL/dopacity) | 6,7,8 dL/dcolour
+// The consumer (project_backward) turns them into dL/dmean2D and dL/dconic with the Gaussian's conic and opacity, once per
+// Gaussian instead of once per (Gaussian, pixel).
 
 int build_instances(const mb_raster_inputs *in, const RasterDims &d, const GeomState &g, const BinningState &b,
                     const ImageState &im, int64_t capacity, cudaStream_t s);
@@ -380,7 +383,6 @@ __global__ void __launch_bounds__(kWarps * 32, MB_BWD_WARPS_PER_SM / kWarps) ble
     const uint32_t wlast_abs = __reduce_max_sync(0xffffffffu, last);
     const int wlast = wlast_abs > s0 ? (int)min(wlast_abs - s0, (uint32_t)len) : 0;
     const uint32_t last_rel = last > s0 ? last - s0 : 0u;
-    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
     for (int i = 0; i < st.nb; ++i) {
         st.advance(i);
         const int cnt = st.count(i);
@@ -426,18 +428,179 @@ __global__ void __launch_bounds__(kWarps * 32, MB_BWD_WARPS_PER_SM / kWarps) ble
                 a0 = active ? n0 : a0; a1 = active ? n1 : a1; a2 = active ? n2 : a2;
                 lc0 = active ? c0 : lc0; lc1 = active ? c1 : lc1; lc2 = active ? c2 : lc2;
                 last_alpha = active ? alpha : last_alpha;
-                const float dL_dG = rb.y * dL_dalpha;   // the 0.99 clamp is not masked (upstream behaviour)
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * ra.z - gdy * ra.w;
-                const float dG_ddely = -gdy * rb.x - gdx * ra.w;
+                // the 0.99 clamp is not masked (upstream behaviour): dL/dG = opacity * dL/dalpha for every active pixel
+                const float q = G * dL_dalpha, qx = q * dx, qy = q * dy;
                 float v[9];
-                v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                v[1] = dL_dG * dG_ddely * ddely_dy;
-                v[2] = -0.5f * gdx * dx * dL_dG;
-                v[3] = -0.5f * gdx * dy * dL_dG;
-                v[4] = -0.5f * gdy * dy * dL_dG;
-                v[5] = G * dL_dalpha;
+                v[0] = qx; v[1] = qy;
+                v[2] = qx * dx; v[3] = qx * dy; v[4] = qy * dy;
+                v[5] = q;
                 v[6] = dch * dp0; v[7] = dch * dp1; v[8] = dch * dp2;
+                const float total = reduce_scatter9(v, lane);
+                if (slot >= 0) red_add(acc + (size_t)ids[j] * kAccStride + slot, total);
+            }
+        }
+        __syncthreads();   // this batch's buffers may be overwritten by the copies issued in the next step
+    }
+}
+
+// ---- packed fp32x2 arithmetic (sm_100a FFMA2 / FMUL2 / FADD2): one issue slot for the two pixels of a lane ----
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// exp(x) of both halves for x <= 0 (|x| < 100): exp(x) = 2^t 2^r with t = fl(x log2e) and r = the rounding residual of that
+// product plus x (log2e - fl(log2e)); |r| < 1e-6, so 2^r = 1 + r ln2.  MUFU.EX2 at the core like expf(), no range split needed.
+__device__ __forceinline__ float2 exp_pair(float2 x) {
+    const float L = 1.4426950216293334961f, Llo = 1.925963033500011079e-08f, ln2 = 0.693147182464599609375f;
+    const float2 t = __fmul2_rn(x, splat(L));
+    float2 r = __ffma2_rn(x, splat(L), neg2(t));
+    r = __ffma2_rn(x, splat(Llo), r);
+    const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+    return __ffma2_rn(e, __fmul2_rn(r, splat(ln2)), e);
+}
+
+#ifndef MB_BWD2_CTAS_PER_SM
+#define MB_BWD2_CTAS_PER_SM 8
+#endif
+// Backward, two pixels per lane.  Work item = one kSeg-entry segment of one 16x16 tile's list (as above); the CTA's four
+// warps own the tile's four 8x8 pixel blocks, lane l the pixels (l & 7, l >> 3) and (l & 7, (l >> 3) + 4) of its block.  The
+// pair shares dx, and everything per pixel that is plain fp32 arithmetic is issued once for both as a packed FFMA2 / FMUL2 /
+// FADD2; per-survivor overhead (list walk, record fetch, the nine-value warp reduction, the RED) is paid once per 64 pixels.
+// The recurrence is upstream's, restated without selects: an inactive (pixel, Gaussian) pair takes alpha = G = 0, for which
+// every update below is the identity and every partial an exact zero.  State per pixel: T and B = the "colour behind" term
+// the NEXT contributor sees, B' = alpha c + (1 - alpha) B (upstream's accum_rec, evaluated one contributor earlier).
+__global__ void __launch_bounds__(128, MB_BWD2_CTAS_PER_SM) blend_backward2_kernel(
+    const Record *__restrict__ recs, const uint32_t *__restrict__ list, const uint2 *__restrict__ ranges,
+    const uint2 *__restrict__ items, const uint32_t *__restrict__ n_items, const uint32_t *__restrict__ tile_maxlast, int W, int H,
+    int gx, const float *__restrict__ bg, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
+    const float4 *__restrict__ ckpt, const float *__restrict__ dL_dout, int64_t sc, int64_t sy, int64_t sx,
+    float *__restrict__ acc) {
+    constexpr int kWarps = 4;
+    __shared__ __align__(128) StageSmem<kWarps> sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int item = blockIdx.x;
+    if ((uint32_t)item >= *n_items) return;
+    const uint2 it = items[item];
+    const int tile = (int)it.x;
+    const uint32_t s0 = it.y * (uint32_t)kSeg;
+    const uint32_t s1 = min(s0 + (uint32_t)kSeg, tile_maxlast[tile]);   // list positions [s0, s1) of this tile
+    const int len = (int)(s1 - s0);
+    const uint2 range = ranges[tile];
+    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 8 + (lane >> 3);   // pixel 0 inside the tile; pixel 1 is 4 rows below
+    const int px = (tile % gx) * kTile + lx, py = (tile / gx) * kTile + ly;
+    const float fx = (float)px;
+    const float2 nfy = make_float2(-(float)py, -(float)(py + 4));
+    const bool in0 = px < W && py < H, in1 = px < W && py + 4 < H;
+    const size_t pix0 = (size_t)py * W + px, pix1 = pix0 + 4 * (size_t)W;
+    const float2 T_final = make_float2(in0 ? final_T[pix0] : 0.f, in1 ? final_T[pix1] : 0.f);
+    const uint32_t last0 = in0 ? n_contrib[pix0] : 0u, last1 = in1 ? n_contrib[pix1] : 0u;
+    float2 dp0 = splat(0.f), dp1 = dp0, dp2 = dp0;
+    if (in0) {
+        const float *gp = dL_dout + (int64_t)py * sy + (int64_t)px * sx;
+        dp0.x = gp[0]; dp1.x = gp[sc]; dp2.x = gp[2 * sc];
+    }
+    if (in1) {
+        const float *gp = dL_dout + (int64_t)(py + 4) * sy + (int64_t)px * sx;
+        dp0.y = gp[0]; dp1.y = gp[sc]; dp2.y = gp[2 * sc];
+    }
+    const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
+    const float2 bg_dot = make_float2(b0 * dp0.x + b1 * dp1.x + b2 * dp2.x, b0 * dp0.y + b1 * dp1.y + b2 * dp2.y);
+    const float2 nTfbg = make_float2(-T_final.x * bg_dot.x, -T_final.y * bg_dot.y);   // (-T_final / (1 - alpha)) bg_dot = rinv * nTfbg
+    const int slot = reduce_slot(lane);
+    const float bcx = (float)(px - (lane & 7)) + 3.5f, bcy = (float)(py - (lane >> 3)) + 3.5f;   // centre of the warp's 8x8 block
+
+    float2 T = T_final, B0 = splat(0.f), B1 = B0, B2 = B0;
+    {   // contributions behind this segment: resume from the forward's state in front of position s1 (per pixel)
+        const uint32_t nseg_list = (range.y - range.x + (uint32_t)kSeg - 1u) / (uint32_t)kSeg;
+        const size_t ck_base = BinningState::ckpt_slot((uint32_t)tile, range.x, it.y) * kTilePixels;
+        const size_t fin_base = BinningState::ckpt_slot((uint32_t)tile, range.x, nseg_list - 1u) * kTilePixels;
+        // the forward indexes a tile's pixels by (8x4 block, lane)
+        const int idx0 = ((lx >> 3) + 2 * (ly >> 2)) * 32 + (lx & 7) + 8 * (ly & 3), idx1 = idx0 + 64;
+        if (last0 > s1) {
+            const float4 ck = ckpt[ck_base + idx0], fin = ckpt[fin_base + idx0];
+            const float inv = 1.0f / ck.x;
+            T.x = ck.x; B0.x = (fin.y - ck.y) * inv; B1.x = (fin.z - ck.z) * inv; B2.x = (fin.w - ck.w) * inv;
+        }
+        if (last1 > s1) {
+            const float4 ck = ckpt[ck_base + idx1], fin = ckpt[fin_base + idx1];
+            const float inv = 1.0f / ck.x;
+            T.y = ck.x; B0.y = (fin.y - ck.y) * inv; B1.y = (fin.z - ck.z) * inv; B2.y = (fin.w - ck.w) * inv;
+        }
+    }
+
+    ListStager<kWarps> st{sm, list, recs, range.x + s0, len, 0, true};
+    st.nb = (len + st.B - 1) / st.B;
+    st.prologue();
+
+    // nothing to do for this warp's pixels behind their deepest last contributor (positions relative to s0)
+    const uint32_t wlast_abs = __reduce_max_sync(0xffffffffu, max(last0, last1));
+    const int wlast = wlast_abs > s0 ? (int)min(wlast_abs - s0, (uint32_t)len) : 0;
+    const uint32_t lrel0 = last0 > s0 ? last0 - s0 : 0u, lrel1 = last1 > s0 ? last1 - s0 : 0u;
+    for (int i = 0; i < st.nb; ++i) {
+        st.advance(i);
+        const int cnt = st.count(i);
+        const float4 *r = st.records(i);
+        const int b = st.batch_of(i);
+        const uint32_t *ids = st.ids(i);
+        int jend = cnt;   // entries at or behind the warp's deepest last contributor cannot matter
+        if (b * st.B + cnt > wlast) jend = wlast - b * st.B;
+        for (int j0 = ((jend - 1) >> 5) << 5; j0 >= 0; j0 -= 32) {
+            bool hit = false;
+            if (j0 + lane < jend) {
+                const float4 ra = r[3 * (j0 + lane)], rc = r[3 * (j0 + lane) + 2];
+                hit = fabsf(ra.x - bcx) <= rc.z + 3.5f && fabsf(ra.y - bcy) <= rc.w + 3.5f;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {   // survivors back to front
+                const int k = 31 - __clz(m);
+                m &= ~(1u << k);
+                const int j = j0 + k;
+                const uint32_t pos = (uint32_t)(b * st.B + j);
+                const float4 ra = r[3 * j], rb = r[3 * j + 1];
+                const float2 rc = *reinterpret_cast<const float2 *>(&r[3 * j + 2]);
+                // power = -0.5 (conic.x dx^2 + conic.z dy^2) - conic.y dx dy ; dx is common to the pair
+                const float dx = ra.x - fx;
+                const float2 dy = __fadd2_rn(splat(ra.y), nfy);
+                const float hxx = (ra.z * dx) * dx, nbdx = -ra.w * dx;
+                const float2 sq = __ffma2_rn(__fmul2_rn(splat(rb.x), dy), dy, splat(hxx));
+                const float2 power = __ffma2_rn(splat(nbdx), dy, __fmul2_rn(sq, splat(-0.5f)));
+                const bool cand0 = (pos < lrel0) && (power.x <= 0.0f) && !(power.x < rc.y);
+                const bool cand1 = (pos < lrel1) && (power.y <= 0.0f) && !(power.y < rc.y);
+                if (!__any_sync(0xffffffffu, cand0 || cand1)) continue;
+                float2 G = exp_pair(power);
+                float2 alpha = __fmul2_rn(splat(rb.y), G);
+                alpha.x = fminf(kAlphaMax, alpha.x);
+                alpha.y = fminf(kAlphaMax, alpha.y);
+                const bool act0 = cand0 && (alpha.x >= kAlphaMin), act1 = cand1 && (alpha.y >= kAlphaMin);
+                // inactive pairs: alpha = G = 0 (G may be inf / NaN there: power > 0 is not excluded before the exponential)
+                G.x = act0 ? G.x : 0.f; alpha.x = act0 ? alpha.x : 0.f;
+                G.y = act1 ? G.y : 0.f; alpha.y = act1 ? alpha.y : 0.f;
+                const float2 om = __ffma2_rn(alpha, splat(-1.0f), splat(1.0f));   // 1 - alpha
+                const float2 rinv = make_float2(fast_rcp(om.x), fast_rcp(om.y));  // exactly 1 for an inactive pair
+                T = __fmul2_rn(T, rinv);
+                const float c0 = rb.z, c1 = rb.w, c2 = rc.x;
+                // dL/dalpha = ((c - B) . dL/dpixel) T + (-T_final / (1 - alpha)) (bg . dL/dpixel)
+                float2 dot = __fmul2_rn(__ffma2_rn(B0, splat(-1.0f), splat(c0)), dp0);
+                dot = __ffma2_rn(__ffma2_rn(B1, splat(-1.0f), splat(c1)), dp1, dot);
+                dot = __ffma2_rn(__ffma2_rn(B2, splat(-1.0f), splat(c2)), dp2, dot);
+                const float2 dL_dalpha = __ffma2_rn(dot, T, __fmul2_rn(rinv, nTfbg));
+                const float2 dch = __fmul2_rn(alpha, T);   // dL/dcolour weight: alpha * (T in front of this Gaussian)
+                B0 = __ffma2_rn(alpha, splat(c0), __fmul2_rn(om, B0));
+                B1 = __ffma2_rn(alpha, splat(c1), __fmul2_rn(om, B1));
+                B2 = __ffma2_rn(alpha, splat(c2), __fmul2_rn(om, B2));
+                // moments of q = G dL/dalpha (the 0.99 clamp is not masked: upstream behaviour)
+                const float2 q = __fmul2_rn(G, dL_dalpha);
+                const float2 qx = __fmul2_rn(q, splat(dx)), qy = __fmul2_rn(q, dy);
+                const float2 qxx = __fmul2_rn(qx, splat(dx)), qxy = __fmul2_rn(qx, dy), qyy = __fmul2_rn(qy, dy);
+                const float2 g0 = __fmul2_rn(dch, dp0), g1 = __fmul2_rn(dch, dp1), g2 = __fmul2_rn(dch, dp2);
+                float v[9];
+                v[0] = qx.x + qx.y; v[1] = qy.x + qy.y;
+                v[2] = qxx.x + qxx.y; v[3] = qxy.x + qxy.y; v[4] = qyy.x + qyy.y;
+                v[5] = q.x + q.y;
+                v[6] = g0.x + g0.y; v[7] = g1.x + g1.y; v[8] = g2.x + g2.y;
                 const float total = reduce_scatter9(v, lane);
                 if (slot >= 0) red_add(acc + (size_t)ids[j] * kAccStride + slot, total);
             }
@@ -452,6 +615,7 @@ struct PreBwdArgs {
     const float *means3D, *cov3D, *scales, *rots, *shs, *view, *proj, *campos, *tanfov_dev;
     const int32_t *radii;
     const uint32_t *clamped;
+    const Record *rec;     // the forward's blend records (opacity as the forward used it)
     const float *acc;
     float *dL_dmeans2D, *dL_dcolors, *dL_dopacity, *dL_dmeans3D, *dL_dcov3D, *dL_dsh, *dL_dscales, *dL_drots;
 };
@@ -477,11 +641,11 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(PreBwdArgs a) 
     const float mx = a.means3D[3 * i], my = a.means3D[3 * i + 1], mz = a.means3D[3 * i + 2];
     if (vis) {
         const float *ac = a.acc + (size_t)i * kAccStride;
-        g2x = ac[0]; g2y = ac[1];
-        const float gx = ac[2], gy = ac[3], gz = ac[4];
         gop = ac[5]; gc[0] = ac[6]; gc[1] = ac[7]; gc[2] = ac[8];
         const float *c6 = a.cov3D + 6 * (size_t)i;
-        project_backward(v, p, a.tanx, a.tany, a.focx, a.focy, mx, my, mz, c6, gx, gy, gz, g2x, g2y, gmean, gcov);
+        float g2[2];
+        project_backward(v, p, a.tanx, a.tany, a.focx, a.focy, a.W, a.H, mx, my, mz, c6, a.rec[i].b.y, ac, g2, gmean, gcov);
+        g2x = g2[0]; g2y = g2[1];
 
         if (kSH) {
             float dx = mx - cam[32], dy = my - cam[33], dz = mz - cam[34];
@@ -566,6 +730,16 @@ static int blend_warps() {
         const char *e = getenv("MB_BLEND_WARPS");
         const int v = e ? atoi(e) : 4;
         cached = (v == 8 || v == 2) ? v : 4;
+    }
+    return cached;
+}
+
+// backward kernel: 2 = two pixels per lane with packed fp32x2 arithmetic (default), 1 = one pixel per lane (MB_BLEND_WARPS shape)
+static int backward_impl() {
+    static int cached = 0;
+    if (!cached) {
+        const char *e = getenv("MB_BWD_IMPL");
+        cached = (e && atoi(e) == 1) ? 1 : 2;
     }
     return cached;
 }
@@ -674,7 +848,11 @@ static int raster_backward_impl(const mb_raster_inputs *in, const int32_t *radii
             // upper bound of the item count (the real one is on the device; surplus CTAs exit at once)
             const int64_t bound = (int64_t)d.tiles + capacity / kSeg + 1;
             const int64_t max_items = bound < b.max_items ? bound : b.max_items;
-            if (blend_warps() == 4)
+            if (backward_impl() == 2)
+                blend_backward2_kernel<<<(unsigned)max_items, 128, 0, s>>>(g.rec, b.gid_b, im.ranges, b.bwd_items, n_items, im.tile_maxlast,
+                                                                          d.W, d.H, d.gx, in->background, im.final_T, im.n_contrib, b.ckpt,
+                                                                          dL_dout, stride_c, stride_y, stride_x, acc);
+            else if (blend_warps() == 4)
                 blend_backward_kernel<4><<<(unsigned)(max_items * 2), 128, 0, s>>>(g.rec, b.gid_b, im.ranges, b.bwd_items, n_items,
                                                                                  im.tile_maxlast, d.W, d.H, d.gx, in->background, im.final_T,
                                                                                  im.n_contrib, b.ckpt, dL_dout, stride_c, stride_y, stride_x, acc);
@@ -697,7 +875,7 @@ static int raster_backward_impl(const mb_raster_inputs *in, const int32_t *radii
     a.means3D = in->means3D; a.cov3D = in->cov3D_precomp ? in->cov3D_precomp : g.cov3D; a.scales = in->scales;
     a.rots = in->rotations; a.shs = in->shs; a.view = in->viewmatrix; a.proj = in->projmatrix; a.campos = in->campos;
     a.tanfov_dev = in->tanfov_dev;
-    a.radii = radii; a.clamped = g.clamped; a.acc = acc;
+    a.radii = radii; a.clamped = g.clamped; a.rec = g.rec; a.acc = acc;
     a.dL_dmeans2D = dL_dmeans2D; a.dL_dcolors = dL_dcolors; a.dL_dopacity = dL_dopacity; a.dL_dmeans3D = dL_dmeans3D;
     a.dL_dcov3D = dL_dcov3D; a.dL_dsh = dL_dsh; a.dL_dscales = dL_dscales; a.dL_drots = dL_drotations;
     const int grid = (d.P + 255) / 256;
