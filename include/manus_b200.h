@@ -50,6 +50,10 @@ int mb_device_sm_count(void);    /* SM count of the current device (148 on B200)
  * since the last report into buf (NUL terminated, truncated to cap). */
 void mb_profile_enable(int on);
 int mb_profile_report(char *buf, size_t cap);
+/* One line "kernel_name stream start_us duration_us" per recorded launch, relative to the earliest start; the record is kept.
+ * Launches recorded while a stream capture was active are event-record nodes of that graph and are re-recorded by every
+ * replay: the timeline of a replayed multi-branch step (which kernels of which view overlap). */
+int mb_profile_timeline(char *buf, size_t cap);
 
 /* ------------------------------------------------------------------------------------------------
  * Rasterizer.  Mirrors RasterizeGaussiansCUDA / RasterizeGaussiansBackwardCUDA / markVisible of the upstream
@@ -158,11 +162,26 @@ typedef struct mb_pose_inputs {
     const float *skin_wts;      /* [num_skinned,B] or NULL when num_skinned == 0 */
     const float *bone_tf;       /* [B,4,4] */
     const float *campos;        /* [3] */
+    /* Optional: build the bone transforms inside the kernels (hand_dynamic.py:93-102) instead of passing bone_tf:
+     * T_b = bones_posed[b] * bones_rest_inv[b] for b < num_posed_bones, identity for the other rows.  NULL = use bone_tf. */
+    const float *bones_posed;    /* [num_posed_bones,4,4] */
+    const float *bones_rest_inv; /* [num_posed_bones,4,4] inverse rest-pose transforms (constant per subject) */
+    int32_t num_posed_bones;
+    int32_t reserved_;
 } mb_pose_inputs;
 
 /* tf_out: optional [num_skinned,4,4] (the reference materialises it; the fused path does not need it). */
 int mb_pose_forward(const mb_pose_inputs *in, float *posed_xyz /*[N,3]*/, float *posed_cov6 /*[N,6]*/,
                     float *colors /*[N,3]*/, float *opacity /*[N]*/, float *tf_out, mb_stream_t stream);
+
+/* mb_pose_forward + the rasterizer's per-Gaussian forward (= mb_raster_forward_geom on the posed arrays) in one kernel: the
+ * projection (A.1) runs on the posed mean / covariance / colour / opacity while they are in registers; geom / radii /
+ * num_rendered_host exactly as mb_raster_forward_geom leaves them.  posed_xyz / posed_cov6 / colors / opacity are optional
+ * (NULL: they never touch HBM; the fused backward mb_pose_backward_from_raster recomputes what it needs).  `raster` carries
+ * the camera and image size (its per-Gaussian pointers are not read); continue with mb_raster_forward_render. */
+int mb_pose_project_forward(const mb_pose_inputs *in, const mb_raster_inputs *raster, void *geom, size_t geom_bytes, int32_t *radii,
+                            int64_t *num_rendered_host, float *posed_xyz, float *posed_cov6, float *colors, float *opacity,
+                            mb_stream_t stream);
 
 /* g_skin_wts: optional [num_skinned,B].  g_f_rest: optional (see mb_sh_grad_from_views).  All other outputs are required and
  * fully written. */

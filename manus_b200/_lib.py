@@ -36,6 +36,7 @@ class PoseInputs(C.Structure):
         ("sh_coeffs", C.c_int32), ("isotropic", C.c_int32),
         ("xyz", C.c_void_p), ("log_scale", C.c_void_p), ("quat", C.c_void_p), ("opacity_logit", C.c_void_p),
         ("f_dc", C.c_void_p), ("f_rest", C.c_void_p), ("skin_wts", C.c_void_p), ("bone_tf", C.c_void_p), ("campos", C.c_void_p),
+        ("bones_posed", C.c_void_p), ("bones_rest_inv", C.c_void_p), ("num_posed_bones", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -46,6 +47,7 @@ SIGNATURES = {
     "mb_device_sm_count": (C.c_int, []),
     "mb_profile_enable": (None, [C.c_int]),
     "mb_profile_report": (C.c_int, [C.c_char_p, C.c_size_t]),
+    "mb_profile_timeline": (C.c_int, [C.c_char_p, C.c_size_t]),
     "mb_raster_geom_bytes": (C.c_size_t, [C.c_int32]),
     "mb_raster_binning_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "mb_raster_image_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
@@ -59,6 +61,8 @@ SIGNATURES = {
     "mb_raster_state_layout": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, i64p, C.c_int32]),
     "mb_mark_visible": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mb_pose_forward": (C.c_int, [C.POINTER(PoseInputs)] + [C.c_void_p] * 5 + [C.c_void_p]),
+    "mb_pose_project_forward": (C.c_int, [C.POINTER(PoseInputs), C.POINTER(RasterInputs), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p] +
+                                [C.c_void_p] * 4 + [C.c_void_p]),
     "mb_pose_backward": (C.c_int, [C.POINTER(PoseInputs)] + [C.c_void_p] * 4 + [C.c_void_p] * 7 + [C.c_void_p]),
     "mb_pose_backward_from_raster": (C.c_int, [C.POINTER(PoseInputs), C.POINTER(RasterInputs), C.c_void_p, C.c_void_p, C.c_void_p] +
                                      [C.c_void_p] * 7 + [C.c_int32, C.c_void_p]),
@@ -122,6 +126,17 @@ def ptr(t):
 
 def profile_enable(on: bool) -> None:
     lib().mb_profile_enable(int(on))
+
+
+def profile_timeline() -> list:
+    """[(kernel, stream, start_us, duration_us)] of the recorded launches (synchronises the device; the record is kept)."""
+    buf = C.create_string_buffer(1 << 20)
+    check(lib().mb_profile_timeline(buf, len(buf)), "mb_profile_timeline")
+    out = []
+    for line in buf.value.decode().splitlines():
+        name, sid, st, du = line.rsplit(" ", 3)
+        out.append((name, int(sid), float(st), float(du)))
+    return out
 
 
 def profile_report() -> dict:

@@ -45,7 +45,7 @@ int sm_count() {
 
 
 // ---- per-kernel event timing ---------------------------------------------------------------------------
-struct TimedLaunch { const char *name; cudaEvent_t start, stop; };
+struct TimedLaunch { const char *name; cudaEvent_t start, stop; unsigned flags; cudaStream_t stream; };
 static bool g_profile = false;
 static std::mutex g_profile_mu;
 static std::vector<TimedLaunch> g_launches;
@@ -63,7 +63,13 @@ KernelTimer::KernelTimer(const char *name, cudaStream_t s) : slot(-1), stream(s)
     } else if (cudaEventCreate(&t.start) != cudaSuccess || cudaEventCreate(&t.stop) != cudaSuccess) {
         return;
     }
-    cudaEventRecord(t.start, s);
+    // inside a stream capture the records must become event-record NODES of the graph (cudaEventRecordExternal): then every
+    // replay re-records them and mb_profile_timeline shows when each kernel of the replayed graph ran
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s, &cap);
+    t.flags = cap == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault;
+    t.stream = s;
+    cudaEventRecordWithFlags(t.start, s, t.flags);
     g_launches.push_back(t);
     slot = (int)g_launches.size() - 1;
 }
@@ -71,7 +77,7 @@ KernelTimer::KernelTimer(const char *name, cudaStream_t s) : slot(-1), stream(s)
 KernelTimer::~KernelTimer() {
     if (slot < 0) return;
     std::lock_guard<std::mutex> lk(g_profile_mu);
-    if (slot < (int)g_launches.size()) cudaEventRecord(g_launches[slot].stop, stream);
+    if (slot < (int)g_launches.size()) cudaEventRecordWithFlags(g_launches[slot].stop, stream, g_launches[slot].flags);
 }
 
 }  // namespace mb
@@ -101,6 +107,40 @@ extern "C" int mb_profile_report(char *buf, size_t cap) {
     for (auto &kv : acc) {
         int n = snprintf(buf ? buf + off : nullptr, buf && cap > off ? cap - off : 0, "%s %d %.6f\n", kv.first.c_str(), kv.second.first,
                          kv.second.second);
+        if (n < 0) break;
+        off += (size_t)n;
+        if (off >= cap) break;
+    }
+    return MB_OK;
+}
+
+// Synchronises the device and writes one line "name stream start_us duration_us" per recorded launch (times relative to the
+// earliest start), WITHOUT clearing the record: launches recorded during a graph capture are re-recorded by every replay.
+extern "C" int mb_profile_timeline(char *buf, size_t cap) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return MB_ERR_CUDA;
+    std::lock_guard<std::mutex> lk(mb::g_profile_mu);
+    if (buf && cap) buf[0] = 0;
+    if (mb::g_launches.empty()) return MB_OK;
+    const cudaEvent_t ref = mb::g_launches[0].start;
+    std::vector<float> st(mb::g_launches.size(), 0.f), du(mb::g_launches.size(), -1.f);
+    float t_min = 0.f;
+    for (size_t i = 0; i < mb::g_launches.size(); ++i) {
+        float a = 0.f, d = 0.f;
+        if (cudaEventElapsedTime(&a, ref, mb::g_launches[i].start) != cudaSuccess ||
+            cudaEventElapsedTime(&d, mb::g_launches[i].start, mb::g_launches[i].stop) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        st[i] = a; du[i] = d;
+        if (a < t_min) t_min = a;
+    }
+    std::map<cudaStream_t, int> ids;
+    size_t off = 0;
+    for (size_t i = 0; i < mb::g_launches.size(); ++i) {
+        if (du[i] < 0.f) continue;
+        const int sid = ids.emplace(mb::g_launches[i].stream, (int)ids.size()).first->second;
+        int n = snprintf(buf ? buf + off : nullptr, buf && cap > off ? cap - off : 0, "%s %d %.3f %.3f\n", mb::g_launches[i].name, sid,
+                         (st[i] - t_min) * 1e3f, du[i] * 1e3f);
         if (n < 0) break;
         off += (size_t)n;
         if (off >= cap) break;

@@ -19,6 +19,8 @@
 
 #include "common.cuh"
 #include "project_bwd.cuh"
+#include "project_fwd.cuh"
+#include "sort_scan.cuh"
 
 namespace mb {
 
@@ -47,6 +49,17 @@ struct PoseArgs {
     float tanx, tany;
     int W, H;
     float *g_means2D;          // [N,3] out: (dL/dmean2D x, y, 0)
+    // bone transforms built in the kernel prologue: T_b = bones_posed[b] * rest_inv[b] for b < n_posed, identity for the
+    // other B - n_posed rows (hand_dynamic.py:93-102); nullptr = take bone_tf as given
+    const float *bones_posed, *rest_inv;
+    int n_posed;
+    // forward fused with the rasterizer's projection (mb_pose_project_forward): record, radius, tile rectangle, depth key of
+    // every Gaussian are written from registers, the posed arrays only if their pointers are given
+    Record *rec;               // nullptr = plain pose forward
+    ushort4 *rect;
+    uint32_t *tiles_touched, *depth_key, *ident, *counters;
+    int32_t *radii_out;
+    int gx, gy;
 };
 
 constexpr int kAccRow = 12;          // floats per accumulator row (kAccStride of raster_blend.cu)
@@ -235,10 +248,11 @@ struct TilePipe {
         const int rs = (a.K - 1) * 3, lsw = a.iso ? 1 : 3;
         int n = 0;
         if (!kBackward) {
-            t[n++] = {a.posed_xyz + (size_t)base * 3, L.xyz, (uint32_t)(cnt * 12)};
-            t[n++] = {a.cov6 + (size_t)base * 6, L.cov, (uint32_t)(cnt * 24)};
-            t[n++] = {a.colors + (size_t)base * 3, L.fdc, (uint32_t)(cnt * 12)};
-            t[n++] = {a.opacity + base, L.opac, (uint32_t)(cnt * 4)};
+            // (the projecting forward may leave the posed arrays out: they then never touch HBM)
+            t[n++] = {a.posed_xyz ? a.posed_xyz + (size_t)base * 3 : nullptr, L.xyz, (uint32_t)(a.posed_xyz ? cnt * 12 : 0)};
+            t[n++] = {a.cov6 ? a.cov6 + (size_t)base * 6 : nullptr, L.cov, (uint32_t)(a.cov6 ? cnt * 24 : 0)};
+            t[n++] = {a.colors ? a.colors + (size_t)base * 3 : nullptr, L.fdc, (uint32_t)(a.colors ? cnt * 12 : 0)};
+            t[n++] = {a.opacity ? a.opacity + base : nullptr, L.opac, (uint32_t)(a.opacity ? cnt * 4 : 0)};
         } else {
             t[n++] = {a.g_f_rest ? a.g_f_rest + (size_t)base * rs : nullptr, L.fr, (uint32_t)(a.g_f_rest && rs > 0 ? cnt * rs * 4 : 0)};
             t[n++] = {a.g_skin ? a.g_skin + (size_t)base * a.B : nullptr, L.sk, (uint32_t)(a.g_skin ? nsk * a.B * 4 : 0)};
@@ -314,13 +328,19 @@ struct TilePipe {
     }
 };
 
-template <bool kBackward, bool kFused = false, typename Body>
-__device__ __forceinline__ void run_tiles(const PoseArgs &a, float *smem, Body body) {
+struct NoPost {
+    __device__ __forceinline__ void operator()(int) const {}
+};
+
+// body(L, stage, i, row, bones, cam) runs for every Gaussian of the tile; post(tile) runs once per tile on ALL threads after it
+// (warp-collective work: the body is skipped by the threads past the end of the last tile)
+template <bool kBackward, bool kFused = false, typename Body, typename Post = NoPost>
+__device__ __forceinline__ void run_tiles(const PoseArgs &a, float *smem, Body body, Post post = Post()) {
     float *bones_s = smem, *cam_s = bones_s + kMaxBones * 13;
     uint64_t *bar = reinterpret_cast<uint64_t *>(cam_s + 4);
     float *rcam_s = cam_s + 8;      // fused backward: view | proj | tanx, tany, focx, focy
     TilePipe<kBackward, kFused> pipe{a, tile_layout(a.K, a.B, a.iso, kBackward), rcam_s + kCamFloats, bar};
-    if (kBackward && kFused) {
+    if (kFused) {
         if (threadIdx.x < 16) rcam_s[threadIdx.x] = a.view[threadIdx.x];
         else if (threadIdx.x < 32) rcam_s[threadIdx.x] = a.proj[threadIdx.x - 16];
         else if (threadIdx.x == 32) {
@@ -330,8 +350,14 @@ __device__ __forceinline__ void run_tiles(const PoseArgs &a, float *smem, Body b
         }
     }
     for (int j = threadIdx.x; j < a.B * 13; j += kPoseThreads) {
-        const int b = j / 13, e = j - 13 * b;
-        bones_s[j] = a.bone_tf[16 * b + (e < 12 ? e : 15)];
+        const int b = j / 13, e = j - 13 * b, idx = e < 12 ? e : 15;
+        if (a.bones_posed == nullptr) bones_s[j] = a.bone_tf[16 * b + idx];
+        else if (b >= a.n_posed) bones_s[j] = (idx % 5 == 0) ? 1.f : 0.f;      // appended identity rows
+        else {      // element (r, c) of bones_posed[b] * rest_inv[b]
+            const int r = idx >> 2, c = idx & 3;
+            const float *P = a.bones_posed + 16 * b + 4 * r, *R = a.rest_inv + 16 * b + c;
+            bones_s[j] = fmaf(P[3], R[12], fmaf(P[2], R[8], fmaf(P[1], R[4], P[0] * R[0])));
+        }
     }
     if (threadIdx.x < 3) cam_s[threadIdx.x] = a.campos[threadIdx.x];
     if (threadIdx.x == 0) {
@@ -374,16 +400,21 @@ __device__ __forceinline__ void run_tiles(const PoseArgs &a, float *smem, Body b
 #ifndef MB_POSE_NOCOMPUTE   // experiment switch (tools/pose_bench.py): data movement only
         if (i < a.N) body(pipe.L, pipe.stage(0), i, row, bones_s, cam_s);
 #endif
+        post(tile);
         pipe.release(tile, 0);
     }
     if (threadIdx.x == 0) bulk_wait_all();
 }
 
-template <int DEG>
+// kProject: the rasterizer's projection (A.1) runs on the posed mean / covariance / colour / opacity while they are in
+// registers (mb_pose_project_forward): the 52 B per Gaussian between the two stages need not cross HBM, one launch less
+template <int DEG, bool kProject>
 __global__ void __launch_bounds__(kPoseThreads) pose_forward_kernel(PoseArgs a) {
     extern __shared__ __align__(128) float smem[];
     constexpr int nb = (DEG + 1) * (DEG + 1);
-    run_tiles<false>(a, smem, [&](const TileLayout &L, float *st, int i, int row, const float *bones_s, const float *cam_s) {
+    bool visible = false;        // of this thread's Gaussian in the current tile (kProject)
+    uint32_t my_tiles = 0;
+    run_tiles<false, kProject>(a, smem, [&](const TileLayout &L, float *st, int i, int row, const float *bones_s, const float *cam_s) {
         PoseLocal p;
         pose_common(a, L, st, i, row, bones_s, p);
         // mean
@@ -440,7 +471,34 @@ __global__ void __launch_bounds__(kPoseThreads) pose_forward_kernel(PoseArgs a) 
         }
 #pragma unroll
         for (int k = 0; k < 6; ++k) st[L.cov + 6 * row + k] = c6[k];
-        st[L.opac + row] = 1.0f / (1.0f + expf(-ol));
+        const float op = 1.0f / (1.0f + expf(-ol));
+        st[L.opac + row] = op;
+        if (kProject) {
+            const float *rc = cam_s + 8;      // view | proj | tanx, tany, focx, focy
+            Projected pr;
+            project_forward(rc, rc + 16, rc[32], rc[33], rc[34], rc[35], a.W, a.H, a.gx, a.gy, px[0], px[1], px[2], c6, op, rgb, pr);
+            visible = pr.visible;
+            my_tiles = pr.tiles;
+            if (pr.visible) {
+                a.rect[i] = pr.rect;
+                a.rec[i] = pr.rec;
+            }
+            a.radii_out[i] = pr.radius;
+            a.tiles_touched[i] = pr.tiles;
+            a.depth_key[i] = pr.key;
+            a.ident[i] = (uint32_t)i;
+        }
+    }, [&](int) {
+        if (kProject) {      // per-warp totals of the tile: visible Gaussians and instances (num_rendered)
+            const unsigned vis = __ballot_sync(0xffffffffu, visible);
+            const uint32_t wt = __reduce_add_sync(0xffffffffu, my_tiles);
+            if ((threadIdx.x & 31) == 0 && vis) {
+                atomicAdd(&a.counters[kCntVisible], (uint32_t)__popc(vis));
+                atomicAdd(&a.counters[kCntRendered], wt);
+            }
+            visible = false;
+            my_tiles = 0;
+        }
     });
 }
 
@@ -728,7 +786,9 @@ static int validate_pose(const mb_pose_inputs *in, const char *who) {
     MB_REQUIRE(in->xyz && in->log_scale && in->quat && in->opacity_logit && in->f_dc && in->campos, "%s: null parameter tensor", who);
     MB_REQUIRE(in->sh_coeffs == 1 || in->f_rest, "%s: f_rest missing", who);
     if (in->num_skinned > 0) {
-        MB_REQUIRE(in->skin_wts && in->bone_tf, "%s: skin_wts / bone_tf missing", who);
+        MB_REQUIRE(in->skin_wts && (in->bone_tf || (in->bones_posed && in->bones_rest_inv)), "%s: skin_wts / bone_tf missing", who);
+        MB_REQUIRE(!in->bones_posed || (in->bones_rest_inv && in->num_posed_bones >= 0 && in->num_posed_bones <= in->num_bones),
+                   "%s: bones_posed needs bones_rest_inv and 0 <= num_posed_bones <= num_bones", who);
         MB_REQUIRE(in->num_bones > 0 && in->num_bones <= kMaxBones, "%s: num_bones %d not in 1..%d", who, in->num_bones, kMaxBones);
     }
     return MB_OK;
@@ -740,6 +800,7 @@ static PoseArgs pose_args(const mb_pose_inputs *in) {
     a.deg = in->sh_degree; a.K = in->sh_coeffs; a.iso = in->isotropic;
     a.xyz = in->xyz; a.log_scale = in->log_scale; a.quat = in->quat; a.opacity_logit = in->opacity_logit;
     a.f_dc = in->f_dc; a.f_rest = in->f_rest; a.skin = in->skin_wts; a.bone_tf = in->bone_tf; a.campos = in->campos;
+    a.bones_posed = in->bones_posed; a.rest_inv = in->bones_rest_inv; a.n_posed = in->num_posed_bones;
     return a;
 }
 
@@ -764,7 +825,10 @@ static int launch_pose(PoseArgs a, bool backward, cudaStream_t s) {
         if (backward) {
             MB_CUDA(cudaFuncSetAttribute(pose_backward_kernel<DEG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             MB_CUDA(cudaFuncSetAttribute(pose_backward_kernel<DEG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        } else MB_CUDA(cudaFuncSetAttribute(pose_forward_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        } else {
+            MB_CUDA(cudaFuncSetAttribute(pose_forward_kernel<DEG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MB_CUDA(cudaFuncSetAttribute(pose_forward_kernel<DEG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
         cur = (int)smem;
     }
     if (backward) {
@@ -773,7 +837,8 @@ static int launch_pose(PoseArgs a, bool backward, cudaStream_t s) {
         else pose_backward_kernel<DEG, false><<<grid, kPoseThreads, smem, s>>>(a);
     } else {
         KernelTimer kt("pose_forward", s);
-        pose_forward_kernel<DEG><<<grid, kPoseThreads, smem, s>>>(a);
+        if (a.rec) pose_forward_kernel<DEG, true><<<grid, kPoseThreads, smem, s>>>(a);
+        else pose_forward_kernel<DEG, false><<<grid, kPoseThreads, smem, s>>>(a);
     }
     return check_launch(backward ? "pose_backward" : "pose_forward", false, s);
 }
@@ -800,6 +865,46 @@ extern "C" int mb_pose_forward(const mb_pose_inputs *in, float *posed_xyz, float
     PoseArgs a = pose_args(in);
     a.posed_xyz = posed_xyz; a.cov6 = posed_cov6; a.colors = colors; a.opacity = opacity; a.tf_out = tf_out;
     return launch_pose_deg(a, false, (cudaStream_t)stream);
+}
+
+extern "C" int mb_pose_project_forward(const mb_pose_inputs *in, const mb_raster_inputs *raster, void *geom, size_t geom_bytes,
+                                       int32_t *radii, int64_t *num_rendered_host, float *posed_xyz, float *posed_cov6, float *colors,
+                                       float *opacity, mb_stream_t stream) {
+    int rc = validate_pose(in, "mb_pose_project_forward");
+    if (rc) return rc;
+    MB_REQUIRE(raster != nullptr && raster->num_points == in->num_points, "mb_pose_project_forward: raster inputs missing or of another size");
+    MB_REQUIRE(raster->viewmatrix && raster->projmatrix && raster->image_width > 0 && raster->image_height > 0 &&
+                   (raster->tanfov_dev || (raster->tanfovx > 0.f && raster->tanfovy > 0.f)),
+               "mb_pose_project_forward: camera missing");
+    MB_REQUIRE(raster->scale_modifier == 1.0f && raster->shs == nullptr, "mb_pose_project_forward: scale_modifier must be 1, colours come from the pose step");
+    cudaStream_t s = (cudaStream_t)stream;
+    const RasterDims d = raster_dims(raster);
+    MB_REQUIRE(geom != nullptr && (d.P == 0 || radii != nullptr), "mb_pose_project_forward: null geom / radii");
+    GeomState g = GeomState::carve(geom, d.P);
+    if (geom_bytes < g.bytes) {
+        set_error("mb_pose_project_forward: geom buffer has %zu bytes, needs %zu", geom_bytes, g.bytes);
+        return MB_ERR_WORKSPACE;
+    }
+    // counters + look-back words of the instance-offset scan (contiguous), as mb_raster_forward_geom
+    MB_CUDA(cudaMemsetAsync(g.counters, 0, (size_t)((char *)(g.scan_status + (d.P + 255) / 256 + 1) - (char *)g.counters), s));
+    if (d.P > 0) {
+        PoseArgs a = pose_args(in);
+        a.posed_xyz = posed_xyz; a.cov6 = posed_cov6; a.colors = colors; a.opacity = opacity;
+        a.view = raster->viewmatrix; a.proj = raster->projmatrix; a.tanfov_dev = raster->tanfov_dev;
+        a.tanx = raster->tanfovx; a.tany = raster->tanfovy; a.W = d.W; a.H = d.H; a.gx = d.gx; a.gy = d.gy;
+        a.rec = g.rec; a.rect = g.rect; a.tiles_touched = g.tiles_touched; a.depth_key = g.depth_key; a.ident = g.ident;
+        a.counters = g.counters; a.radii_out = radii;
+        rc = launch_pose_deg(a, false, s);
+        if (rc) return rc;
+        SortWorkspace ws = carve_sort_workspace(g.sort_ws, d.P);
+        rc = radix_sort_pairs(g.depth_key, g.ident, g.sorted_key, g.sorted_idx, d.P, nullptr, d.P, 0, 32, ws, s, raster->debug != 0);
+        if (rc) return rc;
+    }
+    if (num_rendered_host) {
+        *num_rendered_host = 0;
+        MB_CUDA(cudaMemcpyAsync(num_rendered_host, g.counters + kCntRendered, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    }
+    return MB_OK;
 }
 
 static int pose_backward_impl(const mb_pose_inputs *in, const float *g_posed_xyz, const float *g_posed_cov6,
@@ -839,7 +944,7 @@ extern "C" int mb_pose_backward_from_raster(const mb_pose_inputs *in, const mb_r
     MB_REQUIRE(raster->viewmatrix && raster->projmatrix && raster->image_width > 0 && raster->image_height > 0 &&
                    (raster->tanfov_dev || (raster->tanfovx > 0.f && raster->tanfovy > 0.f)),
                "mb_pose_backward_from_raster: camera missing");
-    MB_REQUIRE(raster->colors_precomp && raster->cov3D_precomp && raster->scale_modifier == 1.0f,
+    MB_REQUIRE(raster->shs == nullptr && raster->scales == nullptr && raster->scale_modifier == 1.0f,
                "mb_pose_backward_from_raster: the rasterizer must have run on this pose's colours and covariances (scale_modifier 1)");
     MB_REQUIRE(radii && grad_scratch && dL_dmeans2D, "mb_pose_backward_from_raster: null radii / accumulator / dL_dmeans2D");
     MB_REQUIRE(g_xyz && g_log_scale && g_quat && g_opacity_logit && g_f_dc, "mb_pose_backward_from_raster: null output");

@@ -462,6 +462,12 @@ __device__ __forceinline__ float2 exp_pair(float2 x) {
     return __ffma2_rn(e, __fmul2_rn(r, splat(ln2)), e);
 }
 
+struct SegmentSmem {
+    Record rec[kSeg];          // the segment's records, list order
+    uint32_t ids[kSeg + 4];    // the segment's slice of the id list (16-B aligned source => up to 3 ids of slack in front)
+    uint64_t bar;
+};
+
 #ifndef MB_BWD2_CTAS_PER_SM
 #define MB_BWD2_CTAS_PER_SM 8
 #endif
@@ -478,11 +484,11 @@ __global__ void __launch_bounds__(128, MB_BWD2_CTAS_PER_SM) blend_backward2_kern
     int gx, const float *__restrict__ bg, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
     const float4 *__restrict__ ckpt, const float *__restrict__ dL_dout, int64_t sc, int64_t sy, int64_t sx,
     float *__restrict__ acc) {
-    constexpr int kWarps = 4;
-    __shared__ __align__(128) StageSmem<kWarps> sm;
+    __shared__ __align__(128) SegmentSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int item = blockIdx.x;
     if ((uint32_t)item >= *n_items) return;
+    MB_TRACE_BEGIN();
     const uint2 it = items[item];
     const int tile = (int)it.x;
     const uint32_t s0 = it.y * (uint32_t)kSeg;
@@ -531,22 +537,38 @@ __global__ void __launch_bounds__(128, MB_BWD2_CTAS_PER_SM) blend_backward2_kern
         }
     }
 
-    ListStager<kWarps> st{sm, list, recs, range.x + s0, len, 0, true};
-    st.nb = (len + st.B - 1) / st.B;
-    st.prologue();
+    // The whole segment is staged at once: ids by one bulk (TMA) copy, then every thread gathers the records of up to
+    // kSeg / 128 entries (three 128-bit cp.async each, L2 hits).  One barrier; after it the four warps walk the segment
+    // independently (their 8x8 blocks keep different survivors, a per-batch barrier made them wait for the slowest).
+    const uint32_t first = range.x + s0, o = first & 3u;
+    if (tid == 0) {
+        mbar_init(&sm.bar, 1);
+        mbar_fence_init();
+        const uint32_t bytes = ((o + (uint32_t)len) * 4u + 15u) & ~15u;
+        mbar_expect_tx(&sm.bar, bytes);
+        bulk_g2s(&sm.ids[0], list + (first - o), bytes, &sm.bar);
+    }
+    __syncthreads();
+    mbar_wait(&sm.bar, 0u);
+    const uint32_t *ids = &sm.ids[o];
+    for (int e = tid; e < len; e += 128) {
+        const char *src = reinterpret_cast<const char *>(recs + ids[e]);
+        char *dst = reinterpret_cast<char *>(&sm.rec[e]);
+        cp_async16(dst, src);
+        cp_async16(dst + 16, src + 16);
+        cp_async16(dst + 32, src + 32);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    const float4 *r = reinterpret_cast<const float4 *>(&sm.rec[0]);
 
     // nothing to do for this warp's pixels behind their deepest last contributor (positions relative to s0)
     const uint32_t wlast_abs = __reduce_max_sync(0xffffffffu, max(last0, last1));
     const int wlast = wlast_abs > s0 ? (int)min(wlast_abs - s0, (uint32_t)len) : 0;
     const uint32_t lrel0 = last0 > s0 ? last0 - s0 : 0u, lrel1 = last1 > s0 ? last1 - s0 : 0u;
-    for (int i = 0; i < st.nb; ++i) {
-        st.advance(i);
-        const int cnt = st.count(i);
-        const float4 *r = st.records(i);
-        const int b = st.batch_of(i);
-        const uint32_t *ids = st.ids(i);
-        int jend = cnt;   // entries at or behind the warp's deepest last contributor cannot matter
-        if (b * st.B + cnt > wlast) jend = wlast - b * st.B;
+    {
+        const int jend = wlast;   // entries at or behind the warp's deepest last contributor cannot matter
         for (int j0 = ((jend - 1) >> 5) << 5; j0 >= 0; j0 -= 32) {
             bool hit = false;
             if (j0 + lane < jend) {
@@ -558,7 +580,7 @@ __global__ void __launch_bounds__(128, MB_BWD2_CTAS_PER_SM) blend_backward2_kern
                 const int k = 31 - __clz(m);
                 m &= ~(1u << k);
                 const int j = j0 + k;
-                const uint32_t pos = (uint32_t)(b * st.B + j);
+                const uint32_t pos = (uint32_t)j;
                 const float4 ra = r[3 * j], rb = r[3 * j + 1];
                 const float2 rc = *reinterpret_cast<const float2 *>(&r[3 * j + 2]);
                 // power = -0.5 (conic.x dx^2 + conic.z dy^2) - conic.y dx dy ; dx is common to the pair
@@ -605,8 +627,8 @@ __global__ void __launch_bounds__(128, MB_BWD2_CTAS_PER_SM) blend_backward2_kern
                 if (slot >= 0) red_add(acc + (size_t)ids[j] * kAccStride + slot, total);
             }
         }
-        __syncthreads();   // this batch's buffers may be overwritten by the copies issued in the next step
     }
+    MB_TRACE_END(1, len);
 }
 
 struct PreBwdArgs {
@@ -767,7 +789,7 @@ extern "C" int mb_raster_state_layout(int32_t num_points, int64_t capacity, int3
 extern "C" int mb_raster_forward_render(const mb_raster_inputs *in, void *geom, void *binning, size_t binning_bytes,
                                         int64_t capacity, void *image_buf, size_t image_bytes, float *out_color,
                                         mb_stream_t stream) {
-    int rc = validate_raster_inputs(in, "mb_raster_forward_render");
+    int rc = validate_raster_inputs(in, "mb_raster_forward_render", false, false);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const RasterDims d = raster_dims(in);
@@ -818,7 +840,7 @@ static int raster_backward_impl(const mb_raster_inputs *in, const int32_t *radii
                                 mb_stream_t stream) {
     // the backward never reads the opacities (they are part of the saved blend records), like upstream's, whose
     // rasterize_gaussians_backward does not take them
-    int rc = validate_raster_inputs(in, "mb_raster_backward", false);
+    int rc = validate_raster_inputs(in, "mb_raster_backward", false, !blend_only);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const RasterDims d = raster_dims(in);

@@ -7,6 +7,7 @@
 // radius ceil, tile rectangle truncation, depth order) is evaluated with individually rounded IEEE operations in a
 // fixed order, so radii / tiles touched / instance lists are reproducible bit-for-bit on any IEEE machine.
 #include "raster_state.cuh"
+#include "project_fwd.cuh"
 
 namespace mb {
 
@@ -17,13 +18,6 @@ struct PreArgs {
     GeomState g;
     int32_t *radii;
 };
-
-__device__ __forceinline__ void tile_rect(float px, float py, int rad, int gx, int gy, int &x0, int &y0, int &x1, int &y1) {
-    x0 = min(gx, max(0, (int)((px - rad) / kTile)));
-    y0 = min(gy, max(0, (int)((py - rad) / kTile)));
-    x1 = min(gx, max(0, (int)((px + rad + kTile - 1) / kTile)));
-    y1 = min(gy, max(0, (int)((py + rad + kTile - 1) / kTile)));
-}
 
 template <bool kPrecompCov, bool kSH>
 __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {   // `a` is a by-value copy: the camera override below is local
@@ -42,148 +36,68 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {   // `a` i
     bool visible = false;
     uint32_t my_tiles = 0;
     if (i < a.P) {
-        int radius = 0;
-        uint32_t tiles = 0, key = 0xffffffffu;
         const float mx = a.means3D[3 * i], my = a.means3D[3 * i + 1], mz = a.means3D[3 * i + 2];
-        // A.1 step 2: view space
-        const float tx0 = v[0] * mx + v[4] * my + v[8] * mz + v[12];
-        const float ty0 = v[1] * mx + v[5] * my + v[9] * mz + v[13];
-        const float tz = v[2] * mx + v[6] * my + v[10] * mz + v[14];
-        if (tz > kNearZ) {
-            // step 3
-            const float hx = p[0] * mx + p[4] * my + p[8] * mz + p[12];
-            const float hy = p[1] * mx + p[5] * my + p[9] * mz + p[13];
-            const float hw = p[3] * mx + p[7] * my + p[11] * mz + p[15];
-            const float pw = 1.0f / (hw + 0.0000001f);
-            const float ndcx = hx * pw, ndcy = hy * pw;
-            // step 4: 3-D covariance
-            float c6[6];
-            if (kPrecompCov) {
+        // A.1 step 4: 3-D covariance
+        float c6[6];
+        if (kPrecompCov) {
 #pragma unroll
-                for (int k = 0; k < 6; ++k) c6[k] = a.cov3D_precomp[6 * (size_t)i + k];
-            } else {
-                float R[9], L[9];
-                quat_to_rot(a.rots[4 * i], a.rots[4 * i + 1], a.rots[4 * i + 2], a.rots[4 * i + 3], R);
-                const float s[3] = {a.scale_mod * a.scales[3 * i], a.scale_mod * a.scales[3 * i + 1], a.scale_mod * a.scales[3 * i + 2]};
+            for (int k = 0; k < 6; ++k) c6[k] = a.cov3D_precomp[6 * (size_t)i + k];
+        } else {
+            float R[9], L[9];
+            quat_to_rot(a.rots[4 * i], a.rots[4 * i + 1], a.rots[4 * i + 2], a.rots[4 * i + 3], R);
+            const float s[3] = {a.scale_mod * a.scales[3 * i], a.scale_mod * a.scales[3 * i + 1], a.scale_mod * a.scales[3 * i + 2]};
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) L[3 * r + k] = R[3 * r + k] * s[k];
-                float S[9];
+                for (int k = 0; k < 3; ++k) L[3 * r + k] = R[3 * r + k] * s[k];
+            float S[9];
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        float acc = 0.f;
+                for (int c = 0; c < 3; ++c) {
+                    float acc = 0.f;
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) acc += L[3 * r + k] * L[3 * c + k];
-                        S[3 * r + c] = acc;
-                    }
-                c6[0] = S[0]; c6[1] = S[1]; c6[2] = S[2]; c6[3] = S[4]; c6[4] = S[5]; c6[5] = S[8];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) a.g.cov3D[6 * (size_t)i + k] = c6[k];
-            }
-            // step 5: EWA projection with the clamped view-space point
-            const float limx = 1.3f * a.tanx, limy = 1.3f * a.tany;
-            float rx = tx0 / tz, ry = ty0 / tz;
-            rx = rx < -limx ? -limx : (rx > limx ? limx : rx);
-            ry = ry < -limy ? -limy : (ry > limy ? limy : ry);
-            const float tx = rx * tz, ty = ry * tz;
-            const float J00 = a.focx / tz, J02 = -(a.focx * tx) / (tz * tz);
-            const float J11 = a.focy / tz, J12 = -(a.focy * ty) / (tz * tz);
-            float M0[3], M1[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                M0[k] = J00 * v[4 * k + 0] + J02 * v[4 * k + 2];
-                M1[k] = J11 * v[4 * k + 1] + J12 * v[4 * k + 2];
-            }
-            const float S[9] = {c6[0], c6[1], c6[2], c6[1], c6[3], c6[4], c6[2], c6[4], c6[5]};
-            float SM0[3], SM1[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                SM0[k] = S[3 * k] * M0[0] + S[3 * k + 1] * M0[1] + S[3 * k + 2] * M0[2];
-                SM1[k] = S[3 * k] * M1[0] + S[3 * k + 1] * M1[1] + S[3 * k + 2] * M1[2];
-            }
-            const float ca = M0[0] * SM0[0] + M0[1] * SM0[1] + M0[2] * SM0[2] + kLowPass;
-            const float cb = M0[0] * SM1[0] + M0[1] * SM1[1] + M0[2] * SM1[2];
-            const float cc = M1[0] * SM1[0] + M1[1] * SM1[1] + M1[2] * SM1[2] + kLowPass;
-            // steps 6-7
-            const float det = ca * cc - cb * cb;
-            if (det != 0.0f) {
-                const float di = 1.0f / det;
-                const float mid = 0.5f * (ca + cc);
-                float disc = mid * mid - det;
-                if (disc < 0.1f) disc = 0.1f;
-                const float sq = sqrtf(disc);
-                const float l1 = mid + sq, l2 = mid - sq;
-                const int rad = (int)ceilf(3.0f * sqrtf(l1 > l2 ? l1 : l2));
-                // steps 8-9
-                const float px = ((ndcx + 1.0f) * a.W - 1.0f) * 0.5f, py = ((ndcy + 1.0f) * a.H - 1.0f) * 0.5f;
-                int x0, y0, x1, y1;
-                tile_rect(px, py, rad, a.gx, a.gy, x0, y0, x1, y1);
-                const int area = (x1 - x0) * (y1 - y0);
-                if (area > 0) {
-                    visible = true;
-                    radius = rad;
-                    key = __float_as_uint(tz);
-                    const float op = a.opac[i];
-                    // below this power, op * exp(power) < 1/255 with a wide margin (NaN for op < 0: never skips)
-                    const float cut = -logf(255.0f * op) - 1e-4f;
-                    // half extents of the bounding box of { power >= cut }: dx^2 <= 2|cut| cov2D.xx, dy^2 <= 2|cut| cov2D.yy
-                    // (NaN when no pixel can pass the alpha gate: such a record never survives the tile kernels' box test)
-                    float ex = sqrtf(-2.0f * cut * ca) * 1.0001f + 0.01f, ey = sqrtf(-2.0f * cut * cc) * 1.0001f + 0.01f;
-                    // an indefinite 2-D covariance (det < 0: only possible with a non-PSD cov3D_precomp) has no bounded
-                    // { power >= cut } set: keep upstream's whole rectangle and let the per-pixel gates decide
-                    if (det < 0.0f && cut <= 0.0f) ex = ey = 1.0e9f;
-                    // Instances are only emitted for the tiles of upstream's rectangle that this box reaches: in the others
-                    // every pixel fails the alpha >= 1/255 gate, so dropping them changes neither image nor gradients
-                    // (it only shortens the lists; radii and visibility stay upstream's).
-                    if (ex >= 0.f && ey >= 0.f) {
-                        x0 = max(x0, (int)floorf((px - ex) / kTile));
-                        y0 = max(y0, (int)floorf((py - ey) / kTile));
-                        x1 = min(x1, (int)floorf((px + ex) / kTile) + 1);
-                        y1 = min(y1, (int)floorf((py + ey) / kTile) + 1);
-                        tiles = (uint32_t)(max(x1 - x0, 0) * max(y1 - y0, 0));
-                    } else {
-                        tiles = 0;
-                    }
-                    if (tiles == 0) x0 = y0 = x1 = y1 = 0;
-                    a.g.rect[i] = make_ushort4((unsigned short)x0, (unsigned short)y0, (unsigned short)x1, (unsigned short)y1);
-                    float rgb[3];
-                    if (kSH) {   // step 10: colour from SH in the world-space view direction
-                        float dx = mx - cam[32], dy = my - cam[33], dz = mz - cam[34];
-                        const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-                        dx *= inv; dy *= inv; dz *= inv;
-                        float basis[16];
-                        sh_basis(a.deg, dx, dy, dz, basis);
-                        const int nb = (a.deg + 1) * (a.deg + 1);
-                        const float *sh = a.shs + (size_t)i * a.M * 3;
-                        uint32_t mask = 0;
-#pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) {
-                            float r = 0.f;
-                            for (int k = 0; k < nb; ++k) r += basis[k] * sh[3 * k + ch];
-                            r += 0.5f;
-                            if (r < 0.f) { mask |= 1u << ch; r = 0.f; }
-                            rgb[ch] = r;
-                        }
-                        a.g.clamped[i] = mask;
-                    } else {
-#pragma unroll
-                        for (int ch = 0; ch < 3; ++ch) rgb[ch] = a.colors[3 * (size_t)i + ch];
-                    }
-                    Record r;
-                    r.a = make_float4(px, py, cc * di, -cb * di);
-                    r.b = make_float4(ca * di, op, rgb[0], rgb[1]);
-                    r.c = make_float4(rgb[2], cut, ex, ey);
-                    a.g.rec[i] = r;
+                    for (int k = 0; k < 3; ++k) acc += L[3 * r + k] * L[3 * c + k];
+                    S[3 * r + c] = acc;
                 }
-            }
+            c6[0] = S[0]; c6[1] = S[1]; c6[2] = S[2]; c6[3] = S[4]; c6[4] = S[5]; c6[5] = S[8];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) a.g.cov3D[6 * (size_t)i + k] = c6[k];
         }
-        a.radii[i] = radius;
-        my_tiles = tiles;
-        a.g.tiles_touched[i] = tiles;
-        a.g.depth_key[i] = key;
+        float rgb[3];
+        if (kSH) {   // step 10: colour from SH in the world-space view direction
+            float dx = mx - cam[32], dy = my - cam[33], dz = mz - cam[34];
+            const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            dx *= inv; dy *= inv; dz *= inv;
+            float basis[16];
+            sh_basis(a.deg, dx, dy, dz, basis);
+            const int nb = (a.deg + 1) * (a.deg + 1);
+            const float *sh = a.shs + (size_t)i * a.M * 3;
+            uint32_t mask = 0;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float r = 0.f;
+                for (int k = 0; k < nb; ++k) r += basis[k] * sh[3 * k + ch];
+                r += 0.5f;
+                if (r < 0.f) { mask |= 1u << ch; r = 0.f; }
+                rgb[ch] = r;
+            }
+            a.g.clamped[i] = mask;
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) rgb[ch] = a.colors[3 * (size_t)i + ch];
+        }
+        Projected pr;
+        project_forward(v, p, a.tanx, a.tany, a.focx, a.focy, a.W, a.H, a.gx, a.gy, mx, my, mz, c6, a.opac[i], rgb, pr);
+        visible = pr.visible;
+        if (visible) {
+            a.g.rect[i] = pr.rect;
+            a.g.rec[i] = pr.rec;
+        }
+        a.radii[i] = pr.radius;
+        my_tiles = pr.tiles;
+        a.g.tiles_touched[i] = pr.tiles;
+        a.g.depth_key[i] = pr.key;
         a.g.ident[i] = (uint32_t)i;
     }
     // per-CTA totals: visible Gaussians and instances (num_rendered is known as soon as this kernel has run)
@@ -540,10 +454,15 @@ int segment_items(const uint32_t *maxlast, int tiles, uint2 *items, uint32_t *n_
     return check_launch("segment_items", debug, s);
 }
 
-int validate_raster_inputs(const mb_raster_inputs *in, const char *who, bool need_opacities) {
+int validate_raster_inputs(const mb_raster_inputs *in, const char *who, bool need_opacities, bool need_arrays) {
     MB_REQUIRE(in != nullptr, "%s: null inputs", who);
     MB_REQUIRE(in->num_points >= 0 && in->image_width > 0 && in->image_height > 0, "%s: bad sizes P=%d W=%d H=%d", who,
                in->num_points, in->image_width, in->image_height);
+    if (!need_arrays) {      // stages that only read the opaque state (binning + tile kernels): camera, sizes, background
+        MB_REQUIRE(in->background && in->viewmatrix && in->projmatrix && in->campos, "%s: camera tensors missing", who);
+        MB_REQUIRE(in->tanfov_dev || (in->tanfovx > 0.f && in->tanfovy > 0.f), "%s: tanfov must be positive", who);
+        return MB_OK;
+    }
     MB_REQUIRE((in->colors_precomp != nullptr) != (in->shs != nullptr),
                "%s: Please provide excatly one of either SHs or precomputed colors!", who);
     const bool sr = in->scales != nullptr && in->rotations != nullptr;

@@ -70,7 +70,7 @@ struct GeomState {
 // per-pixel transmittance and accumulated colour in front of its far end: the forward writes that state (16 B per pixel)
 // every kSeg entries.
 #ifndef MB_BWD_SEG
-#define MB_BWD_SEG 512
+#define MB_BWD_SEG 256
 #endif
 constexpr int kSeg = MB_BWD_SEG;   // multiple of every batch size (64 / 128 / 256)
 
@@ -156,7 +156,7 @@ inline RasterDims raster_dims(const mb_raster_inputs *in) {
     return d;
 }
 
-int validate_raster_inputs(const mb_raster_inputs *in, const char *who, bool need_opacities = true);
+int validate_raster_inputs(const mb_raster_inputs *in, const char *who, bool need_opacities = true, bool need_arrays = true);
 
 // order[i] = tile with the i-th largest weight (approximately: descending quarter-octave buckets).  `ws` = kOrderWs zeroed
 // words; the kernel leaves them zeroed again.

@@ -190,7 +190,7 @@ class SceneRenderer:
 
     def render(self, view: int, sink: Optional[Dict[str, torch.Tensor]] = None, cam_dev=None, bones_dev=None,
                device_intrinsics: bool = False, compact_sh: bool = False, accumulate: bool = False, slot: int = 0,
-               fuse_backward: Optional[bool] = None):
+               fuse_backward: Optional[bool] = None, want_posed: bool = False):
         """Forward of one view through render_fused; returns the result dict (image is out['render'], HWC).
         cam_dev / bones_dev: the packed per-view inputs already on the device (``view_inputs_host`` layout).
         device_intrinsics: read tan(fov/2) from cam_dev[37:39] on the device instead of from the host camera, so that the
@@ -199,7 +199,9 @@ class SceneRenderer:
         f_dc gradients of all ranks' views by ``CompactGradExchange`` (the per-view SH gradient is rank one).
         accumulate: the backward ADDS this view's parameter gradients to ``sink`` (gradient accumulation over the views of a step).
         slot: views that are in flight at the same time (``GraphedStep(views_in_flight=V)``) use different slots, each with its
-        own bone-transform buffer."""
+        own bone-transform buffer.
+        want_posed: also return posed_xyz / posed_cov / colors / cano_opacity (52 B per Gaussian written to HBM); on the fused
+        path they are otherwise left in registers between the pose step and the projection."""
         from .cameras import Camera
         from .pose import bone_transforms
         from .render import render_fused
@@ -211,22 +213,27 @@ class SceneRenderer:
         dcam = Camera(cam.width, cam.height, cam.fovx, cam.fovy, cam_dev[0:16].view(4, 4), cam_dev[16:32].view(4, 4), cam_dev[32:35], None,
                       tanfov_dev=cam_dev[37:39] if device_intrinsics else None)
         bone_tf = None
+        fuse = self.fuse_backward if fuse_backward is None else fuse_backward
         if self.n_hand > 0:
-            # = bone_transforms(posed, rest, append_identity=True), written into a persistent [B+1,4,4] buffer whose last
-            # row stays the identity "background" bone (one small batched product per frame, no concatenation)
             nb = self.rest_inv.shape[0]
-            tfs = self.__dict__.setdefault("_bone_tfs", {})
-            if slot not in tfs:
-                tfs[slot] = torch.eye(4, dtype=torch.float32, device=self.device).repeat(nb + 1, 1, 1)
-            bone_tf = tfs[slot]
-            torch.bmm(bones_dev.view(-1, 4, 4), self.rest_inv, out=bone_tf[:nb])
-            self._bone_tf = bone_tf
+            if fuse and not compact_sh:
+                # the kernels build T_b = posed_b rest_b^-1 (+ the identity "background" row) in their prologue: no per-frame
+                # batched product, nothing to keep per slot
+                bone_tf = (bones_dev.view(-1, 4, 4), self.rest_inv, nb + 1)
+            else:
+                # = bone_transforms(posed, rest, append_identity=True), written into a persistent [B+1,4,4] buffer whose last
+                # row stays the identity (one small batched product per frame; the compact exchange ships this buffer)
+                tfs = self.__dict__.setdefault("_bone_tfs", {})
+                if slot not in tfs:
+                    tfs[slot] = torch.eye(4, dtype=torch.float32, device=self.device).repeat(nb + 1, 1, 1)
+                bone_tf = tfs[slot]
+                torch.bmm(bones_dev.view(-1, 4, 4), self.rest_inv, out=bone_tf[:nb])
+                self._bone_tf = bone_tf
         if compact_sh and sink is not None:
             sink = dict(sink, f_rest=None)
         self._last_campos = cam_dev[32:35]
         return render_fused(self.flat.leaves(), self.skin, bone_tf, dcam, self.bg, self.sh_degree, self.flat.isotropic,
-                            self.n_hand, grad_sink=sink, accumulate=accumulate,
-                            fuse_backward=self.fuse_backward if fuse_backward is None else fuse_backward)
+                            self.n_hand, grad_sink=sink, accumulate=accumulate, fuse_backward=fuse, want_posed=want_posed)
 
 
 class CompactGradExchange:
@@ -312,7 +319,7 @@ class GraphedStep:
     """
 
     def __init__(self, renderer: SceneRenderer, loss_fn, target_like: torch.Tensor, view: int = 0, warmup: int = 3,
-                 compact_sh: bool = False, views_in_flight: int = 1, ordered: bool = False):
+                 compact_sh: bool = False, views_in_flight: int = 1, ordered: bool = False, profile: bool = False):
         from . import rasterizer as rz
 
         if rz._Plan.mode != "reserve":
@@ -375,8 +382,15 @@ class GraphedStep:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
+        if profile:     # event-record nodes around every library kernel of the graph: _lib.profile_timeline() after a replay
+            from . import _lib
+
+            _lib.profile_report()
+            _lib.profile_enable(True)
         with torch.cuda.graph(self.graph):
             self.loss, self.losses, radii = step()
+        if profile:
+            _lib.profile_enable(False)
         self.radii = radii[0]
         self.radii_all = radii
         self.state = self.states[0]

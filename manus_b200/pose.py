@@ -47,7 +47,13 @@ def _inputs(xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, bone_tf
     pi.isotropic = int(bool(isotropic))
     pi.xyz, pi.log_scale, pi.quat, pi.opacity_logit = ptr(xyz), ptr(log_scale), ptr(quat), ptr(opacity_logit)
     pi.f_dc, pi.f_rest = ptr(f_dc), (ptr(f_rest) if f_rest is not None and f_rest.numel() else None)
-    pi.skin_wts, pi.bone_tf, pi.campos = ptr(skin_wts), ptr(bone_tf), ptr(campos)
+    pi.skin_wts, pi.campos = ptr(skin_wts), ptr(campos)
+    if isinstance(bone_tf, (tuple, list)):      # (bones_posed, bones_rest_inv): the kernels build T_b = posed_b rest_b^-1 (+ identity rows)
+        posed, rest_inv = bone_tf[0], bone_tf[1]
+        pi.bone_tf = None
+        pi.bones_posed, pi.bones_rest_inv, pi.num_posed_bones = ptr(posed), ptr(rest_inv), int(rest_inv.shape[0])
+    else:
+        pi.bone_tf = ptr(bone_tf)
     return pi
 
 

@@ -101,15 +101,15 @@ class RasterState:
 
 
 def _make_inputs(settings: GaussianRasterizationSettings, means3D, opacities, colors_precomp, shs, cov3D_precomp, scales,
-                 rotations, keep: list) -> _lib.RasterInputs:
-    dev = means3D.device
+                 rotations, keep: list, num_points: Optional[int] = None, dev=None) -> _lib.RasterInputs:
+    dev = means3D.device if dev is None else dev
     bg = _dense(settings.bg.to(dev), (3,))
     view = _dense(settings.viewmatrix.to(dev), (16,))
     proj = _dense(settings.projmatrix.to(dev), (16,))
     cam = _dense(settings.campos.to(dev), (3,))
     keep += [bg, view, proj, cam]
     ri = _lib.RasterInputs()
-    ri.num_points = means3D.shape[0]
+    ri.num_points = means3D.shape[0] if num_points is None else int(num_points)
     ri.image_width, ri.image_height = int(settings.image_width), int(settings.image_height)
     ri.sh_degree = int(settings.sh_degree)
     ri.sh_coeffs = 0 if shs is None else int(shs.shape[1])
@@ -135,17 +135,26 @@ def _make_inputs(settings: GaussianRasterizationSettings, means3D, opacities, co
 
 
 def rasterize_forward(settings: GaussianRasterizationSettings, means3D, opacities, colors_precomp=None, shs=None,
-                      cov3D_precomp=None, scales=None, rotations=None, capacity: Optional[int] = None, exact: bool = False):
+                      cov3D_precomp=None, scales=None, rotations=None, capacity: Optional[int] = None, exact: bool = False,
+                      pose_inputs=None):
     """-> (color[3,H,W], radii[N], RasterState).  Inputs must already be dense fp32 CUDA tensors (or None).
-    exact=True: size the instance buffers from this frame's own num_rendered (one host read) whatever the capacity mode."""
+    exact=True: size the instance buffers from this frame's own num_rendered (one host read) whatever the capacity mode.
+    pose_inputs: a filled ``_lib.PoseInputs`` -- the per-Gaussian stage then is mb_pose_project_forward (LBS + covariance +
+    SH->RGB + projection in ONE kernel) instead of mb_raster_forward_geom on precomputed arrays; means3D / opacities /
+    colors_precomp / cov3D_precomp are then OUTPUT buffers of that kernel, or all None (the posed arrays never touch HBM;
+    only the fused backward, mb_pose_backward_from_raster, can follow)."""
     L = _lib.lib()
-    if not means3D.is_cuda:
+    if pose_inputs is None and not means3D.is_cuda:
         raise _lib.ManusB200Error("manus_b200 rasterizer needs CUDA tensors (there is no CPU path)")
-    dev = means3D.device
-    N, H, W = means3D.shape[0], int(settings.image_height), int(settings.image_width)
+    if pose_inputs is not None:
+        N = int(pose_inputs.num_points)
+        dev = settings.viewmatrix.device
+    else:
+        N, dev = means3D.shape[0], means3D.device
+    H, W = int(settings.image_height), int(settings.image_width)
     st = RasterState()
     st.keep = [means3D, opacities, colors_precomp, shs, cov3D_precomp, scales, rotations]
-    st.inputs = _make_inputs(settings, means3D, opacities, colors_precomp, shs, cov3D_precomp, scales, rotations, st.keep)
+    st.inputs = _make_inputs(settings, means3D, opacities, colors_precomp, shs, cov3D_precomp, scales, rotations, st.keep, N, dev)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         st.geom = torch.empty(L.mb_raster_geom_bytes(N), dtype=torch.uint8, device=dev)
@@ -157,8 +166,14 @@ def rasterize_forward(settings: GaussianRasterizationSettings, means3D, opacitie
         # reserve mode: nothing is read back per frame (the frame can be captured in a CUDA graph); an overflow is
         # recorded in the device counters and raised by check_overflow() / raster_query()
         st.host_count = None if reserve else torch.zeros(1, dtype=torch.int64).pin_memory()
-        _lib.check(L.mb_raster_forward_geom(C.byref(st.inputs), ptr(st.geom), st.geom.numel(), ptr(st.radii),
-                                            None if reserve else st.host_count.data_ptr(), stream), "mb_raster_forward_geom")
+        count_ptr = None if reserve else st.host_count.data_ptr()
+        if pose_inputs is not None:
+            _lib.check(L.mb_pose_project_forward(C.byref(pose_inputs), C.byref(st.inputs), ptr(st.geom), st.geom.numel(), ptr(st.radii),
+                                                 count_ptr, ptr(means3D), ptr(cov3D_precomp), ptr(colors_precomp), ptr(opacities), stream),
+                       "mb_pose_project_forward")
+        else:
+            _lib.check(L.mb_raster_forward_geom(C.byref(st.inputs), ptr(st.geom), st.geom.numel(), ptr(st.radii), count_ptr, stream),
+                       "mb_raster_forward_geom")
         st.num_rendered = -1
         st.event = None
         if reserve:

@@ -121,30 +121,44 @@ class _RenderFused(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, screenspace, bone_tf, campos, settings, sh_degree,
-                isotropic, num_skinned, grad_sink, accumulate):
+                isotropic, num_skinned, grad_sink, accumulate, want_posed):
         L = _lib.lib()
         if not xyz.is_cuda:
             raise _lib.ManusB200Error("manus_b200.render_fused needs CUDA tensors (there is no CPU path)")
         dev = xyz.device
-        t = [_f32c(v) for v in (xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, bone_tf)]
+        t = [_f32c(v) for v in (xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts)]
+        if isinstance(bone_tf, (tuple, list)):      # (bones_posed, bones_rest_inv, B): transforms built inside the kernels
+            posed_b, rest_inv = _f32c(bone_tf[0]).reshape(-1, 4, 4), _f32c(bone_tf[1]).reshape(-1, 4, 4)
+            n_rows = int(bone_tf[2]) if len(bone_tf) > 2 else rest_inv.shape[0]
+            if posed_b.shape != rest_inv.shape or n_rows < rest_inv.shape[0]:
+                raise RuntimeError(f"bones_posed {tuple(posed_b.shape)} / bones_rest_inv {tuple(rest_inv.shape)} / B={n_rows} do not match")
+            t.append((posed_b, rest_inv))
+        else:
+            t.append(_f32c(bone_tf))
+            n_rows = None if t[7] is None else t[7].shape[0]
         cam = _f32c(campos).reshape(-1)[:3].contiguous()
         N = t[0].shape[0]
-        if t[6] is not None and (t[6].shape[0] != num_skinned or t[7] is None or t[7].shape[0] != t[6].shape[1]):
-            raise RuntimeError(f"skin_wts {tuple(t[6].shape)} does not match num_skinned={num_skinned} / bone_tf "
-                               f"{None if t[7] is None else tuple(t[7].shape)}")   # hand_dynamic.py:104
+        if t[6] is not None and (t[6].shape[0] != num_skinned or t[7] is None or n_rows != t[6].shape[1]):
+            raise RuntimeError(f"skin_wts {tuple(t[6].shape)} does not match num_skinned={num_skinned} / {n_rows} bone transforms")   # hand_dynamic.py:104
         pi = _inputs(*t, cam, sh_degree, isotropic, num_skinned)
         new = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
-        posed_xyz, cov6, colors, opacity = new(N, 3), new(N, 6), new(N, 3), new(N, 1)
-        with torch.cuda.device(dev):
-            _lib.check(L.mb_pose_forward(C.byref(pi), ptr(posed_xyz), ptr(cov6), ptr(colors), ptr(opacity), None,
-                                         torch.cuda.current_stream(dev).cuda_stream), "mb_pose_forward")
-        color, radii, st = rasterize_forward(settings, posed_xyz, opacity.reshape(-1), colors_precomp=colors, cov3D_precomp=cov6)
+        if want_posed:
+            posed_xyz, cov6, colors, opacity = new(N, 3), new(N, 6), new(N, 3), new(N, 1)
+        else:       # the posed arrays stay in registers between the pose step and the projection
+            posed_xyz = cov6 = colors = opacity = None
+        # ONE kernel for LBS + covariance + SH->RGB + projection (mb_pose_project_forward), then binning + tile kernels
+        color, radii, st = rasterize_forward(settings, posed_xyz, None if opacity is None else opacity.reshape(-1),
+                                             colors_precomp=colors, cov3D_precomp=cov6, pose_inputs=pi)
+        st.keep += [v for v in t[:7]] + list(t[7] if isinstance(t[7], tuple) else [t[7]]) + [cam]
         ctx.saved = (t, cam, sh_degree, isotropic, num_skinned, st)
         ctx.grad_sink, ctx.accumulate = grad_sink, bool(accumulate) and grad_sink is not None
         ctx.need_skin = skin_wts is not None and skin_wts.requires_grad
         ctx.shapes = [None if v is None else v.shape for v in (xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, screenspace)]
-        ctx.mark_non_differentiable(radii, posed_xyz, cov6, colors, opacity)
         ctx.set_materialize_grads(False)
+        if not want_posed:
+            ctx.mark_non_differentiable(radii)
+            return color, radii, None, None, None, None
+        ctx.mark_non_differentiable(radii, posed_xyz, cov6, colors, opacity)
         return color, radii, posed_xyz, cov6, colors, opacity
 
     @staticmethod
@@ -152,7 +166,7 @@ class _RenderFused(torch.autograd.Function):
         L = _lib.lib()
         t, cam, sh_degree, isotropic, num_skinned, st = ctx.saved
         if g_color is None:
-            return (None,) * 16
+            return (None,) * 17
         if st.host_count is not None:
             st.resolve()
         dev = t[0].device
@@ -187,13 +201,17 @@ class _RenderFused(torch.autograd.Function):
         rs = lambda v, s: None if v is None else v.reshape(s)
         ctx.saved = None
         head = (None,) * 6 if sink is not None else tuple(rs(gk, s) for gk, s in zip(g, sh[:6]))
-        return head + (rs(g_skin, sh[6]), rs(g_means2D, sh[7])) + (None,) * 8
+        return head + (rs(g_skin, sh[6]), rs(g_means2D, sh[7])) + (None,) * 9
 
 
 def render_fused(params, skin_wts, bone_tf, camera, bg_color, sh_degree=3, isotropic=False, num_skinned=None, grad_sink=None,
-                 accumulate=False, fuse_backward=False):
+                 accumulate=False, fuse_backward=False, want_posed=True):
     """params: (xyz, log_scale, quat, opacity_logit, f_dc, f_rest) -- the six nn.Parameters of GaussianModel.
-    Returns the render_gaussians dict plus the posed quantities (what TrainingModule.forward returns)."""
+    Returns the render_gaussians dict plus the posed quantities (what TrainingModule.forward returns).
+    bone_tf: [B,4,4] transforms, or a (bones_posed[nb,4,4], bones_rest_inv[nb,4,4], B) triple -- the kernels then build
+    T_b = posed_b rest_b^-1 (+ identity rows up to B) themselves (hand_dynamic.py:93-102).
+    want_posed=False (fused backward only): posed_xyz / posed_cov / colors / cano_opacity are not produced (None in the dict);
+    they never touch HBM."""
     xyz, log_scale, quat, opacity_logit, f_dc, f_rest = params
     device = xyz.device
     campos = torch.as_tensor(camera.camera_center).to(device)
@@ -204,7 +222,8 @@ def render_fused(params, skin_wts, bone_tf, camera, bg_color, sh_degree=3, isotr
         screenspace = _screenspace_leaf(xyz)
         image, radii, posed_xyz, posed_cov, colors, opacity = _RenderFused.apply(
             xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, screenspace, bone_tf, campos,
-            _settings(camera, bg_color, sh_degree, device), int(sh_degree), bool(isotropic), int(num_skinned), grad_sink, accumulate)
+            _settings(camera, bg_color, sh_degree, device), int(sh_degree), bool(isotropic), int(num_skinned), grad_sink, accumulate,
+            bool(want_posed))
         return {"render": torch.permute(image, (1, 2, 0)), "viewspace_points": screenspace, "visibility_filter": radii > 0, "radii": radii,
                 "posed_xyz": posed_xyz, "posed_cov": posed_cov, "colors": colors, "cano_opacity": opacity}
     posed_xyz, posed_cov, colors, opacity = pose_gaussians(xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, bone_tf,
