@@ -369,12 +369,28 @@ __global__ void __launch_bounds__(kOrderThreads) tile_order_kernel(const uint32_
         for (int b = tid; b < kOrderWs; b += kOrderThreads) ws[b] = 0;
 }
 
+// The CTAs of the two ordering kernels meet at an arrival counter, so all of them must be resident at the same time: a
+// COOPERATIVE launch (at most 32 CTAs) makes the driver start the grid only when every CTA fits on the device at once, whatever
+// else is running (the other views of a step share the GPU); the guarantee also holds for the kernel node of a captured graph.
+template <typename... Params, typename... Args>
+static cudaError_t launch_cooperative(void (*kernel)(Params...), int grid, int block, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeCooperative;
+    attr.val.cooperative = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
 int tile_order(const uint32_t *weight_or_null, const uint2 *ranges_or_null, int tiles, uint32_t *order, uint32_t *ws,
                cudaStream_t s, bool debug) {
     KernelTimer kt("tile_order", s);
-    // every CTA must be resident at the same time (they wait for each other): at most one CTA per SM
-    const int grid = max(1, min((tiles + kOrderThreads - 1) / kOrderThreads, sm_count()));
-    tile_order_kernel<<<grid, kOrderThreads, 0, s>>>(weight_or_null, ranges_or_null, tiles, order, ws);
+    const int grid = max(1, min((tiles + kOrderThreads - 1) / kOrderThreads, min(32, sm_count())));
+    MB_CUDA(launch_cooperative(tile_order_kernel, grid, kOrderThreads, s, weight_or_null, ranges_or_null, tiles, order, ws));
     return check_launch("tile_order", debug, s);
 }
 
@@ -449,8 +465,8 @@ __global__ void __launch_bounds__(kOrderThreads) segment_items_kernel(const uint
 
 int segment_items(const uint32_t *maxlast, int tiles, uint2 *items, uint32_t *n_items, uint32_t *ws, cudaStream_t s, bool debug) {
     KernelTimer kt("tile_order", s);
-    const int grid = max(1, min((tiles + kOrderThreads - 1) / kOrderThreads, sm_count()));
-    segment_items_kernel<<<grid, kOrderThreads, 0, s>>>(maxlast, tiles, items, n_items, ws);
+    const int grid = max(1, min((tiles + kOrderThreads - 1) / kOrderThreads, min(32, sm_count())));
+    MB_CUDA(launch_cooperative(segment_items_kernel, grid, kOrderThreads, s, maxlast, tiles, items, n_items, ws));
     return check_launch("segment_items", debug, s);
 }
 
