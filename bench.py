@@ -50,6 +50,10 @@ def parse():
                     help="views per rank and step, captured on parallel streams of the step's CUDA graph and accumulated into one "
                          "gradient buffer (the reference's accum_iter); 1 = one view per step")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python each step instead of replaying the captured CUDA graph")
+    ap.add_argument("--chunks", type=int, default=4,
+                    help="N > 1: ranges of Gaussians whose pose backward + all-reduce are pipelined (manus_b200.dist.PipelinedStep); "
+                         "0 = one all-reduce of the flat buffer after the step")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (BASELINE configs 1-3 and 5, drop-in and PyTorch-GPU baselines)")
     return ap.parse_args()
 
 
@@ -252,6 +256,31 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pinned host buffers are placed on the NUMA node of the thread that first touches them: run this rank on the cores of the
+    node its GPU hangs off, so that the host->device copies of the ranks do not all read one socket's memory.  Best effort."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        return None
+    return None
+
+
 def make_scene(args):
     from manus_b200 import synth
 
@@ -297,6 +326,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: manus_b200 has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)      # before any pinned allocation
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -313,8 +343,11 @@ def main():
     views = list(range(args.views))
     VIF = max(1, args.views_in_flight)      # with --no-graph the views of a step are enqueued one after the other
     my_view = lambda it, slot=0: views[((it * VIF + slot) * world + rank) % len(views)]
-    G_host = torch.rand(H, W, 3, generator=torch.Generator().manual_seed(7)).pin_memory()
-    G_dev = G_host.to(dev)
+    # target / loss weights G ~ U[0,1]: 8-bit like the dataset's images (rgb / 255, src/datasets/brics_dynamic.py), so that the
+    # end-to-end step ships one byte per channel over PCIe and converts on the device; the resident steps keep the fp32 copy
+    G_u8_host = torch.randint(0, 256, (H, W, 3), generator=torch.Generator().manual_seed(7), dtype=torch.uint8).pin_memory()
+    G_u8_dev = G_u8_host.to(dev)
+    G_dev = G_u8_dev.float() / 255.0
     staged = {}
     for v in views:
         _, c, b = r.view_inputs_host(v)
@@ -335,12 +368,25 @@ def main():
     # what the smaller collective saves (1.060 vs 1.066 ms/step) and the extra launches hurt the per-step-synchronised e2e
     # loop, so the default switches to the plain all-reduce above 4 ranks
     # the compact exchange carries ONE view per rank; with several views per rank and step the flat buffer is all-reduced
-    compact = world > 1 and VIF == 1 and not args.plain_allreduce and (world <= 4 or args.compact_exchange)
-    from manus_b200.dist import CompactGradExchange
+    compact = world > 1 and VIF == 1 and args.compact_exchange and not args.plain_allreduce
+    pipelined = world > 1 and not compact and not args.plain_allreduce and args.chunks > 0 and not args.no_graph
+    from manus_b200.dist import CompactGradExchange, PipelinedStep
     exchange = CompactGradExchange(r) if compact else None
-    graphed = None if args.no_graph else GraphedStep(r, loss_fn, G_dev, view=views[0], compact_sh=compact, views_in_flight=VIF)
+
+    def make_step(loss, target_like, vif=VIF, stats=None):
+        if args.no_graph:
+            return None
+        if pipelined:
+            # N > 1 (default): the pose backward runs range by range over the Gaussians and each finished range is all-reduced
+            # on the communicator's stream while the next one computes
+            return PipelinedStep(r, loss, target_like, view=views[0], views_in_flight=vif, chunks=args.chunks, stats=stats)
+        return GraphedStep(r, loss, target_like, view=views[0], compact_sh=compact, views_in_flight=vif, stats=stats)
+
+    graphed = make_step(loss_fn, G_dev)
 
     def reduce_gradients():
+        if pipelined:
+            return                       # inside PipelinedStep.replay
         if exchange is not None:
             exchange()
         elif world > 1:
@@ -373,19 +419,21 @@ def main():
     # asynchronous copy and is read by the host one step later (before step i+1 is enqueued the host waits for the loss of
     # step i-1), so the GPU queue never runs dry; the last timed step waits for its own loss inside the timed region.
     copy_stream = torch.cuda.Stream(device=dev)
+    NSLOT = 3      # input sets in flight: the copies of steps i+1 and i+2 are enqueued while step i computes
 
     class E2E:
+        """loss_fn(image, target_u8): the target arrives as uint8 [H,W,3] (one byte per channel over PCIe)."""
+
         def __init__(self, loss_fn):
             self.loss_fn = loss_fn
-            self.graphs = None if args.no_graph else [GraphedStep(r, loss_fn, G_dev, view=views[0], compact_sh=compact,
-                                                                  views_in_flight=VIF) for _ in range(2)]
+            self.graphs = None if args.no_graph else [make_step(loss_fn, G_u8_dev) for _ in range(NSLOT)]
             self.slots = []
-            for k in range(2):
+            for k in range(NSLOT):
                 if self.graphs is not None:
                     g = self.graphs[k]
                     d = dict(g=g.targets, cam=g.cams, bones=g.bones_all)
                 else:
-                    d = dict(g=[torch.empty_like(G_dev) for _ in range(VIF)], cam=[torch.empty(CAM_FLOATS, device=dev) for _ in range(VIF)],
+                    d = dict(g=[torch.empty_like(G_u8_dev) for _ in range(VIF)], cam=[torch.empty(CAM_FLOATS, device=dev) for _ in range(VIF)],
                              bones=[torch.empty(320, device=dev) for _ in range(VIF)])
                 d.update(ready=torch.cuda.Event(), free=torch.cuda.Event(), loss_host=torch.zeros(1).pin_memory(),
                          loss_done=torch.cuda.Event(), staged=None, pending=False)
@@ -394,12 +442,14 @@ def main():
             self.final_it = -1
 
         def stage(self, it):
-            slot = self.slots[it % 2]
+            slot = self.slots[it % NSLOT]
+            if slot["staged"] == it:
+                return
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(slot["free"])           # the step that last used this slot has finished with it
                 for j in range(VIF):                           # every view of the step: target image, camera, posed bones
                     _, c, b = r.view_inputs_host(my_view(it, j))
-                    slot["g"][j].copy_(G_host, non_blocking=True)
+                    slot["g"][j].copy_(G_u8_host, non_blocking=True)
                     slot["cam"][j].copy_(c, non_blocking=True)
                     slot["bones"][j].copy_(b, non_blocking=True)
                 slot["ready"].record(copy_stream)
@@ -412,13 +462,12 @@ def main():
                 slot["pending"] = False
 
         def __call__(self, it):
-            slot = self.slots[it % 2]
-            if slot["staged"] != it:
-                self.stage(it)                                  # first step of a run: nothing was prefetched
+            slot = self.slots[it % NSLOT]
+            self.stage(it)                                      # first step of a run: nothing was prefetched
             cur = torch.cuda.current_stream(dev)
             cur.wait_event(slot["ready"])
             if self.graphs is not None:
-                loss = self.graphs[it % 2].replay()
+                loss = self.graphs[it % NSLOT].replay()
             else:
                 loss = 0.0
                 for j in range(VIF):
@@ -432,10 +481,13 @@ def main():
             slot["loss_done"].record(cur)
             slot["pending"] = True
             slot["free"].record(cur)
-            self.collect(self.slots[(it + 1) % 2])              # loss of the previous step (its slot is reused next)
-            self.stage(it + 1)                                  # next step's host->device copies (copy stream)
+            # the slot that step it + NSLOT - 1 will use held step it - 1: read that step's loss, then refill the slot
+            self.collect(self.slots[(it + NSLOT - 1) % NSLOT])
+            for ahead in range(1, NSLOT):
+                self.stage(it + ahead)                          # host->device copies of the next steps (copy stream)
             if it == self.final_it:
-                self.collect(slot)
+                for sl in self.slots:
+                    self.collect(sl)
             return self.last_loss
 
         def check(self):
@@ -478,23 +530,72 @@ def main():
     sampler = ClockSampler(local_rank)
     ms_step = timed(step_resident, K, sampler)
     clocks = sampler.summary()
-    e2e_step = E2E(loss_fn)
+    # the same loss on a uint8 target: sum(image * g) / 255 (type promotion inside the one elementwise kernel)
+    loss_fn_u8 = lambda image, target: (image * target).sum() * (1.0 / 255.0)
+    e2e_step = E2E(loss_fn_u8)
     ms_e2e = timed(e2e_step, K)
     e2e_step.check()
     del e2e_step
     # the same end-to-end step with the reference's training loss 0.8 L1 + 0.2 (1 - SSIM) (fused kernel, manus_b200.losses)
     from manus_b200.losses import photometric_loss
-    e2e_photo = E2E(lambda image, target: photometric_loss(image, target, 0.8, 0.2))
+    e2e_photo = E2E(lambda image, target: photometric_loss(image, target * (1.0 / 255.0), 0.8, 0.2))
     ms_e2e_photo = timed(e2e_photo, K)
     e2e_photo.check()
     del e2e_photo
     # one view per step (the latency of a single frame; what earlier revisions of this bench reported as `value`)
     ms_single = None
     if graphed is not None and VIF > 1 and world == 1:
-        graphed_one = GraphedStep(r, loss_fn, G_dev, view=views[0])
+        graphed_one = make_step(loss_fn, G_dev, vif=1)
         ms_single = timed(lambda it: step_resident(it, graphed=graphed_one), K)
         graphed_one.check()
         del graphed_one
+    # the step with the densification statistics of the reference's density_update (gaussian.py:335-338, gaussian_utils.py:461-473:
+    # every step while global_step < densify_until_step) updated inside the pose backward kernel, and their reduction over the
+    # ranks (SUM / SUM / MAX; once per densification interval of 100 steps, not per step)
+    densify = None
+    if graphed is not None:
+        from manus_b200.densify import GaussianState
+        gs = GaussianState(r.flat)
+        stats_step = make_step(loss_fn, G_dev, stats=(gs.xyz_gradient_accum, gs.denom, gs.max_radii2D))
+        ms_stats = timed(lambda it: step_resident(it, graphed=stats_step), max(20, K // 4))
+        stats_step.check()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gs.reduce_stats()
+        e1.record()
+        torch.cuda.synchronize()
+        densify = {"ms_per_step_with_stats": ms_stats, "ms_per_step": ms_step, "reduce_stats_ms": e0.elapsed_time(e1),
+                   "reduce_every_steps": 100, "visible_updates_seen": float(gs.denom.max()),
+                   "note": "statistics updated by the pose backward kernel (atomics; V views in flight); reduce_stats all-reduces "
+                           "3 x N floats once per densification interval (config/model/gaussian/gaussian.yaml:15)"}
+        del stats_step
+    # N > 1: the exchanged gradients against rank 0 rendering ALL the step's views alone with gradient accumulation
+    # (hand_dynamic.py:248,259-277: the R-rank step must equal the 1-rank step with accum_iter = R x V)
+    grad_check = None
+    if world > 1 and graphed is not None:
+        for slot in range(graphed.V):
+            v = my_view(0, slot)
+            graphed.set_inputs(staged[v][0], staged[v][1], None, slot=slot)
+        graphed.replay()
+        reduce_gradients()
+        torch.cuda.synchronize()
+        got = r.flat.grad.clone()
+        if rank == 0:
+            want = torch.zeros_like(got)
+            for rk in range(world):
+                for slot in range(VIF):
+                    v = views[((0 * VIF + slot) * world + rk) % len(views)]
+                    out = r.render(v, sink=r.flat.grads, cam_dev=staged[v][0], bones_dev=staged[v][1])
+                    loss_fn(out["render"], G_dev).backward()
+                    want += r.flat.grad
+            torch.cuda.synchronize()
+            scale = float(want.abs().max())
+            grad_check = {"max_abs_err": float((got - want).abs().max()), "max_abs_grad": scale,
+                          "max_rel_err": float((got - want).abs().max()) / max(scale, 1e-30),
+                          "rel_l2_err": float((got - want).double().norm() / want.double().norm().clamp_min(1e-30)),
+                          "views": world * VIF, "note": "all-reduced flat gradient buffer of one step vs the same views accumulated on rank 0"}
+        dist.barrier()
     # reserve mode reads nothing back per frame: make sure no timed frame ran out of instance capacity
     if graphed is not None:
         graphed.check()
@@ -529,7 +630,7 @@ def main():
     fbytes = frame_bytes(n_hand, n_obj, D_mean, P)
     value = world * VIF * 1e3 / ms_step
     e2e_val = world * VIF * 1e3 / ms_e2e
-    h2d = VIF * (G_host.numel() * 4 + (CAM_FLOATS + 320) * 4)
+    h2d = VIF * (G_u8_host.numel() + (CAM_FLOATS + 320) * 4)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": WU, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -545,15 +646,39 @@ def main():
             "frame": {"num_rendered_mean": D_mean, "visible_mean": V_mean, "algorithmic_bytes": fbytes,
                       "achieved_gbps": fbytes * (VIF * 1e3 / ms_step) / 1e9, "frac_of_hbm_peak": fbytes * (VIF * 1e3 / ms_step) / 1e9 / peak,
                       "allreduce_bytes": r.flat.allreduce_bytes() if world > 1 else 0,
-                      "exchange": ("none" if world == 1 else "compact: all-gather of the DC gradients (12 B per Gaussian and rank) + all-reduce of "
+                      "exchange": ("none" if world == 1 else f"pipelined: pose backward over {args.chunks} ranges of Gaussians, each range's six "
+                                   "gradient pieces all-reduced (one coalesced NCCL op) while the next range computes" if pipelined else "compact: all-gather of the DC gradients (12 B per Gaussian and rank) + all-reduce of "
                                    "the 11 non-SH floats + local rebuild of the SH gradients" if compact else "all-reduce of the flat gradient buffer"),
                       "exchange_bytes_per_rank": (0 if world == 1 else (scene.n * (12 * world + 44)) if compact else r.flat.allreduce_bytes())}}
+    line["densification_stats"] = densify
+    line["grad_check"] = grad_check
+    line["numa_binding"] = numa
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        cb = cpu_baseline_frame(scene, W, H, 0, threads)
+        cpu_baseline_frame(scene, W, H, 0, threads)                    # warm-up (thread pools, page faults, library load)
+        cbs = sorted((cpu_baseline_frame(scene, W, H, v, threads) for v in (0, 1, 2)), key=lambda c: c["total_s"])
+        cb = cbs[1]                                                    # median of 3
         line["cpu_baseline"] = {"value": 1.0 / cb["total_s"], "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "one full 1080p frame of the same scene (view 0): pose fwd+bwd in PyTorch-CPU + raster "
-                                          "fwd+bwd in C (oracle/), all host threads", "breakdown_s": {k: round(v, 4) for k, v in cb.items() if k != "D"}}
+                                "sample": "full 1080p frames of the same scene (views 0-2; one warm-up frame, median of 3): pose fwd+bwd in "
+                                          "PyTorch-CPU + raster fwd+bwd in C (oracle/), all host threads",
+                                "breakdown_s": {k: round(v, 4) for k, v in cb.items() if k != "D"}}
+    if rank == 0 and world == 1 and not args.no_extras and graphed is not None:
+        import bench_extras as bx
+        torch.cuda.empty_cache()
+        ex = {}
+        try:
+            ex["config1_pose_only_50k"] = bx.pose_only(dev)
+            ex["config2_object_100k_800x800"] = bx.config_run(dev, "object", 100_000, 800, 800, 1, 1, 100, peak, seed=1)
+            ex["config3_hand_300k_1080p_50views"] = bx.config_run(dev, "hand", 300_000, 1920, 1080, 50, VIF, 40, peak)
+            ex["config5_sweep_1gpu"] = [bx.config_run(dev, "composite", n, 1920, 1080, 1, VIF, 16, peak) for n in
+                                        (50_000, 100_000, 200_000, 500_000, 1_000_000, 2_000_000)]
+            ex["dropin"] = bx.dropin_lines(dev, scene, W, H, views)
+            up = bx.upstream_rasterizer_line(dev, scene, W, H, views)
+            if up is not None:
+                line["reference_cuda_rasterizer"] = up
+        except Exception as e:          # a secondary measurement must not cost the headline line
+            ex["error"] = f"{type(e).__name__}: {e}"
+        line["extras"] = ex
     # north_star asks for the reference's own CUDA rasterizer on one GPU next to this number: it is a third-party submodule
     # cloned at install time (setup_env.sh:6-13), absent from the reference tree and from this image (no network)
     line["reference_cuda_rasterizer"] = {"value": None, "unavailable": "diff-gaussian-rasterization / simple-knn sources are not part of "

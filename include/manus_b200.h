@@ -193,10 +193,13 @@ int mb_pose_backward(const mb_pose_inputs *in, const float *g_posed_xyz, const f
  * pass): `raster` is the mb_raster_inputs of the forward that rendered THIS pose's outputs
  * (colors_precomp / cov3D_precomp mode, scale_modifier 1), radii its radii, grad_scratch the rows written by
  * mb_raster_backward_blend.  Writes dL_dmeans2D [N,3] (the screen-space gradient MANUS's densification reads,
- * src/models/gaussian.py:335-338) and the parameter gradients; accumulate != 0 adds to them like mb_pose_backward_accumulate. */
+ * src/models/gaussian.py:335-338) and the parameter gradients; accumulate != 0 adds to them like mb_pose_backward_accumulate.
+ * xyz_gradient_accum / denom / max_radii2D (all three or none): the densification statistics of add_densification_stats /
+ * density_update (gaussian.py:335-338, gaussian_utils.py:461-473) updated in the same kernel for the visible Gaussians. */
 int mb_pose_backward_from_raster(const mb_pose_inputs *in, const struct mb_raster_inputs *raster, const int32_t *radii,
                                  const void *grad_scratch, float *dL_dmeans2D, float *g_xyz, float *g_log_scale, float *g_quat,
                                  float *g_opacity_logit, float *g_f_dc, float *g_f_rest, float *g_skin_wts, int32_t accumulate,
+                                 float *xyz_gradient_accum /*[N] or NULL*/, float *denom /*[N]*/, float *max_radii2D /*[N]*/,
                                  mb_stream_t stream);
 
 /* Same, but the gradients are ADDED to the output buffers (bulk TMA reduce-add, fp32 adds resolved in L2): gradient

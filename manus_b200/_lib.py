@@ -65,7 +65,7 @@ SIGNATURES = {
                                 [C.c_void_p] * 4 + [C.c_void_p]),
     "mb_pose_backward": (C.c_int, [C.POINTER(PoseInputs)] + [C.c_void_p] * 4 + [C.c_void_p] * 7 + [C.c_void_p]),
     "mb_pose_backward_from_raster": (C.c_int, [C.POINTER(PoseInputs), C.POINTER(RasterInputs), C.c_void_p, C.c_void_p, C.c_void_p] +
-                                     [C.c_void_p] * 7 + [C.c_int32, C.c_void_p]),
+                                     [C.c_void_p] * 7 + [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mb_raster_backward_blend": (C.c_int, [C.POINTER(RasterInputs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                            C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mb_pose_backward_accumulate": (C.c_int, [C.POINTER(PoseInputs)] + [C.c_void_p] * 4 + [C.c_void_p] * 7 + [C.c_void_p]),

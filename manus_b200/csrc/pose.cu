@@ -49,6 +49,9 @@ struct PoseArgs {
     float tanx, tany;
     int W, H;
     float *g_means2D;          // [N,3] out: (dL/dmean2D x, y, 0)
+    // optional densification statistics of the visible Gaussians (gaussian.py:335-338, gaussian_utils.py:461-473), updated
+    // with atomics because the views of a step run concurrently: accum += |dL/dmean2D.xy|, denom += 1, max_radii = max(., radius)
+    float *stat_accum, *stat_denom, *stat_maxrad;
     // bone transforms built in the kernel prologue: T_b = bones_posed[b] * rest_inv[b] for b < n_posed, identity for the
     // other B - n_posed rows (hand_dynamic.py:93-102); nullptr = take bone_tf as given
     const float *bones_posed, *rest_inv;
@@ -544,6 +547,11 @@ __global__ void __launch_bounds__(kPoseThreads, kFused ? 4 : 1) pose_backward_ke
                 project_backward(rc, rc + 16, rc[32], rc[33], rc[34], rc[35], a.W, a.H, pm[0], pm[1], pm[2], c6, op, m, g2, gp, g6);
             }
             a.g_means2D[3 * (size_t)i] = g2[0]; a.g_means2D[3 * (size_t)i + 1] = g2[1]; a.g_means2D[3 * (size_t)i + 2] = 0.f;
+            if (a.stat_accum && rad > 0) {
+                atomicAdd(a.stat_accum + i, sqrtf(g2[0] * g2[0] + g2[1] * g2[1]));
+                atomicAdd(a.stat_denom + i, 1.0f);
+                atomicMax(reinterpret_cast<int *>(a.stat_maxrad) + i, __float_as_int((float)rad));   // non-negative floats order like ints
+            }
         } else {
 #pragma unroll
             for (int r = 0; r < 3; ++r) gp[r] = st[L.gpx + 3 * row + r];
@@ -936,7 +944,8 @@ extern "C" int mb_pose_backward(const mb_pose_inputs *in, const float *g_posed_x
 extern "C" int mb_pose_backward_from_raster(const mb_pose_inputs *in, const mb_raster_inputs *raster, const int32_t *radii,
                                            const void *grad_scratch, float *dL_dmeans2D, float *g_xyz, float *g_log_scale,
                                            float *g_quat, float *g_opacity_logit, float *g_f_dc, float *g_f_rest, float *g_skin_wts,
-                                           int32_t accumulate, mb_stream_t stream) {
+                                           int32_t accumulate, float *xyz_gradient_accum, float *denom, float *max_radii2D,
+                                           mb_stream_t stream) {
     int rc = validate_pose(in, "mb_pose_backward_from_raster");
     if (rc) return rc;
     MB_REQUIRE(raster != nullptr && raster->num_points == in->num_points, "mb_pose_backward_from_raster: raster inputs missing or of another size");
@@ -953,6 +962,9 @@ extern "C" int mb_pose_backward_from_raster(const mb_pose_inputs *in, const mb_r
     a.g_f_dc = g_f_dc; a.g_f_rest = g_f_rest; a.g_skin = g_skin_wts;
     a.accumulate = accumulate;
     a.acc = reinterpret_cast<const float *>(grad_scratch); a.radii = radii; a.g_means2D = dL_dmeans2D;
+    MB_REQUIRE((xyz_gradient_accum != nullptr) == (denom != nullptr) && (denom != nullptr) == (max_radii2D != nullptr),
+               "mb_pose_backward_from_raster: give all three densification statistics or none");
+    a.stat_accum = xyz_gradient_accum; a.stat_denom = denom; a.stat_maxrad = max_radii2D;
     a.view = raster->viewmatrix; a.proj = raster->projmatrix; a.tanfov_dev = raster->tanfov_dev;
     a.tanx = raster->tanfovx; a.tany = raster->tanfovy; a.W = raster->image_width; a.H = raster->image_height;
     return launch_pose_deg(a, true, (cudaStream_t)stream);

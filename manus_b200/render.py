@@ -114,6 +114,53 @@ def render_gaussians(posed_means, posed_cov, cano_means, cano_features, cano_opa
     return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii}
 
 
+class DeferredPoseBackward:
+    """The second half of the fused backward of one view -- mb_pose_backward_from_raster on the blend backward's accumulator
+    rows -- kept for the caller to launch on ranges of Gaussians (``run(lo, hi, accumulate)``; lo must be a multiple of 128,
+    the pose kernels' tile, so that every sub-array stays 16-byte aligned for the bulk copies)."""
+
+    def __init__(self, t, cam, sh_degree, isotropic, num_skinned, st, scratch, g_means2D, grads, stats=None):
+        self.t, self.cam, self.sh_degree, self.isotropic, self.num_skinned = t, cam, sh_degree, isotropic, num_skinned
+        self.st, self.scratch, self.g_means2D, self.grads, self.stats = st, scratch, g_means2D, grads, stats
+
+    def run(self, lo: int, hi: int, accumulate: bool) -> None:
+        L = _lib.lib()
+        t, N = self.t, self.t[0].shape[0]
+        if lo % 128 or not (0 <= lo < hi <= N):
+            raise ValueError(f"bad Gaussian range [{lo}, {hi}) of {N} (lo must be a multiple of 128)")
+        n, ns = hi - lo, max(0, min(self.num_skinned, hi) - lo)
+        row = lambda v: None if v is None else v[lo:hi]
+        skin = None if (t[6] is None or ns == 0) else t[6][lo:lo + ns]
+        tt = [row(v) for v in t[:6]] + [skin, t[7]]
+        pi = _inputs(*tt, self.cam, self.sh_degree, self.isotropic, ns)
+        if skin is None and t[6] is not None:
+            pi.num_bones = t[6].shape[1]
+        ri = type(self.st.inputs)()
+        C.memmove(C.byref(ri), C.byref(self.st.inputs), C.sizeof(ri))
+        ri.num_points = n
+        g = [row(v) for v in self.grads]
+        dev = t[0].device
+        with torch.cuda.device(dev):
+            _lib.check(L.mb_pose_backward_from_raster(C.byref(pi), C.byref(ri), ptr(self.st.radii[lo:hi]), self.scratch.data_ptr() + lo * 48,
+                                                      ptr(self.g_means2D[lo:hi]), ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(g[3]), ptr(g[4]),
+                                                      ptr(g[5]) if g[5] is not None and g[5].numel() else None, None,
+                                                      int(accumulate), *_stat_ptrs(self.stats, N, lo),
+                                                      torch.cuda.current_stream(dev).cuda_stream),
+                       "mb_pose_backward_from_raster")
+
+
+def _stat_ptrs(stats, n: int, lo: int = 0):
+    """(xyz_gradient_accum, denom, max_radii2D) -> the three device pointers (offset by ``lo`` Gaussians), or three NULLs."""
+    if stats is None:
+        return None, None, None
+    out = []
+    for s in stats:
+        if not (s.is_cuda and s.dtype == torch.float32 and s.is_contiguous() and s.numel() == n):
+            raise RuntimeError("densification statistics must be dense fp32 CUDA tensors with one element per Gaussian")
+        out.append(s.data_ptr() + 4 * lo)
+    return tuple(out)
+
+
 class _RenderFused(torch.autograd.Function):
     """pose forward + rasterizer forward as ONE autograd node, so that the backward can keep the rasterizer's per-Gaussian
     gradients out of HBM: tile backward (accumulator rows) -> pose backward with the projection backward inside
@@ -187,16 +234,24 @@ class _RenderFused(torch.autograd.Function):
         if ctx.need_skin:
             g_skin = torch.zeros_like(t[6]) if ctx.accumulate else torch.empty_like(t[6])
         g_means2D = torch.empty((N, 3), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            if sink is not None and sink.get("_wait") is not None:
-                torch.cuda.current_stream(dev).wait_event(sink["_wait"])
-            _lib.check(L.mb_pose_backward_from_raster(C.byref(pi), C.byref(st.inputs), ptr(st.radii), ptr(scratch), ptr(g_means2D),
-                                                      ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(g[3]), ptr(g[4]),
-                                                      ptr(g[5]) if g[5] is not None and g[5].numel() else None, ptr(g_skin),
-                                                      int(ctx.accumulate), torch.cuda.current_stream(dev).cuda_stream),
-                       "mb_pose_backward_from_raster")
-            if sink is not None and sink.get("_record") is not None:
-                sink["_record"].record(torch.cuda.current_stream(dev))
+        if sink is not None and sink.get("_defer") is not None:
+            # the caller runs the pose backward itself, range by range (DeferredPoseBackward.run): the data-parallel step
+            # all-reduces the gradients of one range of Gaussians while the pose backward of the next range computes
+            if ctx.need_skin:
+                raise RuntimeError("a deferred pose backward does not produce skin-weight gradients")
+            sink["_defer"].append(DeferredPoseBackward(t, cam, sh_degree, isotropic, num_skinned, st, scratch, g_means2D, g, sink.get("_stats")))
+        else:
+            with torch.cuda.device(dev):
+                if sink is not None and sink.get("_wait") is not None:
+                    torch.cuda.current_stream(dev).wait_event(sink["_wait"])
+                _lib.check(L.mb_pose_backward_from_raster(C.byref(pi), C.byref(st.inputs), ptr(st.radii), ptr(scratch), ptr(g_means2D),
+                                                          ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(g[3]), ptr(g[4]),
+                                                          ptr(g[5]) if g[5] is not None and g[5].numel() else None, ptr(g_skin),
+                                                          int(ctx.accumulate), *_stat_ptrs(None if sink is None else sink.get("_stats"), N),
+                                                          torch.cuda.current_stream(dev).cuda_stream),
+                           "mb_pose_backward_from_raster")
+                if sink is not None and sink.get("_record") is not None:
+                    sink["_record"].record(torch.cuda.current_stream(dev))
         sh = ctx.shapes
         rs = lambda v, s: None if v is None else v.reshape(s)
         ctx.saved = None

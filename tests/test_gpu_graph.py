@@ -139,6 +139,66 @@ def test_views_in_flight_sum_the_single_view_gradients(built_lib, V, ordered):
         rz.set_capacity_mode("exact")
 
 
+@pytest.mark.parametrize("V,chunks", [(1, 1), (2, 3), (3, 5)])
+def test_pipelined_step_equals_the_sum_of_single_view_gradients(built_lib, V, chunks):
+    """PipelinedStep: tile backward of every view inside one graph, pose backward afterwards range by range over the Gaussians
+    (view 0 overwrites a range, the others add) -- the single-rank half of the data-parallel step that all-reduces a finished
+    range while the next one computes.  Same gradients as accumulating the views one by one; ranges that do not divide N."""
+    from manus_b200 import rasterizer as rz
+    from manus_b200.dist import PipelinedStep, gaussian_chunks
+
+    scene, r = _renderer(n=6007)
+    H, W, dev = r.H, r.W, r.device
+    targets = [torch.rand(H, W, 3, generator=torch.Generator().manual_seed(30 + i)).to(dev) for i in range(3)]
+    loss_fn = lambda image, target: (image * target).sum()
+    views = (7, 11, 2)
+    assert gaussian_chunks(6007, 5) == [(0, 1280), (1280, 2560), (2560, 3840), (3840, 5120), (5120, 6007)]
+    rz.set_capacity_mode("exact")
+    try:
+        eager, dmax = [], 0
+        for i, view in enumerate(views):
+            _, c, b = r.view_inputs_host(view)
+            out = r.render(view, sink=r.flat.grads, cam_dev=c.to(dev), bones_dev=b.to(dev))
+            loss = loss_fn(out["render"], targets[i])
+            loss.backward()
+            eager.append((float(loss.detach()), r.flat.grad.clone(), int(rz.check_overflow()), out["viewspace_points"].grad.clone()))
+            dmax = max(dmax, eager[-1][2])
+        rz.set_capacity_mode("reserve", margin=1.2)
+        rz.reserve_capacity(dev.index, scene.n, H, W, dmax)
+        from manus_b200.densify import GaussianState
+        gs = GaussianState(r.flat)
+        stats = (gs.xyz_gradient_accum, gs.denom, gs.max_radii2D)
+        step = PipelinedStep(r, loss_fn, targets[0], view=2, views_in_flight=V, chunks=chunks, stats=stats)
+        ref_stats = GaussianState(r.flat)
+        assert len(step.ranges) == chunks
+        for rep in range(2):
+            order = [(rep + i) % 3 for i in range(V)]
+            for slot, k in enumerate(order):
+                _, c, b = r.view_inputs_host(views[k])
+                step.set_inputs(c.to(dev), b.to(dev), targets[k], slot=slot)
+            r.flat.grad.fill_(float("nan"))                      # every element must be overwritten by the step
+            loss = step.replay()
+            torch.cuda.synchronize()
+            assert step.check() == sum(eager[k][2] for k in order)
+            want_loss = sum(eager[k][0] for k in order)
+            assert abs(float(loss) - want_loss) <= 2e-6 * abs(want_loss)
+            want = sum(eager[k][1] for k in order)
+            ok, e, s = grad_close(r.flat.grad.cpu().numpy(), want.cpu().numpy())
+            assert ok, (V, chunks, rep, e, s)
+            for slot, k in enumerate(order):                     # the densification statistic of every view (U1)
+                ok, e, s = grad_close(step.viewspace[slot].grad.cpu().numpy(), eager[k][3].cpu().numpy())
+                assert ok, ("viewspace", slot, e, s)
+                # ... and the statistics the pose backward kernel accumulates from it (gaussian.py:335-338, gaussian_utils.py:461-473)
+                radii = step.states[slot].radii
+                ref_stats.add_densification_stats(step.viewspace[slot].grad, radii > 0, radii)
+            for got, want in zip(stats, (ref_stats.xyz_gradient_accum, ref_stats.denom, ref_stats.max_radii2D)):
+                ok, e, s = grad_close(got.cpu().numpy(), want.cpu().numpy(), 2e-6)
+                assert ok, ("stats", e, s)
+            assert float(gs.denom.max()) == (rep + 1) * V
+    finally:
+        rz.set_capacity_mode("exact")
+
+
 @pytest.mark.parametrize("n", [6007, 4096])
 def test_fused_projection_and_pose_backward_matches_the_two_kernel_path(built_lib, n):
     """render_fused(fuse_backward=True): ONE autograd node whose backward feeds the blend backward's accumulator rows straight
