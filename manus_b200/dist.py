@@ -388,6 +388,9 @@ class PipelinedStep:
             with torch.cuda.graph(g, pool=self.graph_front.pool()):
                 back(self._defs, c)
             self.graph_back.append(g)
+        if stats is not None:       # the warm-up steps above went through the same kernels: start the statistics from zero
+            for s_ in stats:
+                s_.zero_()
 
     def set_inputs(self, cam_dev, bones_dev, target_dev=None, slot: int = 0) -> None:
         self.cams[slot].copy_(cam_dev, non_blocking=True)
@@ -523,6 +526,9 @@ class GraphedStep:
         self.radii = radii[0]
         self.radii_all = radii
         self.state = self.states[0]
+        if stats is not None:       # the warm-up steps above went through the same kernels: start the statistics from zero
+            for s_ in stats:
+                s_.zero_()
 
     def set_inputs(self, cam_dev: torch.Tensor, bones_dev: torch.Tensor, target_dev: Optional[torch.Tensor] = None,
                    slot: int = 0) -> None:
