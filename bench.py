@@ -53,6 +53,10 @@ def parse():
     ap.add_argument("--chunks", type=int, default=4,
                     help="N > 1: ranges of Gaussians whose pose backward + all-reduce are pipelined (manus_b200.dist.PipelinedStep); "
                          "0 = one all-reduce of the flat buffer after the step")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "multimem"],
+                    help="N > 1: who sums the gradient ranges over the ranks -- NCCL (coalesced all-reduce per range) or the repository's "
+                         "own multimem.ld_reduce / multimem.st kernel over NVSwitch multicast memory (csrc/exchange.cu)")
+    ap.add_argument("--exchange-ctas", type=int, default=32, help="CTAs of the multimem exchange kernel (it runs beside the pose backward)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (BASELINE configs 1-3 and 5, drop-in and PyTorch-GPU baselines)")
     return ap.parse_args()
 
@@ -339,6 +343,14 @@ def main():
     W, H, K, WU = args.width, args.height, args.steps, max(args.warmup, 3)
     scene = make_scene(args)
     r = SceneRenderer(scene, dev, W, H)
+    mc_exchange, mc_note = None, None
+    if world > 1 and args.exchange == "multimem":
+        # the gradient buffer moves into NVSwitch multicast memory BEFORE anything captures its address
+        try:
+            from manus_b200.exchange import MulticastExchange
+            mc_exchange = MulticastExchange(r.flat)
+        except Exception as e:      # no multicast on this system: NCCL does the exchange (said in the line)
+            mc_note = f"multimem unavailable ({type(e).__name__}: {e}); NCCL used"
     n_hand, n_obj = scene.n_hand, scene.n - scene.n_hand
     views = list(range(args.views))
     VIF = max(1, args.views_in_flight)      # with --no-graph the views of a step are enqueued one after the other
@@ -379,7 +391,8 @@ def main():
         if pipelined:
             # N > 1 (default): the pose backward runs range by range over the Gaussians and each finished range is all-reduced
             # on the communicator's stream while the next one computes
-            return PipelinedStep(r, loss, target_like, view=views[0], views_in_flight=vif, chunks=args.chunks, stats=stats)
+            return PipelinedStep(r, loss, target_like, view=views[0], views_in_flight=vif, chunks=args.chunks, stats=stats,
+                                 exchange=mc_exchange, exchange_ctas=args.exchange_ctas)
         return GraphedStep(r, loss, target_like, view=views[0], compact_sh=compact, views_in_flight=vif, stats=stats)
 
     graphed = make_step(loss_fn, G_dev)
@@ -389,6 +402,8 @@ def main():
             return                       # inside PipelinedStep.replay
         if exchange is not None:
             exchange()
+        elif world > 1 and mc_exchange is not None:
+            mc_exchange.all_reduce_all(args.exchange_ctas)
         elif world > 1:
             dist.all_reduce(r.flat.grad)
 
@@ -650,6 +665,8 @@ def main():
                                    "gradient pieces all-reduced (one coalesced NCCL op) while the next range computes" if pipelined else "compact: all-gather of the DC gradients (12 B per Gaussian and rank) + all-reduce of "
                                    "the 11 non-SH floats + local rebuild of the SH gradients" if compact else "all-reduce of the flat gradient buffer"),
                       "exchange_bytes_per_rank": (0 if world == 1 else (scene.n * (12 * world + 44)) if compact else r.flat.allreduce_bytes())}}
+    line["exchange_impl"] = (None if world == 1 else "multimem.ld_reduce / multimem.st kernel over NVSwitch multicast memory (csrc/exchange.cu)"
+                             if mc_exchange is not None else (mc_note or "NCCL all-reduce"))
     line["densification_stats"] = densify
     line["grad_check"] = grad_check
     line["numa_binding"] = numa

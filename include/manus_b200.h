@@ -291,6 +291,17 @@ int mb_radix_sort_pairs(uint32_t *keys_in, uint32_t *vals_in, uint32_t *keys_out
                         const uint32_t *n_dev, int64_t max_n, int32_t end_bit, void *workspace, size_t workspace_bytes,
                         mb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * The gradient exchange of the view-sharded step over NVSwitch multicast memory (replaces the one ncclAllReduce per step,
+ * SURVEY.md section 8e; reference semantics: the sum over accum_iter views, src/modules/hand_dynamic.py:248,259-277).
+ * multicast_base: the multicast (multimem) address of a symmetric allocation that holds every rank's gradient buffer at the same
+ * offsets.  pieces: up to 8 [offset, offset + count) float ranges of it; rank r reduces 1/world of every piece with
+ * multimem.ld_reduce (fp32 add in the switch) and broadcasts the sums with multimem.st.  The caller synchronises the ranks before
+ * (gradients complete everywhere) and after (stores landed everywhere).  max_ctas <= 0: one CTA per SM.
+ * ---------------------------------------------------------------------------------------------- */
+int mb_multimem_allreduce(float *multicast_base, const int64_t *piece_offsets, const int64_t *piece_counts, int32_t num_pieces,
+                          int32_t rank, int32_t world, int32_t max_ctas, mb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -317,10 +317,14 @@ class PipelinedStep:
     ``GaussianState.reduce_stats`` combines them, once per densification interval)."""
 
     def __init__(self, renderer: SceneRenderer, loss_fn, target_like: torch.Tensor, view: int = 0, views_in_flight: int = 1,
-                 chunks: int = 4, warmup: int = 3, group=None, stats=None):
+                 chunks: int = 4, warmup: int = 3, group=None, stats=None, exchange=None, exchange_ctas: int = 0):
         from . import rasterizer as rz
 
         self.stats = stats
+        # exchange: a manus_b200.exchange.MulticastExchange built on renderer.flat BEFORE this step (the gradient buffer then lives
+        # in NVSwitch multicast memory and the ranges are summed by the repository's own multimem kernel on a side stream);
+        # None: one coalesced NCCL all-reduce per range
+        self.exchange, self.exchange_ctas = exchange, exchange_ctas
         if rz._Plan.mode != "reserve":
             raise RuntimeError("PipelinedStep needs set_capacity_mode('reserve') and reserve_capacity(...) (no host read-back in a graph)")
         self.r, self.V, self.group = renderer, int(views_in_flight), group
@@ -334,6 +338,10 @@ class PipelinedStep:
         self.ranges = gaussian_chunks(renderer.flat.n, chunks)
         flat = renderer.flat
         self.pieces = [[flat.grads[name][lo:hi] for name in PARAM_ORDER] for lo, hi in self.ranges]
+        if exchange is not None:
+            self.piece_ranges = [exchange.pieces(lo, hi) for lo, hi in self.ranges]
+            self.comm = torch.cuda.Stream(device=dev)
+            self._done = [torch.cuda.Event() for _ in self.ranges]
         self._sides = [torch.cuda.Stream(device=dev) for _ in range(V - 1)]
         self.states = [None] * V
         self.viewspace = [None] * V
@@ -403,6 +411,16 @@ class PipelinedStep:
         reaches the end of what this call enqueued."""
         self.graph_front.replay()
         works = []
+        if self.exchange is not None:
+            cur = torch.cuda.current_stream(self.r.device)
+            for c, g in enumerate(self.graph_back):
+                g.replay()
+                self._done[c].record(cur)
+                with torch.cuda.stream(self.comm):      # the range's sum over the ranks runs beside the next range's pose backward
+                    self.comm.wait_event(self._done[c])
+                    self.exchange.all_reduce(self.piece_ranges[c], self.exchange_ctas)
+            cur.wait_stream(self.comm)
+            return self.loss
         for c, g in enumerate(self.graph_back):
             g.replay()
             if self.world > 1:

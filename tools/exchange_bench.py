@@ -38,6 +38,36 @@ res = {
     "all_gather 6 MB per rank": timeit(lambda: dist.all_gather_into_tensor(recv.view(-1), send)),
     "both, back to back": timeit(lambda: (dist.all_gather_into_tensor(recv.view(-1), send), dist.all_reduce(head))),
 }
+# ---- the repository's own exchange over NVSwitch multicast memory against NCCL on the same 118 MB
+from manus_b200.dist import FlatGaussians  # noqa: E402
+from manus_b200.exchange import MulticastExchange  # noqa: E402
+
+fg = FlatGaussians(N, dev)
+try:
+    ex = MulticastExchange(fg)
+    src = torch.randn(N * 59, device=dev, generator=torch.Generator(device=dev).manual_seed(rank))
+    fg.grad.copy_(src)
+    want = src.clone()
+    dist.all_reduce(want)
+    torch.cuda.synchronize(); dist.barrier()
+    ex.all_reduce_all()
+    torch.cuda.synchronize()
+    err = float((fg.grad - want).abs().max()) / float(want.abs().max())
+    same = torch.equal(fg.grad, want)
+    # every rank must hold the same bits
+    probe = fg.grad[:: 4099].clone()
+    ref = probe.clone()
+    dist.broadcast(ref, 0)
+    identical = bool(torch.equal(probe, ref))
+    for ctas in (0, 64, 32, 16):
+        res[f"multimem all-reduce 118 MB, max_ctas={ctas or 'SMs'}"] = timeit(lambda: ex.all_reduce_all(ctas))
+    chunk = ex.pieces(0, 125056)
+    res["multimem all-reduce, one of 4 ranges (6 pieces, 29.5 MB)"] = timeit(lambda: ex.all_reduce(chunk))
+    res["max rel err vs NCCL"] = err
+    res["bitwise equal to NCCL"] = float(same)
+    res["replicas bitwise identical"] = float(identical)
+except Exception as e:  # noqa: BLE001
+    res["multimem"] = f"unavailable: {type(e).__name__}: {e}"
 if rank == 0:
-    print({k: round(v, 1) for k, v in res.items()}, "us, world", world)
+    print({k: (round(v, 1) if isinstance(v, float) and v > 1 else v) for k, v in res.items()}, "us, world", world)
 dist.destroy_process_group()
