@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "multimem"],
                     help="N > 1: who sums the gradient ranges over the ranks -- NCCL (coalesced all-reduce per range) or the repository's "
                          "own multimem.ld_reduce / multimem.st kernel over NVSwitch multicast memory (csrc/exchange.cu)")
+    ap.add_argument("--deferred-views", type=int, default=0,
+                    help="N > 1: views per rank whose pose backward runs in the range-by-range tail (the others finish inside their branch); 0 = all")
     ap.add_argument("--exchange-ctas", type=int, default=32, help="CTAs of the multimem exchange kernel (it runs beside the pose backward)")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (BASELINE configs 1-3 and 5, drop-in and PyTorch-GPU baselines)")
     return ap.parse_args()
@@ -271,7 +273,7 @@ def bind_to_gpu_numa_node(local_rank):
         path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
         node = int(open(path).read().strip())
         if node < 0:
-            return None
+            return {"unavailable": f"{path} reports no NUMA node"}
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
@@ -280,9 +282,9 @@ def bind_to_gpu_numa_node(local_rank):
         if allowed:
             os.sched_setaffinity(0, allowed)
             return {"numa_node": node, "cpus": len(allowed)}
-    except Exception:
-        return None
-    return None
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    return {"unavailable": "no allowed CPU on the GPU's NUMA node"}
 
 
 def make_scene(args):
@@ -392,7 +394,7 @@ def main():
             # N > 1 (default): the pose backward runs range by range over the Gaussians and each finished range is all-reduced
             # on the communicator's stream while the next one computes
             return PipelinedStep(r, loss, target_like, view=views[0], views_in_flight=vif, chunks=args.chunks, stats=stats,
-                                 exchange=mc_exchange, exchange_ctas=args.exchange_ctas)
+                                 exchange=mc_exchange, exchange_ctas=args.exchange_ctas, deferred_views=args.deferred_views or None)
         return GraphedStep(r, loss, target_like, view=views[0], compact_sh=compact, views_in_flight=vif, stats=stats)
 
     graphed = make_step(loss_fn, G_dev)

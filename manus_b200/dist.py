@@ -317,9 +317,15 @@ class PipelinedStep:
     ``GaussianState.reduce_stats`` combines them, once per densification interval)."""
 
     def __init__(self, renderer: SceneRenderer, loss_fn, target_like: torch.Tensor, view: int = 0, views_in_flight: int = 1,
-                 chunks: int = 4, warmup: int = 3, group=None, stats=None, exchange=None, exchange_ctas: int = 0):
+                 chunks: int = 4, warmup: int = 3, group=None, stats=None, exchange=None, exchange_ctas: int = 0,
+                 deferred_views: Optional[int] = None):
         from . import rasterizer as rz
 
+        # deferred_views = d: only the LAST d views of the step leave their pose backward for the range-by-range tail; the others
+        # run it inside their branch (hidden under the tile kernels of the other views, as in GraphedStep) and add into the buffer,
+        # which is then cleared at the head of the step.  The tail is as long as the exchange either way; fewer deferred views
+        # mean less serialised pose backward in front of it.  None = all views.
+        self.deferred_views = int(views_in_flight) if deferred_views is None else max(1, min(int(deferred_views), int(views_in_flight)))
         self.stats = stats
         # exchange: a manus_b200.exchange.MulticastExchange built on renderer.flat BEFORE this step (the gradient buffer then lives
         # in NVSwitch multicast memory and the ranges are summed by the repository's own multimem kernel on a side stream);
@@ -352,13 +358,19 @@ class PipelinedStep:
             deferred.clear()
             cur = torch.cuda.current_stream(dev)
             losses = [None] * V
+            early = V - self.deferred_views          # views [0, early) finish inside their branch and ADD to the buffer
+            if early > 0:
+                flat.grad.zero_()
             for side in self._sides:
                 side.wait_stream(cur)
             outs = [None] * V
             for i in range(V):
                 with torch.cuda.stream(cur if i == 0 else self._sides[i - 1]):
-                    sink = dict(flat.grads, _defer=[], _stats=stats)
-                    out = renderer.render(view, sink=sink, cam_dev=self.cams[i], bones_dev=self.bones_all[i], device_intrinsics=True, slot=i)
+                    sink = dict(flat.grads, _stats=stats)
+                    if i >= early:
+                        sink["_defer"] = []
+                    out = renderer.render(view, sink=sink, cam_dev=self.cams[i], bones_dev=self.bones_all[i], device_intrinsics=True, slot=i,
+                                          accumulate=i < early)
                     self.states[i] = rz._Plan.last_state
                     self.viewspace[i] = out["viewspace_points"]
                     losses[i] = loss_fn(out["render"], self.targets[i])
@@ -367,7 +379,7 @@ class PipelinedStep:
                 with torch.cuda.stream(cur if i == 0 else self._sides[i - 1]):
                     losses[i].backward()
                     losses[i] = losses[i].detach()
-                    deferred.extend(outs[i]["_defer"])
+                    deferred.extend(outs[i].get("_defer", []))
             for i in range(1, V):
                 cur.wait_stream(self._sides[i - 1])
             return (losses[0] if V == 1 else torch.stack(losses).sum()), list(deferred)
@@ -375,7 +387,7 @@ class PipelinedStep:
         def back(defs, c):
             lo, hi = self.ranges[c]
             for i, d in enumerate(defs):
-                d.run(lo, hi, accumulate=i > 0)
+                d.run(lo, hi, accumulate=i > 0 or self.deferred_views < V)
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
