@@ -383,24 +383,28 @@ def main():
     # loop, so the default switches to the plain all-reduce above 4 ranks
     # the compact exchange carries ONE view per rank; with several views per rank and step the flat buffer is all-reduced
     compact = world > 1 and VIF == 1 and args.compact_exchange and not args.plain_allreduce
-    pipelined = world > 1 and not compact and not args.plain_allreduce and args.chunks > 0 and not args.no_graph
+    # the step object: PipelinedStep whenever a step holds several views (their pose backwards run as ONE multi-view pass over the
+    # Gaussians, range by range when there is an exchange to overlap); GraphedStep for one view per step
+    pipelined = not compact and not args.no_graph and (VIF > 1 or (world > 1 and not args.plain_allreduce and args.chunks > 0))
+    n_chunks = args.chunks if (world > 1 and args.chunks > 0 and not args.plain_allreduce) else 1
     from manus_b200.dist import CompactGradExchange, PipelinedStep
     exchange = CompactGradExchange(r) if compact else None
 
     def make_step(loss, target_like, vif=VIF, stats=None):
         if args.no_graph:
             return None
-        if pipelined:
-            # N > 1 (default): the pose backward runs range by range over the Gaussians and each finished range is all-reduced
-            # on the communicator's stream while the next one computes
-            return PipelinedStep(r, loss, target_like, view=views[0], views_in_flight=vif, chunks=args.chunks, stats=stats,
-                                 exchange=mc_exchange, exchange_ctas=args.exchange_ctas, deferred_views=args.deferred_views or None)
+        if pipelined and (vif > 1 or world > 1):
+            # the pose backward of all the step's views runs range by range over the Gaussians; with N > 1 each finished range is
+            # summed over the ranks on a side stream while the next one computes
+            return PipelinedStep(r, loss, target_like, view=views[0], views_in_flight=vif, chunks=n_chunks, stats=stats,
+                                 exchange=mc_exchange if n_chunks > 1 else None, exchange_ctas=args.exchange_ctas,
+                                 deferred_views=args.deferred_views or None, reduce=n_chunks > 1)
         return GraphedStep(r, loss, target_like, view=views[0], compact_sh=compact, views_in_flight=vif, stats=stats)
 
     graphed = make_step(loss_fn, G_dev)
 
     def reduce_gradients():
-        if pipelined:
+        if pipelined and n_chunks > 1:
             return                       # inside PipelinedStep.replay
         if exchange is not None:
             exchange()

@@ -202,6 +202,26 @@ int mb_pose_backward_from_raster(const mb_pose_inputs *in, const struct mb_raste
                                  float *xyz_gradient_accum /*[N] or NULL*/, float *denom /*[N]*/, float *max_radii2D /*[N]*/,
                                  mb_stream_t stream);
 
+/* The pose backward of ALL the views of one optimisation step in one pass (gradient accumulation over accum_iter views,
+ * src/modules/hand_dynamic.py:248,259-277): the parameters of a tile are staged once, every thread walks the views of its Gaussian
+ * (accumulator row, radius, pose and camera differ per view) and the summed parameter gradients are written once.  Same sums as
+ * num_views calls of mb_pose_backward_from_raster with accumulate = 1, a quarter of the HBM traffic at four views.
+ * `in`: the shared parameters (its bone_tf / bones_posed are ignored; bones_rest_inv / num_posed_bones are used with the views'
+ * bones_posed).  Skin-weight gradients are not produced here. */
+typedef struct mb_view_inputs {
+    const struct mb_raster_inputs *raster; /* the view's forward: camera, image size */
+    const int32_t *radii;                  /* [N] */
+    const void *grad_scratch;              /* accumulator rows of the view's mb_raster_backward_blend */
+    float *dL_dmeans2D;                    /* [N,3] out */
+    const float *bone_tf;                  /* [B,4,4], or NULL with bones_posed */
+    const float *bones_posed;              /* [num_posed_bones,4,4], or NULL with bone_tf */
+    const float *campos;                   /* [3] */
+} mb_view_inputs;
+int mb_pose_backward_from_raster_views(const mb_pose_inputs *in, int32_t num_views, const mb_view_inputs *views, float *g_xyz,
+                                       float *g_log_scale, float *g_quat, float *g_opacity_logit, float *g_f_dc, float *g_f_rest,
+                                       int32_t accumulate, float *xyz_gradient_accum, float *denom, float *max_radii2D,
+                                       mb_stream_t stream);
+
 /* Same, but the gradients are ADDED to the output buffers (bulk TMA reduce-add, fp32 adds resolved in L2): gradient
  * accumulation over the views of one optimisation step -- the reference's accum_iter loop, src/modules/hand_dynamic.py:248,
  * 259-277, where autograd accumulates every view's gradient into the parameters' .grad.  The caller orders the

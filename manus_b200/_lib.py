@@ -40,6 +40,12 @@ class PoseInputs(C.Structure):
     ]
 
 
+class ViewInputs(C.Structure):
+    """struct mb_view_inputs"""
+    _fields_ = [("raster", C.c_void_p), ("radii", C.c_void_p), ("grad_scratch", C.c_void_p), ("dL_dmeans2D", C.c_void_p),
+                ("bone_tf", C.c_void_p), ("bones_posed", C.c_void_p), ("campos", C.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol include/manus_b200.h declares
 SIGNATURES = {
     "mb_version": (C.c_int, []),
@@ -65,6 +71,8 @@ SIGNATURES = {
     "mb_pose_forward": (C.c_int, [C.POINTER(PoseInputs)] + [C.c_void_p] * 5 + [C.c_void_p]),
     "mb_pose_project_forward": (C.c_int, [C.POINTER(PoseInputs), C.POINTER(RasterInputs), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p] +
                                 [C.c_void_p] * 4 + [C.c_void_p]),
+    "mb_pose_backward_from_raster_views": (C.c_int, [C.POINTER(PoseInputs), C.c_int32, C.POINTER(ViewInputs)] + [C.c_void_p] * 6 +
+                                           [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mb_pose_backward": (C.c_int, [C.POINTER(PoseInputs)] + [C.c_void_p] * 4 + [C.c_void_p] * 7 + [C.c_void_p]),
     "mb_pose_backward_from_raster": (C.c_int, [C.POINTER(PoseInputs), C.POINTER(RasterInputs), C.c_void_p, C.c_void_p, C.c_void_p] +
                                      [C.c_void_p] * 7 + [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

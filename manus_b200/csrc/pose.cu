@@ -30,6 +30,16 @@ namespace mb {
 constexpr int kPoseThreads = MB_POSE_THREADS;   // Gaussians per tile = threads per CTA
 constexpr int kMaxBones = 64;
 constexpr int kMaxArrays = 12;
+constexpr int kMaxViews = 8;      // views of one step whose pose backward runs as ONE pass over the parameters
+
+struct ViewArgs {      // what differs between the views of a step (multi-view pose backward)
+    const float *acc;            // [N,12] accumulator rows of the view's tile backward
+    const int32_t *radii;        // [N]
+    const float *bone_tf, *bones_posed;   // the view's pose (one of the two; rest_inv is shared)
+    const float *campos, *view, *proj, *tanfov_dev;
+    float tanx, tany;
+    float *g_means2D;            // [N,3] out
+};
 
 struct PoseArgs {
     int N, n_skinned, B, deg, K, iso;
@@ -58,6 +68,8 @@ struct PoseArgs {
     int n_posed;
     // forward fused with the rasterizer's projection (mb_pose_project_forward): record, radius, tile rectangle, depth key of
     // every Gaussian are written from registers, the posed arrays only if their pointers are given
+    int n_views;               // > 0: multi-view backward (views[]); the single-view fields above are unused
+    ViewArgs views[kMaxViews];
     Record *rec;               // nullptr = plain pose forward
     ushort4 *rect;
     uint32_t *tiles_touched, *depth_key, *ident, *counters;
@@ -237,7 +249,7 @@ struct TilePipe {
             // upstream-gradient arrays (13 floats per Gaussian) and are transposed in place (run_tiles)
             t[n++] = {a.acc + (size_t)base * kAccRow, L.gpx, (uint32_t)(cnt * kAccRow * 4)};
             t[n++] = {reinterpret_cast<const float *>(a.radii) + base, L.gpx + kPoseThreads * kAccRow, (uint32_t)(cnt * 4)};
-        } else if (kBackward) {
+        } else if (kBackward && a.n_views == 0) {
             t[n++] = {a.g_posed_xyz + (size_t)base * 3, L.gpx, (uint32_t)(cnt * 12)};
             t[n++] = {a.g_cov6 + (size_t)base * 6, L.gcov, (uint32_t)(cnt * 24)};
             t[n++] = {a.g_colors + (size_t)base * 3, L.gcol, (uint32_t)(cnt * 12)};
@@ -665,6 +677,261 @@ __global__ void __launch_bounds__(kPoseThreads, kFused ? 4 : 1) pose_backward_ke
     });
 }
 
+// ---- multi-view pose backward --------------------------------------------------------------------------------------
+// The V views of one optimisation step (gradient accumulation, hand_dynamic.py:248,259-277) differ only in pose, camera and
+// in what their tile backward left in the accumulator rows; the parameters are the same.  One pass: a tile's parameters are
+// staged ONCE, every thread walks the V views of its Gaussian (its 48-byte accumulator row and radius come straight from global
+// memory, one view ahead), sums the parameter gradients in registers and writes them once -- instead of V launches that each
+// re-read 236 + 4B bytes of parameters per Gaussian and read-modify-write 236 bytes of gradients.  The f_rest gradient is
+// rank one per view, sum_v basis_k(dir_v) go_v[c]: the loop keeps (dir_v, go_v) and the rows are rebuilt after the last view
+// has read the coefficients.
+constexpr int kViewCam = 44;      // floats per view in shared memory: campos 3 (+1) | view 16 | proj 16 | tanx, tany, focx, focy | pad
+
+__host__ __device__ inline int multi_bones_floats(int B, int V) { return (V * B * 13 + 3) & ~3; }   // keeps what follows 16-byte aligned
+
+inline size_t pose_multi_smem_bytes(int B, int K, int iso, int V) {
+    return sizeof(float) * ((size_t)multi_bones_floats(B, V) + (size_t)V * kViewCam + 8) + sizeof(float) * (size_t)tile_layout(K, B, iso, true).floats;
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(kPoseThreads, 4) pose_backward_multi_kernel(PoseArgs a) {
+    extern __shared__ __align__(128) float smem[];
+    constexpr int nb = (DEG + 1) * (DEG + 1);
+    const int V = a.n_views;
+    float *bones_all = smem, *cams = bones_all + multi_bones_floats(a.B, V);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(cams + V * kViewCam);
+    TilePipe<true, false> pipe{a, tile_layout(a.K, a.B, a.iso, true), cams + V * kViewCam + 8, bar};
+    for (int j = threadIdx.x; j < V * a.B * 13; j += kPoseThreads) {
+        const int v = j / (a.B * 13), jj = j - v * (a.B * 13);
+        const int b = jj / 13, e = jj - 13 * b, idx = e < 12 ? e : 15;
+        const ViewArgs &w = a.views[v];
+        if (w.bones_posed == nullptr) bones_all[j] = w.bone_tf[16 * b + idx];
+        else if (b >= a.n_posed) bones_all[j] = (idx % 5 == 0) ? 1.f : 0.f;
+        else {
+            const int r = idx >> 2, c = idx & 3;
+            const float *P = w.bones_posed + 16 * b + 4 * r, *R = a.rest_inv + 16 * b + c;
+            bones_all[j] = fmaf(P[3], R[12], fmaf(P[2], R[8], fmaf(P[1], R[4], P[0] * R[0])));
+        }
+    }
+    for (int j = threadIdx.x; j < V * kViewCam; j += kPoseThreads) {
+        const int v = j / kViewCam, e = j - v * kViewCam;
+        const ViewArgs &w = a.views[v];
+        float val = 0.f;
+        if (e < 3) val = w.campos[e];
+        else if (e >= 4 && e < 20) val = w.view[e - 4];
+        else if (e >= 20 && e < 36) val = w.proj[e - 20];
+        else if (e >= 36 && e < 40) {
+            const float tx = w.tanfov_dev ? w.tanfov_dev[0] : w.tanx, ty = w.tanfov_dev ? w.tanfov_dev[1] : w.tany;
+            val = e == 36 ? tx : e == 37 ? ty : e == 38 ? a.W / (2.0f * tx) : a.H / (2.0f * ty);
+        }
+        cams[j] = val;
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const TileLayout &L = pipe.L;
+    const int ntiles = (a.N + kPoseThreads - 1) / kPoseThreads;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_wait_read_all();
+            pipe.prefetch(tile, 0);
+        }
+        __syncthreads();
+        const int row = threadIdx.x, i = tile * kPoseThreads + row;
+        // the first view's accumulator row is requested before the tile's parameters have arrived
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+        int rad = 0;
+        if (i < a.N) {
+            const float4 *rp = reinterpret_cast<const float4 *>(a.views[0].acc + (size_t)i * kAccRow);
+            r0 = __ldg(rp); r1 = __ldg(rp + 1); r2 = __ldg(rp + 2);
+            rad = __ldg(a.views[0].radii + i);
+        }
+        pipe.acquire(tile, 0, phase);
+        if (i < a.N) {
+            float *st = pipe.stage(0);
+            PoseLocal p;
+            // ---- view-independent part: rotation, scales, L = R diag(S)
+            p.x[0] = st[L.xyz + 3 * row]; p.x[1] = st[L.xyz + 3 * row + 1]; p.x[2] = st[L.xyz + 3 * row + 2];
+            p.skinned = i < a.n_skinned;
+            {
+                const float4 q = *reinterpret_cast<const float4 *>(st + L.quat + 4 * row);
+                p.qnorm = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+                p.qn[0] = q.x / p.qnorm; p.qn[1] = q.y / p.qnorm; p.qn[2] = q.z / p.qnorm; p.qn[3] = q.w / p.qnorm;
+                quat_to_rot(p.qn[0], p.qn[1], p.qn[2], p.qn[3], p.R);
+                if (a.iso) p.S[0] = p.S[1] = p.S[2] = expf(st[L.ls + row]);
+                else { p.S[0] = expf(st[L.ls + 3 * row]); p.S[1] = expf(st[L.ls + 3 * row + 1]); p.S[2] = expf(st[L.ls + 3 * row + 2]); }
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) p.L[3 * r + k] = p.R[3 * r + k] * p.S[k];
+            }
+            const float op = 1.0f / (1.0f + expf(-st[L.opac + row]));
+            const float *fr = st + L.fr + row * (a.K - 1) * 3;
+            const float fdc[3] = {st[L.fdc + 3 * row], st[L.fdc + 3 * row + 1], st[L.fdc + 3 * row + 2]};
+            float gx[3] = {0.f, 0.f, 0.f}, dLs[9], gop = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) dLs[k] = 0.f;
+            float go_v[kMaxViews][3], dir_v[kMaxViews][3];
+            for (int v = 0; v < V; ++v) {
+                const float4 c0 = r0, c1 = r1, c2 = r2;
+                const int crad = rad;
+                if (v + 1 < V) {      // next view's row in flight while this one is processed
+                    const float4 *rp = reinterpret_cast<const float4 *>(a.views[v + 1].acc + (size_t)i * kAccRow);
+                    r0 = __ldg(rp); r1 = __ldg(rp + 1); r2 = __ldg(rp + 2);
+                    rad = __ldg(a.views[v + 1].radii + i);
+                }
+                const float *bones_s = bones_all + v * a.B * 13, *cam = cams + v * kViewCam;
+                // ---- the view's blended transform
+                if (p.skinned) {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) p.A[k] = 0.f;
+                    p.t[0] = p.t[1] = p.t[2] = 0.f; p.s = 0.f;
+                    const float *w_row = st + L.sk + row * a.B;
+                    for (int b = 0; b < a.B; ++b) {
+                        const float w = w_row[b];
+                        if (w == 0.f) continue;
+                        const float *T = bones_s + 13 * b;
+                        p.A[0] += w * T[0]; p.A[1] += w * T[1]; p.A[2] += w * T[2]; p.t[0] += w * T[3];
+                        p.A[3] += w * T[4]; p.A[4] += w * T[5]; p.A[5] += w * T[6]; p.t[1] += w * T[7];
+                        p.A[6] += w * T[8]; p.A[7] += w * T[9]; p.A[8] += w * T[10]; p.t[2] += w * T[11];
+                        p.s += w * T[12];
+                    }
+                } else {
+                    p.A[0] = p.A[4] = p.A[8] = 1.f;
+                    p.A[1] = p.A[2] = p.A[3] = p.A[5] = p.A[6] = p.A[7] = 0.f;
+                    p.t[0] = p.t[1] = p.t[2] = 0.f; p.s = 1.f;
+                }
+                float Bm[9];
+                if (p.skinned) mat3_mul(p.A, p.L, Bm);
+                else {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) Bm[k] = p.L[k];
+                }
+                // ---- projection backward from the view's accumulator row
+                float gp[3] = {0.f, 0.f, 0.f}, g6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, g2[2] = {0.f, 0.f};
+                if (crad > 0) {
+                    float pm[3], c6[6];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) pm[r] = p.A[3 * r] * p.x[0] + p.A[3 * r + 1] * p.x[1] + p.A[3 * r + 2] * p.x[2] + p.t[r];
+                    c6[0] = Bm[0] * Bm[0] + Bm[1] * Bm[1] + Bm[2] * Bm[2];
+                    c6[1] = Bm[0] * Bm[3] + Bm[1] * Bm[4] + Bm[2] * Bm[5];
+                    c6[2] = Bm[0] * Bm[6] + Bm[1] * Bm[7] + Bm[2] * Bm[8];
+                    c6[3] = Bm[3] * Bm[3] + Bm[4] * Bm[4] + Bm[5] * Bm[5];
+                    c6[4] = Bm[3] * Bm[6] + Bm[4] * Bm[7] + Bm[5] * Bm[8];
+                    c6[5] = Bm[6] * Bm[6] + Bm[7] * Bm[7] + Bm[8] * Bm[8];
+                    const float m[5] = {c0.x, c0.y, c0.z, c0.w, c1.x};
+                    project_backward(cam + 4, cam + 20, cam[36], cam[37], cam[38], cam[39], a.W, a.H, pm[0], pm[1], pm[2], c6, op, m, g2, gp, g6);
+                }
+                float *gm = a.views[v].g_means2D + 3 * (size_t)i;
+                gm[0] = g2[0]; gm[1] = g2[1]; gm[2] = 0.f;
+                if (a.stat_accum && crad > 0) {
+                    atomicAdd(a.stat_accum + i, sqrtf(g2[0] * g2[0] + g2[1] * g2[1]));
+                    atomicAdd(a.stat_denom + i, 1.0f);
+                    atomicMax(reinterpret_cast<int *>(a.stat_maxrad) + i, __float_as_int((float)crad));
+                }
+                gop += c1.y;
+                // ---- mean and covariance
+#pragma unroll
+                for (int r = 0; r < 3; ++r) gx[r] += p.A[r] * gp[0] + p.A[3 + r] * gp[1] + p.A[6 + r] * gp[2];
+                const float Gs[9] = {g6[0], 0.5f * g6[1], 0.5f * g6[2], 0.5f * g6[1], g6[3], 0.5f * g6[4], 0.5f * g6[2], 0.5f * g6[4], g6[5]};
+                float dB[9];
+                mat3_mul(Gs, Bm, dB);
+                if (p.skinned) {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) dLs[3 * r + c] += 2.f * (p.A[r] * dB[c] + p.A[3 + r] * dB[3 + c] + p.A[6 + r] * dB[6 + c]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) dLs[k] += 2.f * dB[k];
+                }
+                // ---- colour: the view direction in canonical space
+                float Ainv[9], ci[3], dir[3], basis[16], bxg[16], byg[16], bzg[16];
+                if (p.skinned) mat3_inverse(p.A, Ainv);
+                const float dn = view_dir(p, cam, Ainv, ci, dir);
+                sh_basis(DEG, dir[0], dir[1], dir[2], basis);
+                sh_basis_grad(DEG, dir[0], dir[1], dir[2], bxg, byg, bzg);
+                const float gcol[3] = {c1.z, c1.w, c2.x};
+                float go[3], gd[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float val = basis[0] * fdc[c];
+#pragma unroll
+                    for (int k = 1; k < nb; ++k) val += basis[k] * fr[3 * (k - 1) + c];
+                    go[c] = (val + 0.5f >= 0.f) ? gcol[c] : 0.f;
+                }
+#pragma unroll
+                for (int k = 1; k < nb; ++k)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float sv = fr[3 * (k - 1) + c] * go[c];
+                        gd[0] += bxg[k] * sv; gd[1] += byg[k] * sv; gd[2] += bzg[k] * sv;
+                    }
+                const float dot = dir[0] * gd[0] + dir[1] * gd[1] + dir[2] * gd[2];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    gx[r] += (gd[r] - dir[r] * dot) / dn;
+                    go_v[v][r] = go[r];
+                    dir_v[v][r] = dir[r];
+                }
+            }
+            // ---- view-independent tail: scale / rotation gradients from the summed dL/dL
+            float dS[3], dR[9], dqn[4];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                dS[k] = dLs[k] * p.R[k] + dLs[3 + k] * p.R[3 + k] + dLs[6 + k] * p.R[6 + k];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) dR[3 * r + k] = dLs[3 * r + k] * p.S[k];
+            }
+            quat_to_rot_bwd(p.qn[0], p.qn[1], p.qn[2], p.qn[3], dR, dqn);
+            const float qd = p.qn[0] * dqn[0] + p.qn[1] * dqn[1] + p.qn[2] * dqn[2] + p.qn[3] * dqn[3];
+            float4 gq;
+            gq.x = (dqn[0] - p.qn[0] * qd) / p.qnorm; gq.y = (dqn[1] - p.qn[1] * qd) / p.qnorm;
+            gq.z = (dqn[2] - p.qn[2] * qd) / p.qnorm; gq.w = (dqn[3] - p.qn[3] * qd) / p.qnorm;
+            *reinterpret_cast<float4 *>(st + L.quat + 4 * row) = gq;
+            if (a.iso) st[L.ls + row] = dS[0] * p.S[0] + dS[1] * p.S[1] + dS[2] * p.S[2];
+            else {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) st[L.ls + 3 * row + k] = dS[k] * p.S[k];
+            }
+            // ---- SH gradients: sum over the views of basis_k(dir_v) go_v (the coefficient rows are no longer needed)
+            float gdc[3] = {0.f, 0.f, 0.f};
+            float *frw = st + L.fr + row * (a.K - 1) * 3;
+            for (int v = 0; v < V; ++v) {
+                float basis[16];
+                sh_basis(DEG, dir_v[v][0], dir_v[v][1], dir_v[v][2], basis);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) gdc[c] += basis[0] * go_v[v][c];
+                if (a.g_f_rest) {
+#pragma unroll
+                    for (int k = 1; k < nb; ++k)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float t = basis[k] * go_v[v][c];
+                            frw[3 * (k - 1) + c] = v == 0 ? t : frw[3 * (k - 1) + c] + t;
+                        }
+                }
+            }
+            if (a.g_f_rest)
+                for (int k = nb; k < a.K; ++k)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) frw[3 * (k - 1) + c] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) st[L.gcol + 3 * row + c] = gdc[c];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) st[L.gpx + 3 * row + r] = gx[r];
+            st[L.gop + row] = gop * op * (1.0f - op);
+        }
+        pipe.release(tile, 0);
+    }
+    if (threadIdx.x == 0) bulk_wait_all();
+}
+
 // Rebuilds the SH-coefficient gradients of a sum over R views from what every view contributes through its DC term.
 // For one view, g_f_dc[c] = basis_0 * go[c] and g_f_rest[k][c] = basis_k(dir) * go[c], where go is the colour gradient after
 // the clamp mask and dir the view direction in canonical space (function of the view's bone transforms and camera centre).
@@ -968,6 +1235,79 @@ extern "C" int mb_pose_backward_from_raster(const mb_pose_inputs *in, const mb_r
     a.view = raster->viewmatrix; a.proj = raster->projmatrix; a.tanfov_dev = raster->tanfov_dev;
     a.tanx = raster->tanfovx; a.tany = raster->tanfovy; a.W = raster->image_width; a.H = raster->image_height;
     return launch_pose_deg(a, true, (cudaStream_t)stream);
+}
+
+template <int DEG>
+static int launch_pose_multi(const PoseArgs &a, cudaStream_t s) {
+    const size_t smem = pose_multi_smem_bytes(a.B, a.K, a.iso, a.n_views);
+    int per_sm = (int)((size_t)(220 * 1024) / smem);
+    if (per_sm < 1) {
+        set_error("multi-view pose backward: %d views x %d bones and a tile of %d Gaussians need %zu bytes of shared memory", a.n_views, a.B,
+                  kPoseThreads, smem);
+        return MB_ERR_INVALID;
+    }
+    if (per_sm > 4) per_sm = 4;
+    const int ntiles = (a.N + kPoseThreads - 1) / kPoseThreads;
+    const int grid = min(ntiles, sm_count() * per_sm);
+    static thread_local int limit[16] = {};
+    int dev = 0;
+    MB_CUDA(cudaGetDevice(&dev));
+    if (limit[dev & 15] < (int)smem) {
+        MB_CUDA(cudaFuncSetAttribute(pose_backward_multi_kernel<DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        limit[dev & 15] = (int)smem;
+    }
+    KernelTimer kt("pose_backward", s);
+    pose_backward_multi_kernel<DEG><<<grid, kPoseThreads, smem, s>>>(a);
+    return check_launch("pose_backward_multi", false, s);
+}
+
+extern "C" int mb_pose_backward_from_raster_views(const mb_pose_inputs *in, int32_t num_views, const mb_view_inputs *views, float *g_xyz,
+                                                 float *g_log_scale, float *g_quat, float *g_opacity_logit, float *g_f_dc, float *g_f_rest,
+                                                 int32_t accumulate, float *xyz_gradient_accum, float *denom, float *max_radii2D,
+                                                 mb_stream_t stream) {
+    MB_REQUIRE(in != nullptr && views != nullptr && num_views >= 1 && num_views <= kMaxViews, "mb_pose_backward_from_raster_views: 1..%d views", kMaxViews);
+    // the per-view bone transforms replace those of `in`; everything else of `in` is validated as usual
+    mb_pose_inputs chk = *in;
+    chk.bone_tf = views[0].bone_tf; chk.bones_posed = views[0].bones_posed;
+    int rc = validate_pose(&chk, "mb_pose_backward_from_raster_views");
+    if (rc) return rc;
+    if (in->num_points == 0) return MB_OK;
+    MB_REQUIRE(g_xyz && g_log_scale && g_quat && g_opacity_logit && g_f_dc, "mb_pose_backward_from_raster_views: null output");
+    MB_REQUIRE((xyz_gradient_accum != nullptr) == (denom != nullptr) && (denom != nullptr) == (max_radii2D != nullptr),
+               "mb_pose_backward_from_raster_views: give all three densification statistics or none");
+    PoseArgs a = pose_args(in);
+    a.g_xyz = g_xyz; a.g_log_scale = g_log_scale; a.g_quat = g_quat; a.g_opacity_logit = g_opacity_logit;
+    a.g_f_dc = g_f_dc; a.g_f_rest = g_f_rest; a.g_skin = nullptr;
+    a.accumulate = accumulate;
+    a.stat_accum = xyz_gradient_accum; a.stat_denom = denom; a.stat_maxrad = max_radii2D;
+    a.n_views = num_views;
+    for (int v = 0; v < num_views; ++v) {
+        const mb_view_inputs &w = views[v];
+        const mb_raster_inputs *r = w.raster;
+        MB_REQUIRE(r != nullptr && r->num_points == in->num_points, "mb_pose_backward_from_raster_views: view %d: raster inputs missing or of another size", v);
+        MB_REQUIRE(r->viewmatrix && r->projmatrix && r->image_width > 0 && r->image_height > 0 && (r->tanfov_dev || (r->tanfovx > 0.f && r->tanfovy > 0.f)),
+                   "mb_pose_backward_from_raster_views: view %d: camera missing", v);
+        MB_REQUIRE(r->shs == nullptr && r->scales == nullptr && r->scale_modifier == 1.0f,
+                   "mb_pose_backward_from_raster_views: view %d: the rasterizer must have run on this pose's colours and covariances", v);
+        MB_REQUIRE(v == 0 || (r->image_width == views[0].raster->image_width && r->image_height == views[0].raster->image_height),
+                   "mb_pose_backward_from_raster_views: the views of a step share the image size");
+        MB_REQUIRE(w.radii && w.grad_scratch && w.dL_dmeans2D && w.campos, "mb_pose_backward_from_raster_views: view %d: null radii / accumulator / dL_dmeans2D / campos", v);
+        MB_REQUIRE(in->num_skinned == 0 || w.bone_tf || (w.bones_posed && in->bones_rest_inv), "mb_pose_backward_from_raster_views: view %d: bone transforms missing", v);
+        MB_REQUIRE((w.bones_posed != nullptr) == (views[0].bones_posed != nullptr), "mb_pose_backward_from_raster_views: give every view's bones the same way");
+        ViewArgs &o = a.views[v];
+        o.acc = reinterpret_cast<const float *>(w.grad_scratch); o.radii = w.radii; o.bone_tf = w.bone_tf; o.bones_posed = w.bones_posed;
+        o.campos = w.campos; o.view = r->viewmatrix; o.proj = r->projmatrix; o.tanfov_dev = r->tanfov_dev; o.tanx = r->tanfovx; o.tany = r->tanfovy;
+        o.g_means2D = w.dL_dmeans2D;
+    }
+    a.bones_posed = views[0].bones_posed;      // selects the in-kernel product (rest_inv / n_posed come from `in`)
+    a.W = views[0].raster->image_width; a.H = views[0].raster->image_height;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (a.deg) {
+        case 0: return launch_pose_multi<0>(a, s);
+        case 1: return launch_pose_multi<1>(a, s);
+        case 2: return launch_pose_multi<2>(a, s);
+        default: return launch_pose_multi<3>(a, s);
+    }
 }
 
 extern "C" int mb_pose_backward_accumulate(const mb_pose_inputs *in, const float *g_posed_xyz, const float *g_posed_cov6,

@@ -312,13 +312,15 @@ class PipelinedStep:
     (per element: the same operands; the order over ranks is NCCL's in both cases).
 
     group=None and no initialised process group: single rank, no collective (used by the tests to check the chunked backward).
+    fused_views: the deferred pose backwards of a range run as ONE kernel pass over all their views
+    (mb_pose_backward_from_raster_views) instead of one launch per view.
     stats = (xyz_gradient_accum [N,1], denom [N,1], max_radii2D [N]): the densification statistics of every view are updated by
     the pose backward kernel itself (``GaussianState.add_densification_stats`` semantics; they are per-rank sums / maxima until
     ``GaussianState.reduce_stats`` combines them, once per densification interval)."""
 
     def __init__(self, renderer: SceneRenderer, loss_fn, target_like: torch.Tensor, view: int = 0, views_in_flight: int = 1,
                  chunks: int = 4, warmup: int = 3, group=None, stats=None, exchange=None, exchange_ctas: int = 0,
-                 deferred_views: Optional[int] = None):
+                 deferred_views: Optional[int] = None, fused_views: bool = True, reduce: bool = True):
         from . import rasterizer as rz
 
         # deferred_views = d: only the LAST d views of the step leave their pose backward for the range-by-range tail; the others
@@ -334,7 +336,8 @@ class PipelinedStep:
         if rz._Plan.mode != "reserve":
             raise RuntimeError("PipelinedStep needs set_capacity_mode('reserve') and reserve_capacity(...) (no host read-back in a graph)")
         self.r, self.V, self.group = renderer, int(views_in_flight), group
-        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        # reduce=False: replay() leaves the exchange to the caller (e.g. one all-reduce of the whole buffer after the step)
+        self.world = dist.get_world_size(group) if (reduce and dist.is_available() and dist.is_initialized()) else 1
         dev = renderer.device
         V = self.V
         _, cam_host, bones_host = renderer.view_inputs_host(view)
@@ -386,8 +389,13 @@ class PipelinedStep:
 
         def back(defs, c):
             lo, hi = self.ranges[c]
-            for i, d in enumerate(defs):
-                d.run(lo, hi, accumulate=i > 0 or self.deferred_views < V)
+            if fused_views and len(defs) <= 8:
+                # ONE pass over the range for all deferred views (parameters staged once, gradients written once)
+                from .render import pose_backward_views
+                pose_backward_views(defs, lo, hi, accumulate=self.deferred_views < V)
+            else:
+                for i, d in enumerate(defs):
+                    d.run(lo, hi, accumulate=i > 0 or self.deferred_views < V)
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -423,7 +431,7 @@ class PipelinedStep:
         reaches the end of what this call enqueued."""
         self.graph_front.replay()
         works = []
-        if self.exchange is not None:
+        if self.exchange is not None and self.world > 1:
             cur = torch.cuda.current_stream(self.r.device)
             for c, g in enumerate(self.graph_back):
                 g.replay()

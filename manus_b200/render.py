@@ -149,6 +149,50 @@ class DeferredPoseBackward:
                        "mb_pose_backward_from_raster")
 
 
+def pose_backward_views(defs, lo: int, hi: int, accumulate: bool) -> None:
+    """The deferred pose backwards of ALL the views of a step over Gaussians [lo, hi) in ONE kernel pass
+    (mb_pose_backward_from_raster_views): the parameters are staged once per tile, every thread walks the views of its Gaussian.
+    ``defs``: the DeferredPoseBackward objects of the step's views (same parameters, same gradient sink)."""
+    L = _lib.lib()
+    d0 = defs[0]
+    t, N = d0.t, d0.t[0].shape[0]
+    if lo % 128 or not (0 <= lo < hi <= N):
+        raise ValueError(f"bad Gaussian range [{lo}, {hi}) of {N} (lo must be a multiple of 128)")
+    n, ns = hi - lo, max(0, min(d0.num_skinned, hi) - lo)
+    row = lambda v: None if v is None else v[lo:hi]
+    skin = None if (t[6] is None or ns == 0) else t[6][lo:lo + ns]
+    pi = _inputs(*([row(v) for v in t[:6]] + [skin, t[7]]), d0.cam, d0.sh_degree, d0.isotropic, ns)
+    if skin is None and t[6] is not None:
+        pi.num_bones = t[6].shape[1]
+    views = (_lib.ViewInputs * len(defs))()
+    keep = []
+    for k, d in enumerate(defs):
+        if d.t[0].data_ptr() != t[0].data_ptr() or d.grads[0].data_ptr() != d0.grads[0].data_ptr():
+            raise RuntimeError("the views of a step must share their parameters and their gradient sink")
+        ri = type(d.st.inputs)()
+        C.memmove(C.byref(ri), C.byref(d.st.inputs), C.sizeof(ri))
+        ri.num_points = n
+        keep.append(ri)
+        w = views[k]
+        w.raster = C.addressof(ri)
+        w.radii = d.st.radii.data_ptr() + 4 * lo
+        w.grad_scratch = d.scratch.data_ptr() + 48 * lo
+        w.dL_dmeans2D = d.g_means2D.data_ptr() + 12 * lo
+        bt = d.t[7]
+        if isinstance(bt, (tuple, list)):
+            w.bone_tf, w.bones_posed = None, bt[0].data_ptr()
+        else:
+            w.bone_tf, w.bones_posed = ptr(bt), None
+        w.campos = d.cam.data_ptr()
+    g = [row(v) for v in d0.grads]
+    dev = t[0].device
+    with torch.cuda.device(dev):
+        _lib.check(L.mb_pose_backward_from_raster_views(C.byref(pi), len(defs), views, ptr(g[0]), ptr(g[1]), ptr(g[2]), ptr(g[3]), ptr(g[4]),
+                                                        ptr(g[5]) if g[5] is not None and g[5].numel() else None, int(accumulate),
+                                                        *_stat_ptrs(d0.stats, N, lo), torch.cuda.current_stream(dev).cuda_stream),
+                   "mb_pose_backward_from_raster_views")
+
+
 def _stat_ptrs(stats, n: int, lo: int = 0):
     """(xyz_gradient_accum, denom, max_radii2D) -> the three device pointers (offset by ``lo`` Gaussians), or three NULLs."""
     if stats is None:

@@ -124,7 +124,7 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
     gcc = shutil.which("gcc")
     if gcc is None:
         pytest.skip("gcc not available")
-    pairs = (("mb_raster_inputs", _lib.RasterInputs), ("mb_pose_inputs", _lib.PoseInputs))
+    pairs = (("mb_raster_inputs", _lib.RasterInputs), ("mb_pose_inputs", _lib.PoseInputs), ("mb_view_inputs", _lib.ViewInputs))
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "manus_b200.h"', "int main(void) {"]
     for cname, cls in pairs:
         lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')

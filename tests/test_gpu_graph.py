@@ -139,8 +139,9 @@ def test_views_in_flight_sum_the_single_view_gradients(built_lib, V, ordered):
         rz.set_capacity_mode("exact")
 
 
-@pytest.mark.parametrize("V,chunks,deferred", [(1, 1, None), (2, 3, None), (3, 5, None), (3, 4, 1), (3, 2, 2)])
-def test_pipelined_step_equals_the_sum_of_single_view_gradients(built_lib, V, chunks, deferred):
+@pytest.mark.parametrize("V,chunks,deferred,fused", [(1, 1, None, True), (2, 3, None, True), (3, 5, None, True), (3, 4, 1, True), (3, 2, 2, True),
+                                                   (3, 3, None, False), (2, 2, 1, False)])
+def test_pipelined_step_equals_the_sum_of_single_view_gradients(built_lib, V, chunks, deferred, fused):
     """PipelinedStep: tile backward of every view inside one graph, pose backward afterwards range by range over the Gaussians
     (view 0 overwrites a range, the others add) -- the single-rank half of the data-parallel step that all-reduces a finished
     range while the next one computes.  Same gradients as accumulating the views one by one; ranges that do not divide N."""
@@ -168,7 +169,7 @@ def test_pipelined_step_equals_the_sum_of_single_view_gradients(built_lib, V, ch
         from manus_b200.densify import GaussianState
         gs = GaussianState(r.flat)
         stats = (gs.xyz_gradient_accum, gs.denom, gs.max_radii2D)
-        step = PipelinedStep(r, loss_fn, targets[0], view=2, views_in_flight=V, chunks=chunks, stats=stats, deferred_views=deferred)
+        step = PipelinedStep(r, loss_fn, targets[0], view=2, views_in_flight=V, chunks=chunks, stats=stats, deferred_views=deferred, fused_views=fused)
         ref_stats = GaussianState(r.flat)
         assert len(step.ranges) == chunks
         for rep in range(2):

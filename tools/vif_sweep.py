@@ -8,7 +8,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from manus_b200 import rasterizer as rz, synth  # noqa: E402
-from manus_b200.dist import GraphedStep, SceneRenderer  # noqa: E402
+from manus_b200.dist import GraphedStep, PipelinedStep, SceneRenderer  # noqa: E402
 
 specs = sys.argv[1:] or ["1", "2", "4", "4o", "6", "8"]
 W, H, NV = 1920, 1080, 50
@@ -29,8 +29,13 @@ rz.set_capacity_mode("reserve", margin=1.4)
 rz.reserve_capacity(0, scene.n, H, W, dmax)
 loss_fn = lambda image, target: (image * target).sum()
 for spec in specs:
-    V, ordered = int(spec.rstrip("o")), spec.endswith("o")
-    step = GraphedStep(r, loss_fn, G, view=0, views_in_flight=V, ordered=ordered)
+    # suffixes: o = ordered accumulation; p / pN = PipelinedStep with 1 / N ranges (all pose backwards in one multi-view pass)
+    if "p" in spec:
+        V, chunks = int(spec.split("p")[0]), int(spec.split("p")[1] or 1)
+        step = PipelinedStep(r, loss_fn, G, view=0, views_in_flight=V, chunks=chunks)
+    else:
+        V, ordered = int(spec.rstrip("o")), spec.endswith("o")
+        step = GraphedStep(r, loss_fn, G, view=0, views_in_flight=V, ordered=ordered)
     K = max(20, 400 // V)
 
     def run(n, base):
