@@ -50,12 +50,13 @@ def parse():
                     help="views per rank and step, captured on parallel streams of the step's CUDA graph and accumulated into one "
                          "gradient buffer (the reference's accum_iter); 1 = one view per step")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python each step instead of replaying the captured CUDA graph")
-    ap.add_argument("--chunks", type=int, default=4,
+    ap.add_argument("--chunks", type=int, default=-1,
                     help="N > 1: ranges of Gaussians whose pose backward + all-reduce are pipelined (manus_b200.dist.PipelinedStep); "
-                         "0 = one all-reduce of the flat buffer after the step")
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "multimem"],
+                         "0 = one all-reduce of the flat buffer after the step; -1 = auto (measured on B200 / NVSwitch: 0 at N = 2, 4 above)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "multimem"],
                     help="N > 1: who sums the gradient ranges over the ranks -- NCCL (coalesced all-reduce per range) or the repository's "
-                         "own multimem.ld_reduce / multimem.st kernel over NVSwitch multicast memory (csrc/exchange.cu)")
+                         "own multimem.ld_reduce / multimem.st kernel over NVSwitch multicast memory (csrc/exchange.cu); auto = multimem "
+                         "for N >= 4 when the system offers multicast (at N = 2 NCCL's 118 MB all-reduce is faster: 253 vs 340 us)")
     ap.add_argument("--deferred-views", type=int, default=0,
                     help="N > 1: views per rank whose pose backward runs in the range-by-range tail (the others finish inside their branch); 0 = all")
     ap.add_argument("--exchange-ctas", type=int, default=32, help="CTAs of the multimem exchange kernel (it runs beside the pose backward)")
@@ -346,6 +347,10 @@ def main():
     scene = make_scene(args)
     r = SceneRenderer(scene, dev, W, H)
     mc_exchange, mc_note = None, None
+    if args.chunks < 0:
+        args.chunks = 4 if world >= 4 else 0
+    if args.exchange == "auto":
+        args.exchange = "multimem" if world >= 4 else "nccl"
     if world > 1 and args.exchange == "multimem":
         # the gradient buffer moves into NVSwitch multicast memory BEFORE anything captures its address
         try:
