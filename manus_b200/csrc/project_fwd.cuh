@@ -24,11 +24,12 @@ __device__ __forceinline__ float dot3(float a, float b, float c, float x, float 
 }
 
 __device__ __forceinline__ void tile_rect(float px, float py, int rad, int gx, int gy, int &x0, int &y0, int &x1, int &y1) {
-    const float r = (float)rad, t = (float)kTile;
-    x0 = min(gx, max(0, (int)div_(sub_(px, r), t)));
-    y0 = min(gy, max(0, (int)div_(sub_(py, r), t)));
-    x1 = min(gx, max(0, (int)div_(sub_(add_(add_(px, r), t), 1.0f), t)));   // (px + rad + BLOCK - 1) / BLOCK, left to right
-    y1 = min(gy, max(0, (int)div_(sub_(add_(add_(py, r), t), 1.0f), t)));
+    // division by BLOCK = 16: the multiplication by 1/16 is the same IEEE result (power of two)
+    const float r = (float)rad, t = (float)kTile, it = 1.0f / (float)kTile;
+    x0 = min(gx, max(0, (int)mul_(sub_(px, r), it)));
+    y0 = min(gy, max(0, (int)mul_(sub_(py, r), it)));
+    x1 = min(gx, max(0, (int)mul_(sub_(add_(add_(px, r), t), 1.0f), it)));   // (px + rad + BLOCK - 1) / BLOCK, left to right
+    y1 = min(gy, max(0, (int)mul_(sub_(add_(add_(py, r), t), 1.0f), it)));
 }
 
 struct Projected {
@@ -114,11 +115,11 @@ __device__ __forceinline__ void project_forward(const float *v, const float *p, 
     // radii and visibility stay upstream's).
     uint32_t tiles = 0;
     if (ex >= 0.f && ey >= 0.f) {
-        const float t = (float)kTile;
-        x0 = max(x0, (int)floorf(div_(sub_(px, ex), t)));
-        y0 = max(y0, (int)floorf(div_(sub_(py, ey), t)));
-        x1 = min(x1, (int)floorf(div_(add_(px, ex), t)) + 1);
-        y1 = min(y1, (int)floorf(div_(add_(py, ey), t)) + 1);
+        const float it = 1.0f / (float)kTile;
+        x0 = max(x0, (int)floorf(mul_(sub_(px, ex), it)));
+        y0 = max(y0, (int)floorf(mul_(sub_(py, ey), it)));
+        x1 = min(x1, (int)floorf(mul_(add_(px, ex), it)) + 1);
+        y1 = min(y1, (int)floorf(mul_(add_(py, ey), it)) + 1);
         tiles = (uint32_t)(max(x1 - x0, 0) * max(y1 - y0, 0));
     }
     if (tiles == 0) x0 = y0 = x1 = y1 = 0;
