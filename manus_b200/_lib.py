@@ -9,6 +9,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MANUS_B200_LIB") or os.path.join(_HERE, "lib", "libmanus_b200.so")   # env override: kernel experiments
+if os.environ.get("MANUS_B200_LIB"):
+    import sys as _sys
+    print(f"manus_b200: MANUS_B200_LIB is set -- loading {LIB_PATH} instead of the in-tree library", file=_sys.stderr)
 
 f32p = C.POINTER(C.c_float)
 i32p = C.POINTER(C.c_int32)

@@ -319,130 +319,6 @@ __device__ __forceinline__ float reduce_scatter9(const float (&v)[9], int lane) 
     return d;
 }
 
-#ifndef MB_BWD_WARPS_PER_SM
-#define MB_BWD_WARPS_PER_SM 32
-#endif
-// One work item = one segment [seg*kSeg, min((seg+1)*kSeg, maxlast)) of one (half / quarter) tile's list, walked back to
-// front.  A pixel whose last contributor lies beyond the segment starts from the forward's checkpoint in front of the far
-// end: T = transmittance there, accumulated "colour behind" = (C_final - C_front) / T; a pixel whose last contributor is
-// inside (or in front of) the segment starts from (T_final, 0) exactly like the unsegmented recurrence.
-template <int kWarps>
-__global__ void __launch_bounds__(kWarps * 32, MB_BWD_WARPS_PER_SM / kWarps) blend_backward_kernel(
-    const Record *__restrict__ recs, const uint32_t *__restrict__ list, const uint2 *__restrict__ ranges,
-    const uint2 *__restrict__ items, const uint32_t *__restrict__ n_items, const uint32_t *__restrict__ tile_maxlast, int W, int H,
-    int gx, const float *__restrict__ bg, const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
-    const float4 *__restrict__ ckpt, const float *__restrict__ dL_dout, int64_t sc, int64_t sy, int64_t sx,
-    float *__restrict__ acc) {
-    constexpr int kSplit = 8 / kWarps;
-    __shared__ __align__(128) StageSmem<kWarps> sm;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int item = blockIdx.x / kSplit, sub = blockIdx.x % kSplit;
-    if ((uint32_t)item >= *n_items) return;
-    const uint2 it = items[item];
-    const int tile = (int)it.x;
-    const uint32_t s0 = it.y * (uint32_t)kSeg;
-    const uint32_t s1 = min(s0 + (uint32_t)kSeg, tile_maxlast[tile]);   // list positions [s0, s1) of this tile
-    const int len = (int)(s1 - s0);
-    const uint2 range = ranges[tile];
-    int px, py;
-    pixel_of_thread(tile, gx, sub * kWarps + warp, lane, px, py);
-    const bool inside = px < W && py < H;
-    const float fx = (float)px, fy = (float)py;
-    const size_t pix = (size_t)py * W + px;
-    const float T_final = inside ? final_T[pix] : 0.f;
-    const uint32_t last = inside ? n_contrib[pix] : 0u;
-    float dp0 = 0.f, dp1 = 0.f, dp2 = 0.f;
-    if (inside) {
-        const float *gp = dL_dout + (int64_t)py * sy + (int64_t)px * sx;
-        dp0 = gp[0];
-        dp1 = gp[sc];
-        dp2 = gp[2 * sc];
-    }
-    const float bg_dot = bg[0] * dp0 + bg[1] * dp1 + bg[2] * dp2;
-    const int slot = reduce_slot(lane);
-    const float bcx = (float)(px - (lane & 7)) + 3.5f, bcy = (float)(py - (lane >> 3)) + 1.5f;   // centre of the warp's pixel block
-
-    float T = T_final, a0 = 0.f, a1 = 0.f, a2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
-    if (last > s1) {   // contributions behind this segment: resume from the forward's state in front of position s1
-        const int idx = (sub * kWarps + warp) * 32 + lane;
-        const uint32_t nseg_list = (range.y - range.x + (uint32_t)kSeg - 1u) / (uint32_t)kSeg;
-        const float4 ck = ckpt[BinningState::ckpt_slot((uint32_t)tile, range.x, it.y) * kTilePixels + idx];
-        const float4 fin = ckpt[BinningState::ckpt_slot((uint32_t)tile, range.x, nseg_list - 1u) * kTilePixels + idx];   // final (T, C)
-        const float inv = 1.0f / ck.x;
-        T = ck.x;
-        a0 = (fin.y - ck.y) * inv;
-        a1 = (fin.z - ck.z) * inv;
-        a2 = (fin.w - ck.w) * inv;
-    }
-
-    ListStager<kWarps> st{sm, list, recs, range.x + s0, len, 0, true};
-    st.nb = (len + st.B - 1) / st.B;
-    st.prologue();
-
-    // nothing to do for this warp's pixels behind their deepest last contributor (positions relative to s0)
-    const uint32_t wlast_abs = __reduce_max_sync(0xffffffffu, last);
-    const int wlast = wlast_abs > s0 ? (int)min(wlast_abs - s0, (uint32_t)len) : 0;
-    const uint32_t last_rel = last > s0 ? last - s0 : 0u;
-    for (int i = 0; i < st.nb; ++i) {
-        st.advance(i);
-        const int cnt = st.count(i);
-        const float4 *r = st.records(i);
-        const int b = st.batch_of(i);
-        const uint32_t *ids = st.ids(i);
-        int jend = cnt;   // entries at or behind the warp's deepest last contributor cannot matter
-        if (b * st.B + cnt > wlast) jend = wlast - b * st.B;
-        for (int j0 = ((jend - 1) >> 5) << 5; j0 >= 0; j0 -= 32) {
-            bool hit = false;
-            if (j0 + lane < jend) {
-                const float4 ra = r[3 * (j0 + lane)], rc = r[3 * (j0 + lane) + 2];
-                hit = fabsf(ra.x - bcx) <= rc.z + 3.5f && fabsf(ra.y - bcy) <= rc.w + 1.5f;
-            }
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            while (m) {   // survivors back to front
-                const int k = 31 - __clz(m);
-                m &= ~(1u << k);
-                const int j = j0 + k;
-                const uint32_t pos = (uint32_t)(b * st.B + j);
-                const float4 ra = r[3 * j], rb = r[3 * j + 1];
-                const float2 rc = *reinterpret_cast<const float2 *>(&r[3 * j + 2]);
-                const float dx = ra.x - fx, dy = ra.y - fy;
-                const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
-                const bool cand = (pos < last_rel) && (power <= 0.0f) && !(power < rc.y);
-                if (!__any_sync(0xffffffffu, cand)) continue;
-                // non-candidate lanes get G = 0 (not exp of a possibly huge positive power): their partials are exact zeros
-                const float G = cand ? expf(power) : 0.f;
-                const float alpha = fminf(kAlphaMax, rb.y * G);
-                const bool active = cand && (alpha >= kAlphaMin);
-                // Branch-free update: a lane for which this Gaussian does not contribute keeps its state (selects) and its
-                // partial gradients vanish because their common factors (alpha * T, dL/dalpha) are zeroed.
-                const float rinv = fast_rcp(1.0f - alpha);
-                const float T_new = T * rinv;
-                const float n0 = last_alpha * lc0 + (1.f - last_alpha) * a0;
-                const float n1 = last_alpha * lc1 + (1.f - last_alpha) * a1;
-                const float n2 = last_alpha * lc2 + (1.f - last_alpha) * a2;
-                const float c0 = rb.z, c1 = rb.w, c2 = rc.x;
-                float dL_dalpha = ((c0 - n0) * dp0 + (c1 - n1) * dp1 + (c2 - n2) * dp2) * T_new + (-T_final * rinv) * bg_dot;
-                dL_dalpha = active ? dL_dalpha : 0.f;
-                const float dch = active ? alpha * T_new : 0.f;
-                T = active ? T_new : T;
-                a0 = active ? n0 : a0; a1 = active ? n1 : a1; a2 = active ? n2 : a2;
-                lc0 = active ? c0 : lc0; lc1 = active ? c1 : lc1; lc2 = active ? c2 : lc2;
-                last_alpha = active ? alpha : last_alpha;
-                // the 0.99 clamp is not masked (upstream behaviour): dL/dG = opacity * dL/dalpha for every active pixel
-                const float q = G * dL_dalpha, qx = q * dx, qy = q * dy;
-                float v[9];
-                v[0] = qx; v[1] = qy;
-                v[2] = qx * dx; v[3] = qx * dy; v[4] = qy * dy;
-                v[5] = q;
-                v[6] = dch * dp0; v[7] = dch * dp1; v[8] = dch * dp2;
-                const float total = reduce_scatter9(v, lane);
-                if (slot >= 0) red_add(acc + (size_t)ids[j] * kAccStride + slot, total);
-            }
-        }
-        __syncthreads();   // this batch's buffers may be overwritten by the copies issued in the next step
-    }
-}
-
 // ---- packed fp32x2 arithmetic (sm_100a FFMA2 / FMUL2 / FADD2): one issue slot for the two pixels of a lane ----
 __device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
 __device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
@@ -756,16 +632,6 @@ static int blend_warps() {
     return cached;
 }
 
-// backward kernel: 2 = two pixels per lane with packed fp32x2 arithmetic (default), 1 = one pixel per lane (MB_BLEND_WARPS shape)
-static int backward_impl() {
-    static int cached = 0;
-    if (!cached) {
-        const char *e = getenv("MB_BWD_IMPL");
-        cached = (e && atoi(e) == 1) ? 1 : 2;
-    }
-    return cached;
-}
-
 }  // namespace mb
 
 using namespace mb;
@@ -870,22 +736,9 @@ static int raster_backward_impl(const mb_raster_inputs *in, const int32_t *radii
             // upper bound of the item count (the real one is on the device; surplus CTAs exit at once)
             const int64_t bound = (int64_t)d.tiles + capacity / kSeg + 1;
             const int64_t max_items = bound < b.max_items ? bound : b.max_items;
-            if (backward_impl() == 2)
-                blend_backward2_kernel<<<(unsigned)max_items, 128, 0, s>>>(g.rec, b.gid_b, im.ranges, b.bwd_items, n_items, im.tile_maxlast,
-                                                                          d.W, d.H, d.gx, in->background, im.final_T, im.n_contrib, b.ckpt,
-                                                                          dL_dout, stride_c, stride_y, stride_x, acc);
-            else if (blend_warps() == 4)
-                blend_backward_kernel<4><<<(unsigned)(max_items * 2), 128, 0, s>>>(g.rec, b.gid_b, im.ranges, b.bwd_items, n_items,
-                                                                                 im.tile_maxlast, d.W, d.H, d.gx, in->background, im.final_T,
-                                                                                 im.n_contrib, b.ckpt, dL_dout, stride_c, stride_y, stride_x, acc);
-            else if (blend_warps() == 2)
-                blend_backward_kernel<2><<<(unsigned)(max_items * 4), 64, 0, s>>>(g.rec, b.gid_b, im.ranges, b.bwd_items, n_items,
-                                                                                im.tile_maxlast, d.W, d.H, d.gx, in->background, im.final_T,
-                                                                                im.n_contrib, b.ckpt, dL_dout, stride_c, stride_y, stride_x, acc);
-            else
-                blend_backward_kernel<8><<<(unsigned)max_items, 256, 0, s>>>(g.rec, b.gid_b, im.ranges, b.bwd_items, n_items,
-                                                                           im.tile_maxlast, d.W, d.H, d.gx, in->background, im.final_T,
-                                                                           im.n_contrib, b.ckpt, dL_dout, stride_c, stride_y, stride_x, acc);
+            blend_backward2_kernel<<<(unsigned)max_items, 128, 0, s>>>(g.rec, b.gid_b, im.ranges, b.bwd_items, n_items, im.tile_maxlast,
+                                                                      d.W, d.H, d.gx, in->background, im.final_T, im.n_contrib, b.ckpt,
+                                                                      dL_dout, stride_c, stride_y, stride_x, acc);
         }
         rc = check_launch("blend_backward", dbg, s);
         if (rc) return rc;

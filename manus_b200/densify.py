@@ -121,7 +121,12 @@ class GaussianState:
         self.denom[update_filter] += 1
 
     def reduce_stats(self, group=None) -> None:
-        """Data-parallel runs: statistics are sums / maxima over the ranks' views."""
+        """Data-parallel runs: statistics are sums / maxima over the ranks' views.  In place with SUM: call it
+        ONCE per densification interval, right before densify_and_prune (which resets the statistics); a second call before the
+        reset would count every rank's share world_size times."""
+        if getattr(self, "_stats_reduced", False):
+            raise RuntimeError("reduce_stats() was already called since the statistics were last reset")
+        self._stats_reduced = True
         import torch.distributed as dist
 
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -179,6 +184,7 @@ class GaussianState:
         self.xyz_gradient_accum = torch.zeros((self.n, 1), device=dev)
         self.denom = torch.zeros((self.n, 1), device=dev)
         self.max_radii2D = torch.zeros(self.n, device=dev)
+        self._stats_reduced = False
 
     def densify_and_split(self, grads, grad_threshold, scene_extent, N=2) -> None:
         """gaussian.py:249-284"""

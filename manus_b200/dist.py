@@ -178,6 +178,14 @@ class SceneRenderer:
         # two-node path (pose_gaussians + GaussianRasterizer), which the GPU tests run as well
         self.fuse_backward = os.environ.get("MANUS_B200_FUSE_BACKWARD", "1") == "1"
 
+    def rebind(self, flat: FlatGaussians, skin: Optional[torch.Tensor] = None) -> None:
+        """After densify / prune (``GaussianState`` rebuilds its flat buffers and N changes): point the renderer at the new
+        buffers.  Step objects captured on the old buffers (GraphedStep / PipelinedStep) refuse to replay afterwards."""
+        self.flat = flat
+        self.n_hand = 0 if skin is None else skin.shape[0]
+        self.skin = skin
+        self.generation = getattr(self, "generation", 0) + 1
+
     def view_inputs_host(self, view: int):
         """Per-step inputs as pinned host tensors: camera (view 16 | proj 16 | centre 3 | fovx, fovy) and posed bones [20,16]."""
         if view not in self._cams:
@@ -290,6 +298,23 @@ class CompactGradExchange:
                 flat.grads["f_dc"], flat.grads["f_rest"])
         if pending is not None:
             pending.wait()
+
+
+def _remember_buffers(step, renderer) -> None:
+    step._flat_id, step._n, step._replays = id(renderer.flat), renderer.flat.n, 0
+
+
+def _check_fresh(step, check_every: int = 512) -> None:
+    """A captured step holds the ADDRESSES of the parameter / gradient buffers it was captured on: after a densify / prune rebuilt
+    them (``SceneRenderer.rebind``) a replay would silently train the stale buffers -- refuse instead.  Every ``check_every``
+    replays the step also reads the overflow counters of its frames (one synchronisation): in reserve capacity mode an overflow
+    truncates the farthest instances, and nothing else would notice."""
+    r = step.r
+    if id(r.flat) != step._flat_id or r.flat.n != step._n:
+        raise RuntimeError("this step was captured on buffers that have been replaced (densify / prune): build a new step object")
+    step._replays += 1
+    if check_every and step._replays % check_every == 0:
+        step.check()
 
 
 def gaussian_chunks(n: int, chunks: int, align: int = 128) -> List[tuple]:
@@ -406,6 +431,7 @@ class PipelinedStep:
                     back(defs, c)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        _remember_buffers(self, renderer)
         self.graph_front = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_front):
             self.loss, self._defs = front()
@@ -429,6 +455,7 @@ class PipelinedStep:
     def replay(self) -> torch.Tensor:
         """Enqueue one step; the gradients in ``renderer.flat.grad`` are the sum over all ranks' views when the current stream
         reaches the end of what this call enqueued."""
+        _check_fresh(self)
         self.graph_front.replay()
         works = []
         if self.exchange is not None and self.world > 1:
@@ -551,6 +578,7 @@ class GraphedStep:
                 step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        _remember_buffers(self, renderer)
         self.graph = torch.cuda.CUDAGraph()
         if profile:     # event-record nodes around every library kernel of the graph: _lib.profile_timeline() after a replay
             from . import _lib
@@ -577,6 +605,7 @@ class GraphedStep:
             self.targets[slot].copy_(target_dev, non_blocking=True)
 
     def replay(self) -> torch.Tensor:
+        _check_fresh(self)
         self.graph.replay()
         return self.loss
 

@@ -256,6 +256,11 @@ class _RenderFused(torch.autograd.Function):
     def backward(ctx, g_color, *_unused):
         L = _lib.lib()
         t, cam, sh_degree, isotropic, num_skinned, st = ctx.saved
+        if any(g is not None for g in _unused):
+            # posed_xyz / posed_cov / colors / cano_opacity are outputs for inspection (contact maps, logging): this node does not
+            # propagate gradients that arrive through them -- say so instead of dropping them
+            raise RuntimeError("render_fused: a loss term depends on posed_xyz / posed_cov / colors / cano_opacity; use "
+                               "fuse_backward=False (pose_gaussians + render_gaussians) to differentiate through them")
         if g_color is None:
             return (None,) * 17
         if st.host_count is not None:
