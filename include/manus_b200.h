@@ -312,6 +312,19 @@ int mb_radix_sort_pairs(uint32_t *keys_in, uint32_t *vals_in, uint32_t *keys_out
                         mb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * calculate_colors_from_sh (src/utils/gaussian_utils.py:431-449) + eval_sh (src/utils/sh_utils.py:57-120) for callers that hold the
+ * materialised per-Gaussian transform tf [N,4,4] (unchanged MANUS: render_gaussians(..., tf=...)): colour = max(SH(dir) + 0.5, 0)
+ * with dir = normalize(means - (inv(tf) [campos; 1])[:3]) (tf given: means = canonical means) or normalize(means - campos)
+ * (tf = NULL: means = posed means).  One thread per Gaussian, closed-form 4x4 inverse instead of torch.linalg.inv.
+ * features: [N,sh_coeffs,3].  Backward writes g_means [N,3], g_features [N,sh_coeffs,3] and (optional) g_tf [N,4,4].
+ * ---------------------------------------------------------------------------------------------- */
+int mb_sh_colors_forward(const float *means, const float *features, const float *tf, const float *campos, int32_t num_points,
+                         int32_t sh_degree, int32_t sh_coeffs, float *colors, mb_stream_t stream);
+int mb_sh_colors_backward(const float *means, const float *features, const float *tf, const float *campos, int32_t num_points,
+                          int32_t sh_degree, int32_t sh_coeffs, const float *g_colors, float *g_means, float *g_features, float *g_tf,
+                          mb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * The gradient exchange of the view-sharded step over NVSwitch multicast memory (replaces the one ncclAllReduce per step,
  * SURVEY.md section 8e; reference semantics: the sum over accum_iter views, src/modules/hand_dynamic.py:248,259-277).
  * multicast_base: the multicast (multimem) address of a symmetric allocation that holds every rank's gradient buffer at the same

@@ -17,7 +17,7 @@ OBJ = os.path.join(HERE, "lib", "obj")
 LIB = os.path.join(HERE, "lib", "libmanus_b200.so")
 INCLUDE = os.path.join(HERE, "..", "include")
 
-SOURCES = ["api.cu", "sort_scan.cu", "raster_geom.cu", "raster_blend.cu", "pose.cu", "knn.cu", "loss.cu", "skin.cu", "adam.cu", "exchange.cu"]
+SOURCES = ["api.cu", "sort_scan.cu", "raster_geom.cu", "raster_blend.cu", "pose.cu", "knn.cu", "loss.cu", "skin.cu", "adam.cu", "exchange.cu", "shcolor.cu"]
 PER_FILE_FLAGS = {"raster_geom.cu": ["--fmad=false"]}
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",

@@ -338,11 +338,44 @@ __device__ __forceinline__ float2 exp_pair(float2 x) {
     return __ffma2_rn(e, __fmul2_rn(r, splat(ln2)), e);
 }
 
+#ifndef MB_BWD_SMEM_REDUCE
+#define MB_BWD_SMEM_REDUCE 1
+#endif
+constexpr int kRedStride = 36;     // floats per row of a warp's reduction scratch: 16-B aligned rows, conflict-free 128-bit reads
+
 struct SegmentSmem {
     Record rec[kSeg];          // the segment's records, list order
     uint32_t ids[kSeg + 4];    // the segment's slice of the id list (16-B aligned source => up to 3 ids of slack in front)
     uint64_t bar;
+#if MB_BWD_SMEM_REDUCE
+    alignas(16) float red[4][8 * kRedStride];   // per warp: 8 of the 9 per-Gaussian partials x 32 lanes (transposed reduction)
+#endif
 };
+
+#if MB_BWD_SMEM_REDUCE
+// Sum each of v[0..8] over the 32 lanes through shared memory.  v[0..7]: every lane stores its eight values as one row element each
+// (8 STS, conflict free), then lane (k = lane / 4, part = lane % 4) loads 8 consecutive lanes' values of row k with two 128-bit
+// loads (conflict free per quarter warp with the 36-float row stride), adds them (7 FADD) and the four parts meet with two
+// shuffles: lane 4k holds the total of v[k].  v[8] takes the 5-step butterfly (all lanes hold its total).  ~36 issue slots against
+// ~52 for the register-only reduce-scatter, and the selects of that version (ALU pipe) become LSU work.
+// Returns the value the lane issues its RED with: slot k = lane / 4 on lanes 4k, slot 8 on lane 1 (see reduce_slot_smem).
+__device__ __forceinline__ float reduce9_smem(const float (&v)[9], float *red, int lane) {
+    __syncwarp();      // the previous survivor's loads are done
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[k * kRedStride + lane] = v[k];
+    float w = v[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    __syncwarp();
+    const float4 *row = reinterpret_cast<const float4 *>(red + (lane >> 2) * kRedStride + (lane & 3) * 8);
+    const float4 a = row[0], b = row[1];
+    float t = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    return lane == 1 ? w : t;
+}
+__device__ __forceinline__ int reduce_slot_smem(int lane) { return lane == 1 ? 8 : ((lane & 3) == 0 ? lane >> 2 : -1); }
+#endif
 
 #ifndef MB_BWD2_CTAS_PER_SM
 #define MB_BWD2_CTAS_PER_SM 8
@@ -391,7 +424,12 @@ __global__ void __launch_bounds__(128, MB_BWD2_CTAS_PER_SM) blend_backward2_kern
     const float b0 = bg[0], b1 = bg[1], b2 = bg[2];
     const float2 bg_dot = make_float2(b0 * dp0.x + b1 * dp1.x + b2 * dp2.x, b0 * dp0.y + b1 * dp1.y + b2 * dp2.y);
     const float2 nTfbg = make_float2(-T_final.x * bg_dot.x, -T_final.y * bg_dot.y);   // (-T_final / (1 - alpha)) bg_dot = rinv * nTfbg
+#if MB_BWD_SMEM_REDUCE
+    const int slot = reduce_slot_smem(lane);
+    float *red = sm.red[warp];
+#else
     const int slot = reduce_slot(lane);
+#endif
     const float bcx = (float)(px - (lane & 7)) + 3.5f, bcy = (float)(py - (lane >> 3)) + 3.5f;   // centre of the warp's 8x8 block
 
     float2 T = T_final, B0 = splat(0.f), B1 = B0, B2 = B0;
@@ -499,7 +537,11 @@ __global__ void __launch_bounds__(128, MB_BWD2_CTAS_PER_SM) blend_backward2_kern
                 v[2] = qxx.x + qxx.y; v[3] = qxy.x + qxy.y; v[4] = qyy.x + qyy.y;
                 v[5] = q.x + q.y;
                 v[6] = g0.x + g0.y; v[7] = g1.x + g1.y; v[8] = g2.x + g2.y;
+#if MB_BWD_SMEM_REDUCE
+                const float total = reduce9_smem(v, red, lane);
+#else
                 const float total = reduce_scatter9(v, lane);
+#endif
                 if (slot >= 0) red_add(acc + (size_t)ids[j] * kAccStride + slot, total);
             }
         }

@@ -56,20 +56,52 @@ def eval_sh(deg: int, sh: torch.Tensor, dirs: torch.Tensor) -> torch.Tensor:
     return result
 
 
+class _ShColors(torch.autograd.Function):
+    """mb_sh_colors_forward / backward: one thread per Gaussian, closed-form 4x4 inverse (csrc/shcolor.cu)."""
+
+    @staticmethod
+    def forward(ctx, means, features, tf, campos, sh_degree):
+        L = _lib.lib()
+        m, f = _f32c(means), _f32c(features)
+        t = None if tf is None else _f32c(tf).reshape(-1, 4, 4)
+        c = _f32c(campos).reshape(-1)[:3].contiguous()
+        N, K = m.shape[0], f.shape[1]
+        colors = torch.empty((N, 3), dtype=torch.float32, device=m.device)
+        with torch.cuda.device(m.device):
+            _lib.check(L.mb_sh_colors_forward(ptr(m), ptr(f), ptr(t), ptr(c), N, int(sh_degree), K, ptr(colors),
+                                              torch.cuda.current_stream(m.device).cuda_stream), "mb_sh_colors_forward")
+        ctx.save_for_backward(m, f, c, *(() if t is None else (t,)))
+        ctx.sh_degree, ctx.has_tf = int(sh_degree), t is not None
+        ctx.shapes = (means.shape, features.shape, None if tf is None else tf.shape)
+        return colors
+
+    @staticmethod
+    def backward(ctx, g_colors):
+        L = _lib.lib()
+        saved = ctx.saved_tensors
+        m, f, c = saved[:3]
+        t = saved[3] if ctx.has_tf else None
+        N, K = m.shape[0], f.shape[1]
+        g = _f32c(g_colors)
+        g_m, g_f = torch.empty_like(m), torch.empty_like(f)
+        g_t = torch.empty_like(t) if (t is not None and ctx.needs_input_grad[2]) else None
+        with torch.cuda.device(m.device):
+            _lib.check(L.mb_sh_colors_backward(ptr(m), ptr(f), ptr(t), ptr(c), N, ctx.sh_degree, K, ptr(g), ptr(g_m), ptr(g_f), ptr(g_t),
+                                               torch.cuda.current_stream(m.device).cuda_stream), "mb_sh_colors_backward")
+        sm, sf, st = ctx.shapes
+        return g_m.reshape(sm), g_f.reshape(sf), None if g_t is None else g_t.reshape(st), None, None
+
+
 def calculate_colors_from_sh(posed_means, cano_features, cano_means, camera, sh_degree, tf):
-    """gaussian_utils.py:431-449 for callers that hold the materialised per-Gaussian ``tf`` [N,4,4]: the view direction is
-    taken in canonical space through inv(tf).  Plain torch operations on the tensors' device, like the reference (the fused
-    ``pose_gaussians`` kernel does the same arithmetic without materialising tf and is the fast path)."""
-    shs_view = cano_features.transpose(1, 2).reshape(-1, 3, cano_features.shape[1])[..., : (sh_degree + 1) ** 2]
-    cc = torch.as_tensor(camera.camera_center).to(posed_means.device).reshape(-1, 3)[:1].repeat(cano_features.shape[0], 1)
-    if tf is not None:
-        hom = torch.cat([cc, torch.ones_like(cc[:, :1])], dim=1)
-        cam_inv = torch.einsum("nij,nj->ni", torch.linalg.inv(tf), hom)[..., :3]
-        d = cano_means - cam_inv
-    else:
-        d = posed_means - cc
-    d = d / d.norm(dim=1, keepdim=True)
-    return torch.clamp_min(eval_sh(sh_degree, shs_view, d) + 0.5, 0.0)
+    """gaussian_utils.py:431-449 for callers that hold the materialised per-Gaussian ``tf`` [N,4,4] (unchanged MANUS): the view
+    direction is taken in canonical space through inv(tf).  One kernel forward, one backward (gradients to the features, to the
+    means and to tf); the reference's torch.linalg.inv on N 4x4 matrices becomes a closed-form inverse per thread.  The fused
+    ``pose_gaussians`` kernel does the same arithmetic without materialising tf and remains the fast path."""
+    if not posed_means.is_cuda:
+        raise _lib.ManusB200Error("manus_b200.render.calculate_colors_from_sh needs CUDA tensors (there is no CPU path)")
+    cc = torch.as_tensor(camera.camera_center).to(posed_means.device)
+    means = cano_means if tf is not None else posed_means
+    return _ShColors.apply(means, cano_features, tf, cc, int(sh_degree))
 
 
 _ZEROS = {}

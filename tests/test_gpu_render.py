@@ -67,3 +67,40 @@ def test_render_gaussians_needs_colors_or_features(built_lib):
     z = torch.zeros(4, 3, device=DEV)
     with pytest.raises(ValueError):
         render_gaussians(z, torch.zeros(4, 6, device=DEV), z, None, torch.zeros(4, 1, device=DEV), cam, torch.ones(3, device=DEV))
+
+
+@pytest.mark.parametrize("with_tf", [True, False])
+def test_calculate_colors_from_sh_kernel_matches_the_reference_ops(built_lib, with_tf):
+    """calculate_colors_from_sh with a materialised tf (gaussian_utils.py:431-449): the kernel's closed-form 4x4 inverse and SH
+    evaluation against the restated reference ops (torch.linalg.inv + eval_sh, autograd), forward and the gradients to the
+    features, the means and tf itself; general invertible tf (blends of rigid transforms plus a perturbation of every entry)."""
+    import types
+
+    from manus_b200.render import calculate_colors_from_sh
+
+    sc = synth.make_hand(2500, seed=6)
+    t = lambda a: torch.tensor(a, device=DEV)
+    tfs = pose_ref.bone_transforms(t(synth.posed_bones(21)), t(sc.bones_rest), True)
+    tf0 = torch.einsum("nb,bij->nij", t(sc.skin_wts), tfs)
+    tf0 = tf0 + 0.02 * torch.randn(tf0.shape, generator=torch.Generator().manual_seed(1)).to(DEV)
+    cam = types.SimpleNamespace(camera_center=np.array([0.3, -0.2, 1.4], np.float32))
+    feats0 = np.concatenate([sc.f_dc, sc.f_rest * 4.0], 1)
+    G = torch.rand(sc.n, 3, generator=torch.Generator().manual_seed(2)).to(DEV)
+    res = {}
+    for which in ("kernel", "oracle"):
+        xyz, feats = _leaf(sc.xyz), _leaf(feats0)
+        tf = tf0.clone().requires_grad_(True) if with_tf else None
+        posed = xyz if tf is None else torch.einsum("nij,nj->ni", tf.detach(), torch.cat([xyz.detach(), torch.ones_like(xyz[:, :1])], 1))[..., :3]
+        if which == "kernel":
+            col = calculate_colors_from_sh(posed, feats, xyz, cam, 3, tf)
+        else:
+            col = pose_ref.calculate_colors_from_sh(posed, feats, xyz, t(cam.camera_center), 3, tf)
+        (col * G).sum().backward()
+        res[which] = (col.detach().cpu().numpy(), xyz.grad.cpu().numpy(), feats.grad.cpu().numpy(), None if tf is None else tf.grad.cpu().numpy())
+    np.testing.assert_allclose(res["kernel"][0], res["oracle"][0], atol=2e-6, rtol=0)
+    assert float((res["kernel"][0] == 0).mean()) > 0.001            # the clamp is exercised
+    for k in (1, 2, 3):
+        if res["oracle"][k] is None:
+            continue
+        ok_, e, s = grad_close(res["kernel"][k], res["oracle"][k], GRAD_RTOL)
+        assert ok_, (with_tf, k, e, s)
