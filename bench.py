@@ -308,7 +308,7 @@ def workload_config(args, world, vif=1):
                            "of one CUDA graph), one exchange of per-Gaussian gradients per step",
             "l2": "working set per step (parameters 118 MB + gradients 118 MB + instance records) exceeds the 126 MB L2 and the view "
                   "changes every step; no explicit flush",
-            "loss": "sum(image * G), G ~ U[0,1] fixed (seed 7)"}
+            "loss": "sum(image * G), G ~ U[0,1] fixed (seed 7): one dot product; its gradient G is the seed of the backward"}
 
 
 def main():
@@ -364,9 +364,12 @@ def main():
     my_view = lambda it, slot=0: views[((it * VIF + slot) * world + rank) % len(views)]
     # target / loss weights G ~ U[0,1]: 8-bit like the dataset's images (rgb / 255, src/datasets/brics_dynamic.py), so that the
     # end-to-end step ships one byte per channel over PCIe and converts on the device; the resident steps keep the fp32 copy
-    G_u8_host = torch.randint(0, 256, (H, W, 3), generator=torch.Generator().manual_seed(7), dtype=torch.uint8).pin_memory()
-    G_u8_dev = G_u8_host.to(dev)
-    G_dev = G_u8_dev.float() / 255.0
+    # (stored [3,H,W] like the rasterizer's output and viewed as [H,W,3]: image and target then flatten without a copy)
+    G_u8_host = torch.randint(0, 256, (3, H, W), generator=torch.Generator().manual_seed(7), dtype=torch.uint8).pin_memory().permute(1, 2, 0)
+    G_u8_dev = torch.empty((3, H, W), dtype=torch.uint8, device=dev).permute(1, 2, 0)
+    G_u8_dev.copy_(G_u8_host)
+    G_dev = G_u8_dev.float() / 255.0                  # keeps the [H,W,3]-view-of-[3,H,W] layout
+    G_u8_host_hwc = G_u8_host.contiguous().pin_memory()      # dense HWC copy for the reference's loss kernel (reads gt row by row)
     staged = {}
     for v in views:
         _, c, b = r.view_inputs_host(v)
@@ -380,7 +383,12 @@ def main():
     set_capacity_mode("reserve", margin=1.1)
     _rz.reserve_capacity(dev.index, scene.n, H, W, max(D_all.values()))
 
-    loss_fn = lambda image, target: (image * target).sum()
+    # The probe loss of SURVEY.md section 8d, sum(image * G): one dot product forward, and its gradient IS G -- handed to the backward
+    # as the seed instead of letting autograd form it (the loss is there to time the path, not itself).  image is the permuted
+    # [H,W,3] view of the rasterizer's [3,H,W] output; G is stored the same way, so both flatten without a copy.
+    def loss_fn(image, target):
+        return torch.dot(image.permute(2, 0, 1).reshape(-1), target.permute(2, 0, 1).reshape(-1)), target
+
     # N > 1: the backward skips the f_rest gradient and the ranks exchange the rank-one SH gradient factors instead of
     # all-reducing all 59 floats per Gaussian (manus_b200.dist.CompactGradExchange)
     # measured on B200 / NVSwitch: compact wins at N = 2 (0.838 vs 0.948 ms/step); at N = 8 the rebuild over 8 views costs
@@ -431,8 +439,8 @@ def main():
             for slot in range(VIF):
                 v = my_view(it, slot)
                 out = r.render(v, sink=r.flat.grads, cam_dev=staged[v][0], bones_dev=staged[v][1], compact_sh=compact, accumulate=slot > 0)
-                l = loss_fn(out["render"], G_dev)
-                l.backward()
+                l, seed = loss_fn(out["render"], G_dev)
+                out["render"].backward(seed)
                 loss = loss + l.detach()
         reduce_gradients()
         return loss
@@ -450,16 +458,18 @@ def main():
     class E2E:
         """loss_fn(image, target_u8): the target arrives as uint8 [H,W,3] (one byte per channel over PCIe)."""
 
-        def __init__(self, loss_fn):
+        def __init__(self, loss_fn, host_target=None):
             self.loss_fn = loss_fn
-            self.graphs = None if args.no_graph else [make_step(loss_fn, G_u8_dev) for _ in range(NSLOT)]
+            self.host_target = G_u8_host if host_target is None else host_target
+            like = G_u8_dev if host_target is None else host_target.to(dev)
+            self.graphs = None if args.no_graph else [make_step(loss_fn, like) for _ in range(NSLOT)]
             self.slots = []
             for k in range(NSLOT):
                 if self.graphs is not None:
                     g = self.graphs[k]
                     d = dict(g=g.targets, cam=g.cams, bones=g.bones_all)
                 else:
-                    d = dict(g=[torch.empty_like(G_u8_dev) for _ in range(VIF)], cam=[torch.empty(CAM_FLOATS, device=dev) for _ in range(VIF)],
+                    d = dict(g=[torch.empty_like(like) for _ in range(VIF)], cam=[torch.empty(CAM_FLOATS, device=dev) for _ in range(VIF)],
                              bones=[torch.empty(320, device=dev) for _ in range(VIF)])
                 d.update(ready=torch.cuda.Event(), free=torch.cuda.Event(), loss_host=torch.zeros(1).pin_memory(),
                          loss_done=torch.cuda.Event(), staged=None, pending=False)
@@ -475,7 +485,7 @@ def main():
                 copy_stream.wait_event(slot["free"])           # the step that last used this slot has finished with it
                 for j in range(VIF):                           # every view of the step: target image, camera, posed bones
                     _, c, b = r.view_inputs_host(my_view(it, j))
-                    slot["g"][j].copy_(G_u8_host, non_blocking=True)
+                    slot["g"][j].copy_(self.host_target, non_blocking=True)
                     slot["cam"][j].copy_(c, non_blocking=True)
                     slot["bones"][j].copy_(b, non_blocking=True)
                 slot["ready"].record(copy_stream)
@@ -499,9 +509,13 @@ def main():
                 for j in range(VIF):
                     out = r.render(my_view(it, j), sink=r.flat.grads, cam_dev=slot["cam"][j], bones_dev=slot["bones"][j],
                                    compact_sh=compact, accumulate=j > 0)
-                    l = self.loss_fn(out["render"], slot["g"][j])
-                    l.backward()
-                    loss = loss + l.detach()
+                    res = self.loss_fn(out["render"], slot["g"][j])
+                    if isinstance(res, tuple):
+                        out["render"].backward(res[1])
+                        res = res[0]
+                    else:
+                        res.backward()
+                    loss = loss + res.detach()
             reduce_gradients()
             slot["loss_host"].copy_(loss.reshape(1), non_blocking=True)     # device -> host read of the step's result
             slot["loss_done"].record(cur)
@@ -557,14 +571,17 @@ def main():
     ms_step = timed(step_resident, K, sampler)
     clocks = sampler.summary()
     # the same loss on a uint8 target: sum(image * g) / 255 (type promotion inside the one elementwise kernel)
-    loss_fn_u8 = lambda image, target: (image * target).sum() * (1.0 / 255.0)
+    def loss_fn_u8(image, target):
+        g = target * (1.0 / 255.0)                    # one elementwise kernel: uint8 -> fp32, same layout
+        return torch.dot(image.permute(2, 0, 1).reshape(-1), g.permute(2, 0, 1).reshape(-1)), g
+
     e2e_step = E2E(loss_fn_u8)
     ms_e2e = timed(e2e_step, K)
     e2e_step.check()
     del e2e_step
     # the same end-to-end step with the reference's training loss 0.8 L1 + 0.2 (1 - SSIM) (fused kernel, manus_b200.losses)
     from manus_b200.losses import photometric_loss
-    e2e_photo = E2E(lambda image, target: photometric_loss(image, target * (1.0 / 255.0), 0.8, 0.2))
+    e2e_photo = E2E(lambda image, target: photometric_loss(image, target * (1.0 / 255.0), 0.8, 0.2), host_target=G_u8_host_hwc)
     ms_e2e_photo = timed(e2e_photo, K)
     e2e_photo.check()
     del e2e_photo
@@ -613,7 +630,7 @@ def main():
                 for slot in range(VIF):
                     v = views[((0 * VIF + slot) * world + rk) % len(views)]
                     out = r.render(v, sink=r.flat.grads, cam_dev=staged[v][0], bones_dev=staged[v][1])
-                    loss_fn(out["render"], G_dev).backward()
+                    out["render"].backward(loss_fn(out["render"], G_dev)[1])
                     want += r.flat.grad
             torch.cuda.synchronize()
             scale = float(want.abs().max())

@@ -116,6 +116,12 @@ def pose_only(dev, n: int = 50_000, view: int = 100):
     return res
 
 
+def probe_loss(image, target):
+    """bench.py's probe loss sum(image * G) as one dot product with its analytic gradient (G) handed to the backward; image and
+    target are [H,W,3] views of [3,H,W] storage."""
+    return torch.dot(image.permute(2, 0, 1).reshape(-1), target.permute(2, 0, 1).reshape(-1)), target
+
+
 def _prepare(r, views, probe_every: int = 5):
     """Device copies of the per-view inputs and the largest instance count over a sample of the views (exact mode)."""
     from manus_b200 import rasterizer as rz
@@ -146,8 +152,12 @@ def config_run(dev, kind: str, n: int, W: int, H: int, nviews: int, vif: int, st
     staged, dmax, dmean = _prepare(r, views, probe_every=max(1, nviews // 10))
     rz.set_capacity_mode("reserve", margin=1.3)
     rz.reserve_capacity(dev.index, scene.n, H, W, dmax)
-    G = torch.rand(H, W, 3, device=dev)
-    step = GraphedStep(r, lambda image, target: (image * target).sum(), G, view=views[0], views_in_flight=vif)
+    G = torch.rand(3, H, W, device=dev).permute(1, 2, 0)
+    if vif > 1:      # as the headline: all views' pose backward in one pass
+        from manus_b200.dist import PipelinedStep
+        step = PipelinedStep(r, probe_loss, G, view=views[0], views_in_flight=vif, chunks=1, reduce=False)
+    else:
+        step = GraphedStep(r, probe_loss, G, view=views[0], views_in_flight=vif)
 
     def run(k0, k):
         for it in range(k0, k0 + k):

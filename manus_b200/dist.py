@@ -300,6 +300,23 @@ class CompactGradExchange:
             pending.wait()
 
 
+def _loss_and_seed(loss_fn, image, target):
+    """loss_fn returns the scalar loss, or (loss, dL/dimage) when it knows its own gradient analytically (e.g. a linear probe
+    loss sum(image * G): the gradient is G, no autograd kernel has to form it).  -> (loss, image tensor to call backward on, seed)."""
+    res = loss_fn(image, target)
+    if isinstance(res, tuple):
+        loss, seed = res
+        return loss, image, seed
+    return res, res, None
+
+
+def _backward(root, seed) -> None:
+    if seed is None:
+        root.backward()
+    else:
+        root.backward(seed)
+
+
 def _remember_buffers(step, renderer) -> None:
     step._flat_id, step._n, step._replays = id(renderer.flat), renderer.flat.n, 0
 
@@ -401,12 +418,12 @@ class PipelinedStep:
                                           accumulate=i < early)
                     self.states[i] = rz._Plan.last_state
                     self.viewspace[i] = out["viewspace_points"]
-                    losses[i] = loss_fn(out["render"], self.targets[i])
+                    losses[i] = _loss_and_seed(loss_fn, out["render"], self.targets[i])
                     outs[i] = sink
             for i in range(V):
                 with torch.cuda.stream(cur if i == 0 else self._sides[i - 1]):
-                    losses[i].backward()
-                    losses[i] = losses[i].detach()
+                    _backward(losses[i][1], losses[i][2])
+                    losses[i] = losses[i][0].detach()
                     deferred.extend(outs[i].get("_defer", []))
             for i in range(1, V):
                 cur.wait_stream(self._sides[i - 1])
@@ -505,7 +522,7 @@ class GraphedStep:
     pose backward launches in view order (view 0 overwrites, view i adds after view i-1: event edges in the graph) for a
     reproducible sum, at the price of serialising the last kernel of every branch.
 
-    loss_fn(image[H,W,3], target) -> scalar tensor.  After ``replay()``: ``loss`` (device scalar: the sum over the step's
+    loss_fn(image[H,W,3], target) -> scalar tensor, or (scalar, dL/dimage [H,W,3]) when the loss knows its gradient.  After ``replay()``: ``loss`` (device scalar: the sum over the step's
     views; ``losses`` holds them one by one) and ``renderer.flat.grad`` (sum over the views) hold the step's results.
     ``check()`` (synchronises) raises if a replayed frame overflowed the reserved capacity.  ``radii_all[i]`` are view i's
     radii; the views' screen-space gradients (``viewspace_points.grad``, the densification statistic of
@@ -546,7 +563,7 @@ class GraphedStep:
                                   compact_sh=compact_sh, accumulate=V > 1 and (i > 0 or not ordered), slot=i)
             self.states[i] = rz._Plan.last_state
             self.viewspace[i] = out["viewspace_points"]
-            loss = loss_fn(out["render"], self.targets[i])
+            loss = _loss_and_seed(loss_fn, out["render"], self.targets[i])
             return loss, out["radii"]
 
         def step():
@@ -563,8 +580,8 @@ class GraphedStep:
                     losses[i], radii[i] = frame(i, done)
             for i in range(V):              # host order = view order: event i-1 is recorded before view i waits for it
                 with torch.cuda.stream(cur if i == 0 else self._sides[i - 1]):
-                    losses[i].backward()
-                    losses[i] = losses[i].detach()
+                    _backward(losses[i][1], losses[i][2])
+                    losses[i] = losses[i][0].detach()
             for i in range(1, V):
                 cur.wait_stream(self._sides[i - 1])
             total = losses[0] if V == 1 else torch.stack(losses).sum()
