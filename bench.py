@@ -53,10 +53,11 @@ def parse():
     ap.add_argument("--chunks", type=int, default=-1,
                     help="N > 1: ranges of Gaussians whose pose backward + all-reduce are pipelined (manus_b200.dist.PipelinedStep); "
                          "0 = one all-reduce of the flat buffer after the step; -1 = auto (measured on B200 / NVSwitch: 0 at N = 2, 4 above)")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "multimem"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "multimem", "p2p"],
                     help="N > 1: who sums the gradient ranges over the ranks -- NCCL (coalesced all-reduce per range) or the repository's "
                          "own multimem.ld_reduce / multimem.st kernel over NVSwitch multicast memory (csrc/exchange.cu); auto = multimem "
-                         "for N >= 4 when the system offers multicast (at N = 2 NCCL's 118 MB all-reduce is faster: 253 vs 340 us)")
+                         "for N >= 4 when the system offers multicast, the peer-to-peer kernel of the same file at N = 2 "
+                         "(118 MB on two GPUs: p2p 238 us, NCCL 252 us, multimem 340 us)")
     ap.add_argument("--deferred-views", type=int, default=0,
                     help="N > 1: views per rank whose pose backward runs in the range-by-range tail (the others finish inside their branch); 0 = all")
     ap.add_argument("--exchange-ctas", type=int, default=32, help="CTAs of the multimem exchange kernel (it runs beside the pose backward)")
@@ -350,8 +351,8 @@ def main():
     if args.chunks < 0:
         args.chunks = 4 if world >= 4 else 0
     if args.exchange == "auto":
-        args.exchange = "multimem" if world >= 4 else "nccl"
-    if world > 1 and args.exchange == "multimem":
+        args.exchange = "multimem" if world >= 4 else "p2p"
+    if world > 1 and args.exchange in ("multimem", "p2p"):
         # the gradient buffer moves into NVSwitch multicast memory BEFORE anything captures its address
         try:
             from manus_b200.exchange import MulticastExchange
@@ -422,7 +423,7 @@ def main():
         if exchange is not None:
             exchange()
         elif world > 1 and mc_exchange is not None:
-            mc_exchange.all_reduce_all(args.exchange_ctas)
+            mc_exchange.all_reduce_all(args.exchange_ctas, p2p=args.exchange == "p2p")
         elif world > 1:
             dist.all_reduce(r.flat.grad)
 
@@ -689,12 +690,14 @@ def main():
             "frame": {"num_rendered_mean": D_mean, "visible_mean": V_mean, "algorithmic_bytes": fbytes,
                       "achieved_gbps": fbytes * (VIF * 1e3 / ms_step) / 1e9, "frac_of_hbm_peak": fbytes * (VIF * 1e3 / ms_step) / 1e9 / peak,
                       "allreduce_bytes": r.flat.allreduce_bytes() if world > 1 else 0,
-                      "exchange": ("none" if world == 1 else f"pipelined: pose backward over {args.chunks} ranges of Gaussians, each range's six "
-                                   "gradient pieces all-reduced (one coalesced NCCL op) while the next range computes" if pipelined else "compact: all-gather of the DC gradients (12 B per Gaussian and rank) + all-reduce of "
-                                   "the 11 non-SH floats + local rebuild of the SH gradients" if compact else "all-reduce of the flat gradient buffer"),
+                      "exchange": ("none" if world == 1 else f"pipelined: multi-view pose backward over {n_chunks} ranges of Gaussians, each range's six "
+                                   "gradient pieces summed over the ranks on a side stream while the next range computes" if (pipelined and n_chunks > 1)
+                                   else "compact: all-gather of the DC gradients (12 B per Gaussian and rank) + all-reduce of "
+                                   "the 11 non-SH floats + local rebuild of the SH gradients" if compact else "one sum of the flat gradient buffer over the ranks after the step"),
                       "exchange_bytes_per_rank": (0 if world == 1 else (scene.n * (12 * world + 44)) if compact else r.flat.allreduce_bytes())}}
-    line["exchange_impl"] = (None if world == 1 else "multimem.ld_reduce / multimem.st kernel over NVSwitch multicast memory (csrc/exchange.cu)"
-                             if mc_exchange is not None else (mc_note or "NCCL all-reduce"))
+    line["exchange_impl"] = (None if world == 1 else mc_note or "NCCL all-reduce" if mc_exchange is None else
+                             "peer-to-peer load / add / store kernel over NVLink (csrc/exchange.cu: mb_p2p_allreduce)" if args.exchange == "p2p" and n_chunks == 1
+                             else "multimem.ld_reduce / multimem.st kernel over NVSwitch multicast memory (csrc/exchange.cu)")
     line["densification_stats"] = densify
     line["grad_check"] = grad_check
     line["numa_binding"] = numa

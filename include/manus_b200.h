@@ -332,6 +332,10 @@ int mb_sh_colors_backward(const float *means, const float *features, const float
  * multimem.ld_reduce (fp32 add in the switch) and broadcasts the sums with multimem.st.  The caller synchronises the ranks before
  * (gradients complete everywhere) and after (stores landed everywhere).  max_ctas <= 0: one CTA per SM.
  * ---------------------------------------------------------------------------------------------- */
+/* The same sum through plain peer-to-peer loads and stores on the R mapped buffers (peer_buffers[r] = rank r's copy): meant to run
+ * BESIDE mb_multimem_allreduce on a disjoint part of every piece (the in-switch reduction does not saturate the links). */
+int mb_p2p_allreduce(float *const *peer_buffers, const int64_t *piece_offsets, const int64_t *piece_counts, int32_t num_pieces,
+                     int32_t rank, int32_t world, int32_t max_ctas, mb_stream_t stream);
 int mb_multimem_allreduce(float *multicast_base, const int64_t *piece_offsets, const int64_t *piece_counts, int32_t num_pieces,
                           int32_t rank, int32_t world, int32_t max_ctas, mb_stream_t stream);
 

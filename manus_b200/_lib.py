@@ -59,6 +59,8 @@ SIGNATURES = {
     "mb_profile_timeline": (C.c_int, [C.c_char_p, C.c_size_t]),
     "mb_sh_colors_forward": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p, C.c_void_p]),
     "mb_sh_colors_backward": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p] * 4 + [C.c_void_p]),
+    "mb_p2p_allreduce": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_void_p]),
     "mb_multimem_allreduce": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_void_p]),
     "mb_raster_geom_bytes": (C.c_size_t, [C.c_int32]),

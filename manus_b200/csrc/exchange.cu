@@ -75,9 +75,65 @@ __global__ void __launch_bounds__(512) multimem_allreduce_kernel(AllReduceArgs a
     }
 }
 
+// The same sum through plain peer-to-peer accesses (no multicast): rank r reads its 1/R share of every piece from all R buffers,
+// adds them in rank order and writes the sum into all R buffers.  1.75 x the buffer per GPU and direction at R = 8 -- more than
+// the in-switch reduction -- but it runs on the NVLink bandwidth the switch's reduction rate leaves idle, so the exchange can
+// split every piece between the two kernels (mb_multimem_allreduce / mb_p2p_allreduce on two streams inside the same barriers).
+struct P2PArgs {
+    float *buf[8];                    // the symmetric buffer on every rank (peer pointers)
+    long long off[kMaxPieces], cnt[kMaxPieces];
+    int pieces, rank, world;
+};
+
+__global__ void __launch_bounds__(512) p2p_allreduce_kernel(P2PArgs a) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+    for (int p = 0; p < a.pieces; ++p) {
+        const long long n4 = a.cnt[p] >> 2;       // pieces handed to this kernel are 16-byte aligned and sized
+        const long long lo = n4 * a.rank / a.world, hi = n4 * (a.rank + 1) / a.world;
+        for (long long i = lo + tid; i < hi; i += nthr) {
+            float4 v[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < a.world) v[r] = __ldcg(reinterpret_cast<const float4 *>(a.buf[r] + a.off[p]) + i);
+            float4 s = v[0];
+#pragma unroll
+            for (int r = 1; r < 8; ++r)
+                if (r < a.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < a.world) __stcg(reinterpret_cast<float4 *>(a.buf[r] + a.off[p]) + i, s);
+        }
+    }
+}
+
 }  // namespace mb
 
 using namespace mb;
+
+extern "C" int mb_p2p_allreduce(float *const *peer_buffers, const int64_t *piece_offsets, const int64_t *piece_counts, int32_t num_pieces,
+                                int32_t rank, int32_t world, int32_t max_ctas, mb_stream_t stream) {
+    MB_REQUIRE(peer_buffers != nullptr && world >= 1 && world <= 8 && rank >= 0 && rank < world, "mb_p2p_allreduce: 1..8 ranks");
+    MB_REQUIRE(num_pieces >= 1 && num_pieces <= kMaxPieces && piece_offsets && piece_counts, "mb_p2p_allreduce: 1..%d pieces", kMaxPieces);
+    P2PArgs a;
+    a.pieces = num_pieces; a.rank = rank; a.world = world;
+    for (int r = 0; r < 8; ++r) a.buf[r] = r < world ? peer_buffers[r] : nullptr;
+    long long most = 0;
+    for (int p = 0; p < num_pieces; ++p) {
+        MB_REQUIRE(piece_offsets[p] >= 0 && piece_counts[p] >= 0 && (piece_offsets[p] & 3) == 0 && (piece_counts[p] & 3) == 0,
+                   "mb_p2p_allreduce: pieces must start and end on 16-byte boundaries");
+        a.off[p] = piece_offsets[p]; a.cnt[p] = piece_counts[p];
+        most = piece_counts[p] > most ? piece_counts[p] : most;
+    }
+    if (most == 0) return MB_OK;
+    long long grid = (most / 4 / world + 511) / 512;
+    const int cap = max_ctas > 0 ? max_ctas : sm_count();
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    cudaStream_t s = (cudaStream_t)stream;
+    KernelTimer kt("p2p_allreduce", s);
+    p2p_allreduce_kernel<<<(unsigned)grid, 512, 0, s>>>(a);
+    return check_launch("p2p_allreduce", false, s);
+}
 
 extern "C" int mb_multimem_allreduce(float *multicast_base, const int64_t *piece_offsets, const int64_t *piece_counts, int32_t num_pieces,
                                      int32_t rank, int32_t world, int32_t max_ctas, mb_stream_t stream) {

@@ -61,7 +61,21 @@ try:
     identical = bool(torch.equal(probe, ref))
     for ctas in (0, 64, 32, 16):
         res[f"multimem all-reduce 118 MB, max_ctas={ctas or 'SMs'}"] = timeit(lambda: ex.all_reduce_all(ctas))
+    # hybrid: part of every piece through plain peer-to-peer loads / stores beside the in-switch reduction
+    whole = [(0, N * 59)]
+    for frac in (0.3, 0.4, 0.5, 0.6):
+        fg.grad.copy_(src)
+        torch.cuda.synchronize(); dist.barrier()
+        ex.all_reduce_hybrid(whole, frac, 32, 64)
+        torch.cuda.synchronize()
+        herr = float((fg.grad - want).abs().max()) / float(want.abs().max())
+        for pc in (48, 128):
+            res[f"hybrid p2p={frac} p2p_ctas={pc}"] = timeit(lambda: ex.all_reduce_hybrid(whole, frac, 32, pc))
+        res[f"hybrid p2p={frac} max rel err"] = herr
+    res["p2p only"] = timeit(lambda: ex.all_reduce_hybrid(whole, 1.0, 32, 128))
     chunk = ex.pieces(0, 125056)
+    for frac in (0.4, 0.5):
+        res[f"hybrid p2p={frac}, one of 4 ranges"] = timeit(lambda: ex.all_reduce_hybrid(chunk, frac, 32, 64))
     res["multimem all-reduce, one of 4 ranges (6 pieces, 29.5 MB)"] = timeit(lambda: ex.all_reduce(chunk))
     res["max rel err vs NCCL"] = err
     res["bitwise equal to NCCL"] = float(same)
