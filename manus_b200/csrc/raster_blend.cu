@@ -147,10 +147,25 @@ struct ListStager {
     __device__ __forceinline__ const uint32_t *ids(int i) const { return &sm.ids[i % kIdSlots][(first + (uint32_t)(batch_of(i) * B)) & 3u]; }
 };
 
+#ifndef MB_FWD_FAST_EXP
+#define MB_FWD_FAST_EXP 1
+#endif
 #ifndef MB_FWD_GROUP
 #define MB_FWD_GROUP 4
 #endif
 constexpr int kGroup = MB_FWD_GROUP;   // survivors evaluated together in the forward (independent alpha evaluations)
+
+// exp(x) for x <= 0 (|x| < 100) with one MUFU.EX2, like expf(), in 6 instructions instead of expf()'s range split: exp(x) = 2^t 2^r with
+// t = fl(x log2e) and r = the rounding residual of that product plus x (log2e - fl(log2e)); |r| < 1e-6, so 2^r = 1 + r ln2.
+__device__ __forceinline__ float exp_neg(float x) {
+    const float L = 1.4426950216293334961f, Llo = 1.925963033500011079e-08f, ln2 = 0.693147182464599609375f;
+    const float t = x * L;
+    float r = fmaf(x, L, -t);
+    r = fmaf(x, Llo, r);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    return fmaf(e, r * ln2, e);
+}
 
 // pixel of a thread: the work item covers 8/kWarps... see kernel comments; vw = virtual warp index inside the 16x16 tile
 __device__ __forceinline__ void pixel_of_thread(int tile, int gx, int vw, int lane, int &px, int &py) {
@@ -220,7 +235,11 @@ __global__ void __launch_bounds__(kWarps * 32, 24 / kWarps) blend_forward_kernel
                     const float blue = r[3 * j + 2].x;
                     const float dx = ra.x - fx, dy = ra.y - fy;
                     const float power = -0.5f * (ra.z * dx * dx + rb.x * dy * dy) - ra.w * dx * dy;
+#if MB_FWD_FAST_EXP
+                    alpha[q] = fminf(kAlphaMax, rb.y * exp_neg(power));      // power > 0 gives garbage here and is rejected below
+#else
                     alpha[q] = fminf(kAlphaMax, rb.y * expf(power));
+#endif
                     valid[q] = has && power <= 0.0f && alpha[q] >= kAlphaMin;
                     cr[q] = rb.z; cg[q] = rb.w; cb[q] = blue;
                     pos1[q] = base + (uint32_t)j + 1u;
