@@ -15,7 +15,7 @@ W, H, NV = 1920, 1080, 50
 dev = torch.device("cuda", 0)
 scene = synth.make_composite(500_000, seed=0)
 r = SceneRenderer(scene, dev, W, H)
-G = torch.rand(H, W, 3, device=dev)
+G = torch.rand(3, H, W, device=dev).permute(1, 2, 0)
 staged = {}
 rz.set_capacity_mode("exact")
 dmax = 0
@@ -27,10 +27,10 @@ for v in range(NV):
         dmax = max(dmax, rz.check_overflow())
 rz.set_capacity_mode("reserve", margin=1.4)
 rz.reserve_capacity(0, scene.n, H, W, dmax)
-loss_fn = lambda image, target: (image * target).sum()
+loss_fn = lambda image, target: (torch.dot(image.permute(2, 0, 1).reshape(-1), target.permute(2, 0, 1).reshape(-1)), target)
 for spec in specs:
     # suffixes: o = ordered accumulation; p / pN = PipelinedStep with 1 / N ranges (all pose backwards in one multi-view pass)
-    if "p" in spec:
+    if "p" in spec:      # e.g. 4p, 4p2
         V, chunks = int(spec.split("p")[0]), int(spec.split("p")[1] or 1)
         step = PipelinedStep(r, loss_fn, G, view=0, views_in_flight=V, chunks=chunks)
     else:
