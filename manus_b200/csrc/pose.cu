@@ -163,25 +163,42 @@ __device__ __forceinline__ float mat3_inverse(const float *a, float *inv) {
     return det;
 }
 
+// Bit b of the mask: this Gaussian's weight of bone b is not zero.  The weights do not depend on the view, so kernels that
+// blend the same row against several views' bones build the mask once.
+__device__ __forceinline__ uint64_t bone_mask(const float *w_row, int B) {
+    uint64_t m = 0;
+    for (int b = 0; b < B; ++b) m |= (uint64_t)(w_row[b] != 0.f) << b;
+    return m;
+}
+
+// p.A | p.t | p.s = sum_b w_b T_b over the bones of the mask, in ascending b (the same terms in the same order as a loop over
+// all bones that skips zero weights).  Every lane walks its OWN non-zero bones: a warp of unrelated Gaussians takes as many
+// trips as its busiest lane has bones (~11 of 21 for MANO-style weights) instead of one per bone any lane uses (~20); lanes
+// on different bones read different rows of the 13-float table, 13 being odd the rows fall in different banks.
+__device__ __forceinline__ void blend_bones(const float *w_row, uint64_t mask, const float *bones_s, PoseLocal &p) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) p.A[k] = 0.f;
+    p.t[0] = p.t[1] = p.t[2] = 0.f; p.s = 0.f;
+    while (mask) {
+        const int b = __ffsll((long long)mask) - 1;
+        mask &= mask - 1;
+        const float w = w_row[b];
+        const float *T = bones_s + 13 * b;
+        p.A[0] += w * T[0]; p.A[1] += w * T[1]; p.A[2] += w * T[2]; p.t[0] += w * T[3];
+        p.A[3] += w * T[4]; p.A[4] += w * T[5]; p.A[5] += w * T[6]; p.t[1] += w * T[7];
+        p.A[6] += w * T[8]; p.A[7] += w * T[9]; p.A[8] += w * T[10]; p.t[2] += w * T[11];
+        p.s += w * T[12];
+    }
+}
+
 // everything both directions need: blended transform, rotation, scales.  `st` = the tile's stage, `row` = thread's row.
 __device__ __forceinline__ void pose_common(const PoseArgs &a, const TileLayout &L, const float *st, int i, int row,
                                             const float *bones_s, PoseLocal &p) {
     p.x[0] = st[L.xyz + 3 * row]; p.x[1] = st[L.xyz + 3 * row + 1]; p.x[2] = st[L.xyz + 3 * row + 2];
     p.skinned = i < a.n_skinned;
     if (p.skinned) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) p.A[k] = 0.f;
-        p.t[0] = p.t[1] = p.t[2] = 0.f; p.s = 0.f;
         const float *w_row = st + L.sk + row * a.B;
-        for (int b = 0; b < a.B; ++b) {
-            const float w = w_row[b];
-            if (w == 0.f) continue;
-            const float *T = bones_s + 13 * b;
-            p.A[0] += w * T[0]; p.A[1] += w * T[1]; p.A[2] += w * T[2]; p.t[0] += w * T[3];
-            p.A[3] += w * T[4]; p.A[4] += w * T[5]; p.A[5] += w * T[6]; p.t[1] += w * T[7];
-            p.A[6] += w * T[8]; p.A[7] += w * T[9]; p.A[8] += w * T[10]; p.t[2] += w * T[11];
-            p.s += w * T[12];
-        }
+        blend_bones(w_row, bone_mask(w_row, a.B), bones_s, p);
     } else {
         p.A[0] = p.A[4] = p.A[8] = 1.f;
         p.A[1] = p.A[2] = p.A[3] = p.A[5] = p.A[6] = p.A[7] = 0.f;
@@ -758,6 +775,7 @@ __global__ void __launch_bounds__(kPoseThreads, 4) pose_backward_multi_kernel(Po
             // ---- view-independent part: rotation, scales, L = R diag(S)
             p.x[0] = st[L.xyz + 3 * row]; p.x[1] = st[L.xyz + 3 * row + 1]; p.x[2] = st[L.xyz + 3 * row + 2];
             p.skinned = i < a.n_skinned;
+            const uint64_t nzmask = p.skinned ? bone_mask(st + L.sk + row * a.B, a.B) : 0ull;
             {
                 const float4 q = *reinterpret_cast<const float4 *>(st + L.quat + 4 * row);
                 p.qnorm = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
@@ -788,19 +806,7 @@ __global__ void __launch_bounds__(kPoseThreads, 4) pose_backward_multi_kernel(Po
                 const float *bones_s = bones_all + v * a.B * 13, *cam = cams + v * kViewCam;
                 // ---- the view's blended transform
                 if (p.skinned) {
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) p.A[k] = 0.f;
-                    p.t[0] = p.t[1] = p.t[2] = 0.f; p.s = 0.f;
-                    const float *w_row = st + L.sk + row * a.B;
-                    for (int b = 0; b < a.B; ++b) {
-                        const float w = w_row[b];
-                        if (w == 0.f) continue;
-                        const float *T = bones_s + 13 * b;
-                        p.A[0] += w * T[0]; p.A[1] += w * T[1]; p.A[2] += w * T[2]; p.t[0] += w * T[3];
-                        p.A[3] += w * T[4]; p.A[4] += w * T[5]; p.A[5] += w * T[6]; p.t[1] += w * T[7];
-                        p.A[6] += w * T[8]; p.A[7] += w * T[9]; p.A[8] += w * T[10]; p.t[2] += w * T[11];
-                        p.s += w * T[12];
-                    }
+                    blend_bones(st + L.sk + row * a.B, nzmask, bones_s, p);
                 } else {
                     p.A[0] = p.A[4] = p.A[8] = 1.f;
                     p.A[1] = p.A[2] = p.A[3] = p.A[5] = p.A[6] = p.A[7] = 0.f;
@@ -900,27 +906,38 @@ __global__ void __launch_bounds__(kPoseThreads, 4) pose_backward_multi_kernel(Po
                 for (int k = 0; k < 3; ++k) st[L.ls + 3 * row + k] = dS[k] * p.S[k];
             }
             // ---- SH gradients: sum over the views of basis_k(dir_v) go_v (the coefficient rows are no longer needed)
+            // (the sums over the views stay in registers -- most of the view loop's state is dead here -- and each coefficient is
+            // stored once)
             float gdc[3] = {0.f, 0.f, 0.f};
             float *frw = st + L.fr + row * (a.K - 1) * 3;
-            for (int v = 0; v < V; ++v) {
-                float basis[16];
-                sh_basis(DEG, dir_v[v][0], dir_v[v][1], dir_v[v][2], basis);
+            if (a.g_f_rest) {
+                constexpr int nr = nb > 1 ? (nb - 1) * 3 : 1;
+                float gfr[nr];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) gdc[c] += basis[0] * go_v[v][c];
-                if (a.g_f_rest) {
+                for (int k = 0; k < nr; ++k) gfr[k] = 0.f;
+                for (int v = 0; v < V; ++v) {
+                    float basis[16];
+                    sh_basis(DEG, dir_v[v][0], dir_v[v][1], dir_v[v][2], basis);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) gdc[c] += basis[0] * go_v[v][c];
 #pragma unroll
                     for (int k = 1; k < nb; ++k)
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const float t = basis[k] * go_v[v][c];
-                            frw[3 * (k - 1) + c] = v == 0 ? t : frw[3 * (k - 1) + c] + t;
-                        }
+                        for (int c = 0; c < 3; ++c) gfr[3 * (k - 1) + c] += basis[k] * go_v[v][c];
                 }
-            }
-            if (a.g_f_rest)
+#pragma unroll
+                for (int k = 1; k < nb; ++k)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) frw[3 * (k - 1) + c] = gfr[3 * (k - 1) + c];
                 for (int k = nb; k < a.K; ++k)
 #pragma unroll
                     for (int c = 0; c < 3; ++c) frw[3 * (k - 1) + c] = 0.f;
+            } else {
+                for (int v = 0; v < V; ++v) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) gdc[c] += MB_SH_C0 * go_v[v][c];
+                }
+            }
 #pragma unroll
             for (int c = 0; c < 3; ++c) st[L.gcol + 3 * row + c] = gdc[c];
 #pragma unroll

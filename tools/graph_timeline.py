@@ -30,7 +30,12 @@ for v in range(NV):
         dmax = max(dmax, rz.check_overflow())
 rz.set_capacity_mode("reserve", margin=1.4)
 rz.reserve_capacity(0, scene.n, H, W, dmax)
-step = GraphedStep(r, lambda image, target: (image * target).sum(), G, view=0, views_in_flight=V, profile=True)
+def loss(image, target):      # the bench's probe loss: one dot product, its gradient (the target itself) seeds the backward
+    return torch.dot(image.permute(2, 0, 1).reshape(-1), target.permute(2, 0, 1).reshape(-1)), target
+
+
+G = G.permute(2, 0, 1).contiguous().permute(1, 2, 0)       # stored CHW like the rendered image
+step = GraphedStep(r, loss, G, view=0, views_in_flight=V, profile=True)
 agg = defaultdict(list)
 spans = []
 for it in range(12):
