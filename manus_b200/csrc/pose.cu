@@ -73,6 +73,7 @@ struct PoseArgs {
     Record *rec;               // nullptr = plain pose forward
     ushort4 *rect;
     uint32_t *tiles_touched, *depth_key, *ident, *counters;
+    uint32_t *depth_hist;      // [4][256] digit counts of the depth keys (the depth sort's histogram, zeroed before the launch)
     int32_t *radii_out;
     int gx, gy;
 };
@@ -445,7 +446,11 @@ __global__ void __launch_bounds__(kPoseThreads) pose_forward_kernel(PoseArgs a) 
     extern __shared__ __align__(128) float smem[];
     constexpr int nb = (DEG + 1) * (DEG + 1);
     bool visible = false;        // of this thread's Gaussian in the current tile (kProject)
-    uint32_t my_tiles = 0;
+    bool has_key = false;
+    uint32_t my_tiles = 0, my_key = 0;
+    // kProject: digit counts of the depth keys this CTA writes = the histogram of the depth sort that follows the kernel
+    __shared__ uint32_t hist_s[kProject ? kSortMaxPasses * 256 : 1];
+    if (kProject) hist_smem_zero(hist_s);       // run_tiles starts with a barrier
     run_tiles<false, kProject>(a, smem, [&](const TileLayout &L, float *st, int i, int row, const float *bones_s, const float *cam_s) {
         PoseLocal p;
         pose_common(a, L, st, i, row, bones_s, p);
@@ -519,8 +524,14 @@ __global__ void __launch_bounds__(kPoseThreads) pose_forward_kernel(PoseArgs a) 
             a.tiles_touched[i] = pr.tiles;
             a.depth_key[i] = pr.key;
             a.ident[i] = (uint32_t)i;
+            my_key = pr.key;
+            has_key = true;
         }
     }, [&](int) {
+        if (kProject) {
+            if (has_key) hist_smem_count(hist_s, my_key, 4, 2);
+            has_key = false;
+        }
         if (kProject) {      // per-warp totals of the tile: visible Gaussians and instances (num_rendered)
             const unsigned vis = __ballot_sync(0xffffffffu, visible);
             const uint32_t wt = __reduce_add_sync(0xffffffffu, my_tiles);
@@ -532,6 +543,10 @@ __global__ void __launch_bounds__(kPoseThreads) pose_forward_kernel(PoseArgs a) 
             my_tiles = 0;
         }
     });
+    if (kProject) {
+        __syncthreads();
+        hist_smem_flush(hist_s, 4, a.depth_hist);
+    }
 }
 
 // kFused: upstream gradients from the rasterizer's accumulator rows (mb_pose_backward_from_raster)
@@ -1100,7 +1115,8 @@ template <int DEG>
 static int launch_pose(PoseArgs a, bool backward, cudaStream_t s) {
     const size_t smem = pose_smem_bytes(a.B, a.K, a.iso, backward);
     const int ntiles = (a.N + kPoseThreads - 1) / kPoseThreads;
-    int per_sm = (int)((size_t)(220 * 1024) / smem);
+    // (the fused projection adds the 4 KB static digit histogram of the depth sort)
+    int per_sm = (int)((size_t)(220 * 1024) / (smem + (!backward && a.rec ? sizeof(uint32_t) * kSortMaxPasses * 256 : 0)));
     if (per_sm < 1) {
         set_error("pose kernel: a tile of %d Gaussians with %d SH coefficients and %d bones needs %zu bytes of shared memory", kPoseThreads,
                   a.K, a.B, smem);
@@ -1177,10 +1193,13 @@ extern "C" int mb_pose_project_forward(const mb_pose_inputs *in, const mb_raster
         set_error("mb_pose_project_forward: geom buffer has %zu bytes, needs %zu", geom_bytes, g.bytes);
         return MB_ERR_WORKSPACE;
     }
-    // counters + look-back words of the instance-offset scan (contiguous), as mb_raster_forward_geom
-    MB_CUDA(cudaMemsetAsync(g.counters, 0, (size_t)((char *)(g.scan_status + (d.P + 255) / 256 + 1) - (char *)g.counters), s));
+    // counters + look-back words of the instance-offset scan + the depth sort's histograms / cursors / look-back words
+    // (contiguous), as mb_raster_forward_geom: the kernel counts the digits of the depth keys it writes
+    MB_CUDA(cudaMemsetAsync(g.counters, 0, g.zeroed_bytes(d.P), s));
     if (d.P > 0) {
+        SortWorkspace ws = carve_sort_workspace(g.sort_ws, d.P);
         PoseArgs a = pose_args(in);
+        a.depth_hist = ws.hist;
         a.posed_xyz = posed_xyz; a.cov6 = posed_cov6; a.colors = colors; a.opacity = opacity;
         a.view = raster->viewmatrix; a.proj = raster->projmatrix; a.tanfov_dev = raster->tanfov_dev;
         a.tanx = raster->tanfovx; a.tany = raster->tanfovy; a.W = d.W; a.H = d.H; a.gx = d.gx; a.gy = d.gy;
@@ -1188,8 +1207,7 @@ extern "C" int mb_pose_project_forward(const mb_pose_inputs *in, const mb_raster
         a.counters = g.counters; a.radii_out = radii;
         rc = launch_pose_deg(a, false, s);
         if (rc) return rc;
-        SortWorkspace ws = carve_sort_workspace(g.sort_ws, d.P);
-        rc = radix_sort_pairs(g.depth_key, g.ident, g.sorted_key, g.sorted_idx, d.P, nullptr, d.P, 0, 32, ws, s, raster->debug != 0);
+        rc = radix_sort_pairs(g.depth_key, g.ident, g.sorted_key, g.sorted_idx, d.P, nullptr, d.P, 0, 32, ws, s, raster->debug != 0, true);
         if (rc) return rc;
     }
     if (num_rendered_host) {

@@ -17,6 +17,7 @@ struct PreArgs {
     const float *means3D, *opac, *colors, *cov3D_precomp, *scales, *rots, *shs, *view, *proj, *campos, *tanfov_dev;
     GeomState g;
     int32_t *radii;
+    uint32_t *depth_hist;     // [4][256] digit counts of the depth keys (the depth sort's histogram, zeroed before the launch)
 };
 
 template <bool kPrecompCov, bool kSH>
@@ -34,7 +35,9 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {   // `a` i
     const float *v = cam, *p = cam + 16;
     const int i = blockIdx.x * 256 + tid;
     bool visible = false;
-    uint32_t my_tiles = 0;
+    uint32_t my_tiles = 0, my_key = 0;
+    __shared__ uint32_t hist_s[kSortMaxPasses * 256];
+    hist_smem_zero(hist_s);
     if (i < a.P) {
         const float mx = a.means3D[3 * i], my = a.means3D[3 * i + 1], mz = a.means3D[3 * i + 2];
         // A.1 step 4: 3-D covariance
@@ -99,11 +102,13 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {   // `a` i
         a.g.tiles_touched[i] = pr.tiles;
         a.g.depth_key[i] = pr.key;
         a.g.ident[i] = (uint32_t)i;
+        my_key = pr.key;
     }
     // per-CTA totals: visible Gaussians and instances (num_rendered is known as soon as this kernel has run)
     __shared__ uint32_t s_vis, s_tiles;
     if (tid == 0) { s_vis = 0; s_tiles = 0; }
-    __syncthreads();
+    __syncthreads();      // also: hist_s is zeroed
+    if (i < a.P) hist_smem_count(hist_s, my_key, 4, 2);       // digit counts of the depth sort that follows (bytes 2, 3 aggregated)
     const unsigned vis = __ballot_sync(0xffffffffu, visible);
     const uint32_t wt = __reduce_add_sync(0xffffffffu, my_tiles);
     if ((tid & 31) == 0 && vis) {
@@ -115,6 +120,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(PreArgs a) {   // `a` i
         atomicAdd(&a.g.counters[kCntVisible], s_vis);
         atomicAdd(&a.g.counters[kCntRendered], s_tiles);
     }
+    hist_smem_flush(hist_s, 4, a.depth_hist);
 }
 
 // Instance emission, warp-cooperative: a warp owns 32 consecutive depth-sorted Gaussians; their (tile id, gaussian id)
@@ -139,8 +145,12 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, int gx, cons
                                                              const ushort4 *__restrict__ rect,
                                                              uint32_t *__restrict__ counters, volatile uint32_t *status,
                                                              int64_t capacity, uint32_t *__restrict__ tile_out,
-                                                             uint32_t *__restrict__ gid_out, uint2 *__restrict__ big_list) {
+                                                             uint32_t *__restrict__ gid_out, uint2 *__restrict__ big_list,
+                                                             int key_passes, uint32_t *__restrict__ key_hist) {
     __shared__ uint32_t s_chunk, s_base, s_warp[8];
+    // digit counts of the tile ids this CTA writes: the histogram of the stable partition by tile that follows
+    __shared__ uint32_t hist_s[kSortMaxPasses * 256];
+    hist_smem_zero(hist_s);
     if (blockIdx.x == 0 && threadIdx.x == 0 && (int64_t)counters[kCntRendered] > capacity) counters[kCntOverflow] = 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nchunks = (P + kEmitChunk - 1) / kEmitChunk;
@@ -149,7 +159,10 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, int gx, cons
         if (threadIdx.x == 0) s_chunk = atomicAdd(&counters[kCntEmitCursor], 1u);
         __syncthreads();
         const int chunk = (int)s_chunk;
-        if (chunk >= nchunks) return;
+        if (chunk >= nchunks) {      // two barriers after the last count of this CTA
+            hist_smem_flush(hist_s, key_passes, key_hist);
+            return;
+        }
         // a warp owns 32 * kEmitItems consecutive depth-sorted Gaussians, item k of lane l is Gaussian first + 32 k + l;
         // the three dependent loads of all items are in flight together
         const int first = chunk * kEmitChunk + warp * (32 * kEmitItems);
@@ -243,8 +256,10 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, int gx, cons
                 const int64_t pos = (int64_t)o_off + local;
                 if (sl < total && pos < capacity) {
                     const uint32_t ty = local / o_w, tx = local - ty * o_w;
-                    tile_out[pos] = (o_y0 + ty) * (uint32_t)gx + o_x0 + tx;
+                    const uint32_t tile = (o_y0 + ty) * (uint32_t)gx + o_x0 + tx;
+                    tile_out[pos] = tile;
                     gid_out[pos] = o_g;
+                    hist_smem_count(hist_s, tile, key_passes, 1);
                 }
             }
         }
@@ -256,8 +271,13 @@ __global__ void __launch_bounds__(256) emit_big_kernel(int gx, const uint32_t *_
                                                        const uint32_t *__restrict__ tiles_touched,
                                                        const ushort4 *__restrict__ rect, const uint32_t *__restrict__ counters,
                                                        int64_t capacity, const uint2 *__restrict__ big_list,
-                                                       uint32_t *__restrict__ tile_out, uint32_t *__restrict__ gid_out) {
+                                                       uint32_t *__restrict__ tile_out, uint32_t *__restrict__ gid_out,
+                                                       int key_passes, uint32_t *__restrict__ key_hist) {
     const uint32_t nbig = counters[kCntBig];
+    if (blockIdx.x >= nbig) return;
+    __shared__ uint32_t hist_s[kSortMaxPasses * 256];
+    hist_smem_zero(hist_s);
+    __syncthreads();
     for (uint32_t e = blockIdx.x; e < nbig; e += gridDim.x) {
         const uint2 entry = big_list[e];
         const uint32_t g = sorted_idx[entry.x], cnt = tiles_touched[g];
@@ -268,11 +288,15 @@ __global__ void __launch_bounds__(256) emit_big_kernel(int gx, const uint32_t *_
             const int64_t pos = off + local;
             if (pos < capacity) {
                 const uint32_t ty = local / w, tx = local - ty * w;
-                tile_out[pos] = ((uint32_t)r.y + ty) * (uint32_t)gx + (uint32_t)r.x + tx;
+                const uint32_t tile = ((uint32_t)r.y + ty) * (uint32_t)gx + (uint32_t)r.x + tx;
+                tile_out[pos] = tile;
                 gid_out[pos] = g;
+                hist_smem_count(hist_s, tile, key_passes, 1);
             }
         }
     }
+    __syncthreads();
+    hist_smem_flush(hist_s, key_passes, key_hist);
 }
 
 // tile ranges from the tile-sorted instance list, one thread per instance
@@ -508,23 +532,26 @@ int build_instances(const mb_raster_inputs *in, const RasterDims &d, const GeomS
     const bool dbg = in->debug != 0;
     const int grid_p = max(1, min((d.P + kEmitChunk - 1) / kEmitChunk, sm_count() * 8));
     MB_CUDA(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)d.tiles, s));
+    // the emission kernels count the digits of the tile ids they write (histogram of the partition by tile below): its
+    // workspace is cleared here, in front of them
+    SortWorkspace ws = carve_sort_workspace(b.sort_ws, capacity > 0 ? capacity : 1);
+    const int key_bits = tile_bits(d.tiles), key_passes = sort_passes(0, key_bits);
+    MB_CUDA(cudaMemsetAsync(ws.zeroed, 0, ws.zeroed_bytes, s));
     {
     KernelTimer kt("emit_instances", s);
     emit_instances_kernel<<<grid_p, 256, 0, s>>>(d.P, d.gx, g.sorted_idx, g.tiles_touched, g.rect, g.counters, g.scan_status,
-                                                 capacity, b.tile_a, b.gid_a, g.big_list);
+                                                 capacity, b.tile_a, b.gid_a, g.big_list, key_passes, ws.hist);
     }
     int rc = check_launch("emit_instances", dbg, s);
     if (rc) return rc;
     {
     KernelTimer kt("emit_big", s);
     emit_big_kernel<<<sm_count() * 2, 256, 0, s>>>(d.gx, g.sorted_idx, g.tiles_touched, g.rect, g.counters, capacity, g.big_list,
-                                                  b.tile_a, b.gid_a);
+                                                  b.tile_a, b.gid_a, key_passes, ws.hist);
     }
     rc = check_launch("emit_big", dbg, s);
     if (rc) return rc;
-    SortWorkspace ws = carve_sort_workspace(b.sort_ws, capacity > 0 ? capacity : 1);
-    rc = radix_sort_pairs(b.tile_a, b.gid_a, b.tile_b, b.gid_b, -1, g.counters + kCntRendered, capacity, 0, tile_bits(d.tiles),
-                          ws, s, dbg);
+    rc = radix_sort_pairs(b.tile_a, b.gid_a, b.tile_b, b.gid_b, -1, g.counters + kCntRendered, capacity, 0, key_bits, ws, s, dbg, true);
     if (rc) return rc;
     const int grid_d = (int)max((int64_t)1, min((capacity + 255) / 256, (int64_t)sm_count() * 16));
     {
@@ -560,10 +587,13 @@ extern "C" int mb_raster_forward_geom(const mb_raster_inputs *in, void *geom, si
         return MB_ERR_WORKSPACE;
     }
     const bool dbg = in->debug != 0;
-    // counters + look-back words of the instance-offset scan (contiguous)
-    MB_CUDA(cudaMemsetAsync(g.counters, 0, (size_t)((char *)(g.scan_status + (d.P + 255) / 256 + 1) - (char *)g.counters), s));
+    // counters + look-back words of the instance-offset scan + histograms / cursors / look-back words of the depth sort
+    // (contiguous): the projection kernel counts the digits of the depth keys it writes, so the sort below is its passes only
+    MB_CUDA(cudaMemsetAsync(g.counters, 0, g.zeroed_bytes(d.P), s));
     if (d.P > 0) {
+        SortWorkspace ws = carve_sort_workspace(g.sort_ws, d.P);
         PreArgs a;
+        a.depth_hist = ws.hist;
         a.P = d.P; a.W = d.W; a.H = d.H; a.gx = d.gx; a.gy = d.gy; a.deg = in->sh_degree; a.M = in->sh_coeffs;
         a.tanx = in->tanfovx; a.tany = in->tanfovy; a.focx = d.focx; a.focy = d.focy; a.scale_mod = in->scale_modifier;
         a.means3D = in->means3D; a.opac = in->opacities; a.cov3D_precomp = in->cov3D_precomp; a.scales = in->scales;
@@ -584,8 +614,7 @@ extern "C" int mb_raster_forward_geom(const mb_raster_inputs *in, void *geom, si
         rc = check_launch("preprocess", dbg, s);
         if (rc) return rc;
         // depth order (stable; culled Gaussians carry key 0xffffffff and sink to the end)
-        SortWorkspace ws = carve_sort_workspace(g.sort_ws, d.P);
-        rc = radix_sort_pairs(g.depth_key, g.ident, g.sorted_key, g.sorted_idx, d.P, nullptr, d.P, 0, 32, ws, s, dbg);
+        rc = radix_sort_pairs(g.depth_key, g.ident, g.sorted_key, g.sorted_idx, d.P, nullptr, d.P, 0, 32, ws, s, dbg, true);
         if (rc) return rc;
     }
     if (num_rendered_host) {

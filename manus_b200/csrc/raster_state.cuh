@@ -2,8 +2,8 @@
 //
 // HBM layout (all arrays 256-B aligned inside their buffer):
 //   geom    (per Gaussian, P rows)  : 48-B blend record | cov3D f32x6 (scale/rotation mode only) | tiles u32 | tile rect u16x4 |
-//                                     SH clamp mask u32 | depth key u32 | identity idx u32 | depth-sorted key/idx u32 |
-//                                     sort workspace | counters + look-back words of the instance-offset scan
+//                                     SH clamp mask u32 | depth key u32 | identity idx u32 | depth-sorted key/idx u32;
+//                                     in front of them: counters + look-back words of the instance-offset scan | sort workspace
 //   binning (per instance, D rows)  : tile id u32 x2 (ping-pong) | gaussian id u32 x2 (ping-pong; the sorted one is the per-tile
 //                                     depth-ordered list the tile kernels walk) | sort workspace
 //   image   (per pixel / per tile)  : final_T f32 | n_contrib u32 | tile range u32x2 | deepest last-contributor per tile u32 |
@@ -49,6 +49,9 @@ struct GeomState {
         const size_t n = (size_t)(P > 0 ? P : 1);
         g.counters = c.take<uint32_t>(kNumCounters);
         g.scan_status = c.take<uint32_t>((n + 255) / 256 + 1);
+        // the depth sort's workspace starts with what has to be zero before the projection kernel counts the key digits
+        // (histograms | cursors | look-back words): it follows the counters so that ONE memset per frame clears all of it
+        g.sort_ws = c.take<char>(sort_workspace_bytes((int64_t)n));
         g.rec = c.take<Record>(n);
         g.cov3D = c.take<float>(6 * n);
         g.tiles_touched = c.take<uint32_t>(n);
@@ -59,9 +62,14 @@ struct GeomState {
         g.sorted_key = c.take<uint32_t>(n);
         g.sorted_idx = c.take<uint32_t>(n);
         g.big_list = c.take<uint2>(n);
-        g.sort_ws = c.take<char>(sort_workspace_bytes((int64_t)n));
         g.bytes = c.off;
         return g;
+    }
+
+    // bytes from `counters` to the end of the depth sort's zeroed region
+    size_t zeroed_bytes(int64_t P) const {
+        const SortWorkspace ws = carve_sort_workspace(sort_ws, P > 0 ? P : 1);
+        return (size_t)((char *)ws.zeroed + ws.zeroed_bytes - (char *)counters);
     }
 };
 

@@ -238,10 +238,10 @@ __global__ void copy_pairs_kernel(const uint32_t *__restrict__ ki, const uint32_
 
 int radix_sort_pairs(uint32_t *keys_in, uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out, int64_t n_host,
                      const uint32_t *n_dev, int64_t max_n, int begin_bit, int end_bit, const SortWorkspace &ws,
-                     cudaStream_t stream, bool debug) {
+                     cudaStream_t stream, bool debug, bool hist_ready) {
     const int64_t bound = n_host >= 0 ? n_host : max_n;
     if (bound <= 0) return MB_OK;
-    const int passes = (end_bit - begin_bit + 7) / 8;
+    const int passes = sort_passes(begin_bit, end_bit);
     const int64_t chunks = sort_chunks(bound);
     if (chunks > ws.max_chunks || passes > kSortMaxPasses) {
         set_error("radix_sort_pairs: workspace too small (%lld chunks > %lld) or too many passes (%d)", (long long)chunks,
@@ -253,15 +253,18 @@ int radix_sort_pairs(uint32_t *keys_in, uint32_t *vals_in, uint32_t *keys_out, u
         copy_pairs_kernel<<<grid, 256, 0, stream>>>(keys_in, vals_in, keys_out, vals_out, n_host, n_dev, max_n);
         return check_launch("copy_pairs", debug, stream);
     }
-    MB_CUDA(cudaMemsetAsync(ws.zeroed, 0, ws.zeroed_bytes, stream));
-    {
-        KernelTimer kt("radix_hist", stream);
-        const int64_t want = (bound + kSortThreads * 16 - 1) / (kSortThreads * 16);
-        const int grid = (int)(want < (int64_t)sm_count() * 4 ? want : (int64_t)sm_count() * 4);
-        radix_hist_kernel<<<grid, kSortThreads, 0, stream>>>(keys_in, n_host, n_dev, max_n, begin_bit, passes, ws.hist);
+    int rc = MB_OK;
+    if (!hist_ready) {
+        MB_CUDA(cudaMemsetAsync(ws.zeroed, 0, ws.zeroed_bytes, stream));
+        {
+            KernelTimer kt("radix_hist", stream);
+            const int64_t want = (bound + kSortThreads * 16 - 1) / (kSortThreads * 16);
+            const int grid = (int)(want < (int64_t)sm_count() * 4 ? want : (int64_t)sm_count() * 4);
+            radix_hist_kernel<<<grid, kSortThreads, 0, stream>>>(keys_in, n_host, n_dev, max_n, begin_bit, passes, ws.hist);
+        }
+        rc = check_launch("radix_hist", debug, stream);
+        if (rc) return rc;
     }
-    int rc = check_launch("radix_hist", debug, stream);
-    if (rc) return rc;
     // ping-pong so that the last pass lands in keys_out / vals_out
     uint32_t *src_k = keys_in, *src_v = vals_in;
     for (int p = 0; p < passes; ++p) {

@@ -50,10 +50,48 @@ inline SortWorkspace carve_sort_workspace(void *p, int64_t max_n) {
     return w;
 }
 
-// n = n_host if >= 0 else min(*n_dev, max_n)
+// n = n_host if >= 0 else min(*n_dev, max_n).
+// hist_ready: the caller cleared ws.zeroed (ws.zeroed_bytes) BEFORE the kernel that produced the keys ran, and that kernel
+// counted the digits of every key it wrote into ws.hist (hist_smem_* below): the sort is then the passes only -- no memset and
+// no histogram launch between the producer and the first pass.
 int radix_sort_pairs(uint32_t *keys_in, uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out, int64_t n_host,
                      const uint32_t *n_dev, int64_t max_n, int begin_bit, int end_bit, const SortWorkspace &ws,
-                     cudaStream_t stream, bool debug);
+                     cudaStream_t stream, bool debug, bool hist_ready = false);
+
+inline int sort_passes(int begin_bit, int end_bit) { return (end_bit - begin_bit + 7) / 8; }
+
+#ifdef __CUDACC__
+// Digit counting inside the kernel that produces the keys.  h = kSortMaxPasses * 256 words of shared memory, zeroed by
+// hist_smem_zero (+ a barrier) at the start of the kernel; hist_smem_count for every key the kernel writes (any subset of a
+// warp's lanes may call it: lanes that arrive together are grouped with __activemask); hist_smem_flush once per CTA after a
+// barrier that follows the last count.  Digits from `agg_from` on are counted once per group of lanes holding the same digit
+// (the high bytes of depth keys and of tile ids are nearly constant inside a warp: 32 same-address shared atomics otherwise).
+__device__ __forceinline__ void hist_smem_zero(uint32_t *h) {
+    for (int e = threadIdx.x; e < kSortMaxPasses * 256; e += blockDim.x) h[e] = 0;
+}
+
+__device__ __forceinline__ void hist_smem_count(uint32_t *h, uint32_t key, int passes, int agg_from) {
+    const unsigned act = __activemask();
+    const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+#pragma unroll
+    for (int p = 0; p < kSortMaxPasses; ++p) {
+        if (p < passes) {
+            const uint32_t d = (key >> (8 * p)) & 255u;
+            if (p < agg_from) {
+                atomicAdd(&h[p * 256 + d], 1u);
+            } else {
+                const unsigned peers = __match_any_sync(act, d);
+                if ((peers & lt) == 0) atomicAdd(&h[p * 256 + d], (uint32_t)__popc(peers));
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void hist_smem_flush(const uint32_t *h, int passes, uint32_t *hist) {
+    for (int e = threadIdx.x; e < passes * 256; e += blockDim.x)
+        if (h[e]) atomicAdd(&hist[e], h[e]);
+}
+#endif
 
 // out[i] = sum_{j<i} f(j) for i < n, where f(j) = src[j] or src[index[j]] (gather); *total = sum of all.
 // partials: scratch of scan_blocks(n) uint32.  n is a host value.

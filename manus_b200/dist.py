@@ -160,8 +160,12 @@ class SceneRenderer:
     """Everything one rank needs to render views of a (hand | object | composite) scene forward + backward through the
     public API: resident parameters (flat), skin weights, rest bones, and per-view cameras / bone poses."""
 
-    def __init__(self, scene, device, width: int = 1920, height: int = 1080, bg=(1.0, 1.0, 1.0), sh_degree: int = 3):
-        from . import synth
+    def __init__(self, scene, device, width: int = 1920, height: int = 1080, bg=(1.0, 1.0, 1.0), sh_degree: int = 3, plan=None):
+        from . import rasterizer as rz, synth
+
+        # how this renderer's frames size their instance buffers (exact / reserve, high-water marks, the last frame's state):
+        # the device's default plan unless the caller hands over a private rasterizer.CapacityPlan
+        self.plan = plan if plan is not None else rz.plan_for(device)
 
         self.device, self.W, self.H, self.sh_degree = device, width, height, sh_degree
         self.flat = FlatGaussians.from_scene(scene, device)
@@ -222,6 +226,11 @@ class SceneRenderer:
                       tanfov_dev=cam_dev[37:39] if device_intrinsics else None)
         bone_tf = None
         fuse = self.fuse_backward if fuse_backward is None else fuse_backward
+        if not fuse:
+            from . import rasterizer as rz
+            if self.plan is not rz.plan_for(self.device):
+                # the two-node path goes through the drop-in GaussianRasterizer, whose signature (upstream's) has no room for a plan
+                raise ValueError("a private CapacityPlan needs the fused path (fuse_backward=True)")
         if self.n_hand > 0:
             nb = self.rest_inv.shape[0]
             if fuse and not compact_sh:
@@ -241,7 +250,7 @@ class SceneRenderer:
             sink = dict(sink, f_rest=None)
         self._last_campos = cam_dev[32:35]
         return render_fused(self.flat.leaves(), self.skin, bone_tf, dcam, self.bg, self.sh_degree, self.flat.isotropic,
-                            self.n_hand, grad_sink=sink, accumulate=accumulate, fuse_backward=fuse, want_posed=want_posed)
+                            self.n_hand, grad_sink=sink, accumulate=accumulate, fuse_backward=fuse, want_posed=want_posed, plan=self.plan)
 
 
 class CompactGradExchange:
@@ -375,7 +384,7 @@ class PipelinedStep:
         # in NVSwitch multicast memory and the ranges are summed by the repository's own multimem kernel on a side stream);
         # None: one coalesced NCCL all-reduce per range
         self.exchange, self.exchange_ctas = exchange, exchange_ctas
-        if rz._Plan.mode != "reserve":
+        if renderer.plan.mode != "reserve":
             raise RuntimeError("PipelinedStep needs set_capacity_mode('reserve') and reserve_capacity(...) (no host read-back in a graph)")
         self.r, self.V, self.group = renderer, int(views_in_flight), group
         # reduce=False: replay() leaves the exchange to the caller (e.g. one all-reduce of the whole buffer after the step)
@@ -416,7 +425,7 @@ class PipelinedStep:
                         sink["_defer"] = []
                     out = renderer.render(view, sink=sink, cam_dev=self.cams[i], bones_dev=self.bones_all[i], device_intrinsics=True, slot=i,
                                           accumulate=i < early)
-                    self.states[i] = rz._Plan.last_state
+                    self.states[i] = renderer.plan.last_state
                     self.viewspace[i] = out["viewspace_points"]
                     losses[i] = _loss_and_seed(loss_fn, out["render"], self.targets[i])
                     outs[i] = sink
@@ -536,7 +545,7 @@ class GraphedStep:
 
         self.stats = stats      # (xyz_gradient_accum, denom, max_radii2D) updated by the pose backward of every view, or None
 
-        if rz._Plan.mode != "reserve":
+        if renderer.plan.mode != "reserve":
             raise RuntimeError("GraphedStep needs set_capacity_mode('reserve') and reserve_capacity(...) (no host read-back in a graph)")
         V = int(views_in_flight)
         if V < 1 or (compact_sh and V > 1):
@@ -561,7 +570,7 @@ class GraphedStep:
                 sink = dict(sink, _wait=done[i - 1] if i > 0 else None, _record=done[i])
             out = renderer.render(view, sink=sink, cam_dev=self.cams[i], bones_dev=self.bones_all[i], device_intrinsics=True,
                                   compact_sh=compact_sh, accumulate=V > 1 and (i > 0 or not ordered), slot=i)
-            self.states[i] = rz._Plan.last_state
+            self.states[i] = renderer.plan.last_state
             self.viewspace[i] = out["viewspace_points"]
             loss = _loss_and_seed(loss_fn, out["render"], self.targets[i])
             return loss, out["radii"]

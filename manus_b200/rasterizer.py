@@ -13,7 +13,7 @@ the current stream only.
 from __future__ import annotations
 
 import ctypes as C
-from typing import NamedTuple, Optional
+from typing import Dict, NamedTuple, Optional
 
 import torch
 import torch.nn as nn
@@ -47,32 +47,71 @@ def _dense(t: Optional[torch.Tensor], shape=None) -> Optional[torch.Tensor]:
     return t if shape is None else t.reshape(shape)
 
 
-class _Plan:
-    """How instance capacity is chosen.  'exact': one host read of num_rendered per forward (what upstream does).
-    'reserve': no host synchronisation -- capacity is the high-water mark of earlier frames times a margin; an overflow
-    is detected at the next host read and the frame is redone exactly."""
-    mode = "exact"
-    margin = 1.3
-    high_water = {}
-    last_state = None      # RasterState of the most recent forward (for check_overflow)
+class CapacityPlan:
+    """How the instance capacity of a frame is chosen, and the state that choice needs.  One plan per DEVICE by default
+    (``plan_for``); a renderer may hold its own (``SceneRenderer(plan=...)``) so that two scenes on one GPU do not share
+    high-water marks.
+    'exact': one host read of num_rendered per forward (what upstream does).
+    'reserve': no host synchronisation -- capacity is the high-water mark of earlier frames of the same (N, H, W) times a
+    margin; an overflow is recorded in the frame's device counters and raised at the next host read (``check_overflow``)."""
+
+    def __init__(self, mode: str = "exact", margin: float = 1.3):
+        self.high_water: Dict[tuple, int] = {}
+        self.last_state = None      # RasterState of the most recent forward sized by this plan (for check_overflow)
+        self.set_mode(mode, margin)
+
+    def set_mode(self, mode: str, margin: float = 1.3) -> None:
+        assert mode in ("exact", "reserve")
+        self.mode, self.margin = mode, margin
+        self.high_water.clear()
+
+    def reserve(self, num_points: int, height: int, width: int, instances: int) -> None:
+        key = (int(num_points), int(height), int(width))
+        self.high_water[key] = max(self.high_water.get(key, 0), int(instances))
 
 
-def set_capacity_mode(mode: str, margin: float = 1.3) -> None:
+_plans: Dict[int, CapacityPlan] = {}
+_plan_defaults = ["exact", 1.3]
+
+
+def _device_index(device) -> int:
+    if device is None:
+        return torch.cuda.current_device()
+    if isinstance(device, int):
+        return device
+    device = torch.device(device)
+    return torch.cuda.current_device() if device.index is None else device.index
+
+
+def plan_for(device=None) -> CapacityPlan:
+    """The default plan of a device (index, torch.device or None = the current device)."""
+    idx = _device_index(device)
+    if idx not in _plans:
+        _plans[idx] = CapacityPlan(*_plan_defaults)
+    return _plans[idx]
+
+
+def set_capacity_mode(mode: str, margin: float = 1.3, device=None) -> None:
+    """device=None: every device's default plan (and the default of plans created later); else that device's plan only."""
     assert mode in ("exact", "reserve")
-    _Plan.mode, _Plan.margin = mode, margin
-    _Plan.high_water.clear()
+    if device is None:
+        _plan_defaults[:] = [mode, margin]
+        for pl in _plans.values():
+            pl.set_mode(mode, margin)
+    else:
+        plan_for(device).set_mode(mode, margin)
 
 
 def reserve_capacity(device_index: int, num_points: int, height: int, width: int, instances: int) -> None:
     """Reserve-mode sizing: frames of this (device, N, H, W) get room for ``instances * margin`` instances."""
-    key = (device_index, num_points, height, width)
-    _Plan.high_water[key] = max(_Plan.high_water.get(key, 0), int(instances))
+    plan_for(device_index).reserve(num_points, height, width, instances)
 
 
-def check_overflow(st: "Optional[RasterState]" = None) -> int:
+def check_overflow(st: "Optional[RasterState]" = None, device=None) -> int:
     """Reserve mode reads nothing back per frame; call this when convenient (it synchronises the stream): returns
-    num_rendered of the given / most recent forward, raises if that frame needed more instances than were reserved."""
-    st = st if st is not None else _Plan.last_state
+    num_rendered of the given forward / the most recent forward of the device's default plan, raises if that frame needed
+    more instances than were reserved."""
+    st = st if st is not None else plan_for(device).last_state
     if st is None:
         return 0
     st.num_rendered = -1
@@ -82,7 +121,7 @@ def check_overflow(st: "Optional[RasterState]" = None) -> int:
 
 class RasterState:
     """Opaque state kept from forward to backward (upstream: geomBuffer / binningBuffer / imgBuffer / num_rendered)."""
-    __slots__ = ("inputs", "keep", "geom", "binning", "image", "capacity", "num_rendered", "radii", "host_count", "event", "key")
+    __slots__ = ("inputs", "keep", "geom", "binning", "image", "capacity", "num_rendered", "radii", "host_count", "event", "key", "plan")
 
     def resolve(self) -> int:
         """num_rendered of this frame (waits for the count copy if it is still in flight); raises on overflow."""
@@ -92,7 +131,7 @@ class RasterState:
             else:
                 self.event.synchronize()
                 self.num_rendered = int(self.host_count.item())
-            _Plan.high_water[self.key] = max(_Plan.high_water.get(self.key, 0), self.num_rendered)
+            self.plan.high_water[self.key] = max(self.plan.high_water.get(self.key, 0), self.num_rendered)
             if self.num_rendered > self.capacity:
                 raise _lib.ManusB200Error(
                     f"instance capacity overflow: frame needed {self.num_rendered} instances, {self.capacity} were reserved; "
@@ -136,13 +175,14 @@ def _make_inputs(settings: GaussianRasterizationSettings, means3D, opacities, co
 
 def rasterize_forward(settings: GaussianRasterizationSettings, means3D, opacities, colors_precomp=None, shs=None,
                       cov3D_precomp=None, scales=None, rotations=None, capacity: Optional[int] = None, exact: bool = False,
-                      pose_inputs=None):
+                      pose_inputs=None, plan: Optional[CapacityPlan] = None):
     """-> (color[3,H,W], radii[N], RasterState).  Inputs must already be dense fp32 CUDA tensors (or None).
     exact=True: size the instance buffers from this frame's own num_rendered (one host read) whatever the capacity mode.
     pose_inputs: a filled ``_lib.PoseInputs`` -- the per-Gaussian stage then is mb_pose_project_forward (LBS + covariance +
     SH->RGB + projection in ONE kernel) instead of mb_raster_forward_geom on precomputed arrays; means3D / opacities /
     colors_precomp / cov3D_precomp are then OUTPUT buffers of that kernel, or all None (the posed arrays never touch HBM;
-    only the fused backward, mb_pose_backward_from_raster, can follow)."""
+    only the fused backward, mb_pose_backward_from_raster, can follow).
+    plan: the CapacityPlan that sizes the instance buffers (default: the device's, ``plan_for``)."""
     L = _lib.lib()
     if pose_inputs is None and not means3D.is_cuda:
         raise _lib.ManusB200Error("manus_b200 rasterizer needs CUDA tensors (there is no CPU path)")
@@ -161,8 +201,9 @@ def rasterize_forward(settings: GaussianRasterizationSettings, means3D, opacitie
         st.image = torch.empty(L.mb_raster_image_bytes(W, H), dtype=torch.uint8, device=dev)
         st.radii = torch.empty(N, dtype=torch.int32, device=dev)
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
-        st.key = (dev.index, N, H, W)
-        reserve = capacity is None and not exact and _Plan.mode == "reserve" and st.key in _Plan.high_water
+        st.plan = plan if plan is not None else plan_for(dev)
+        st.key = (N, H, W)
+        reserve = capacity is None and not exact and st.plan.mode == "reserve" and st.key in st.plan.high_water
         # reserve mode: nothing is read back per frame (the frame can be captured in a CUDA graph); an overflow is
         # recorded in the device counters and raised by check_overflow() / raster_query()
         st.host_count = None if reserve else torch.zeros(1, dtype=torch.int64).pin_memory()
@@ -177,7 +218,7 @@ def rasterize_forward(settings: GaussianRasterizationSettings, means3D, opacitie
         st.num_rendered = -1
         st.event = None
         if reserve:
-            capacity = int(_Plan.high_water[st.key] * _Plan.margin) + 1024      # no host synchronisation
+            capacity = int(st.plan.high_water[st.key] * st.plan.margin) + 1024      # no host synchronisation
         else:
             st.event = torch.cuda.Event()
             st.event.record(torch.cuda.current_stream(dev))
@@ -188,7 +229,7 @@ def rasterize_forward(settings: GaussianRasterizationSettings, means3D, opacitie
         st.binning = torch.empty(L.mb_raster_binning_bytes(st.capacity, W, H), dtype=torch.uint8, device=dev)
         _lib.check(L.mb_raster_forward_render(C.byref(st.inputs), ptr(st.geom), ptr(st.binning), st.binning.numel(), st.capacity,
                                               ptr(st.image), st.image.numel(), ptr(color), stream), "mb_raster_forward_render")
-    _Plan.last_state = st
+    st.plan.last_state = st
     return color, st.radii, st
 
 

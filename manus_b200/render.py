@@ -244,7 +244,7 @@ class _RenderFused(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, screenspace, bone_tf, campos, settings, sh_degree,
-                isotropic, num_skinned, grad_sink, accumulate, want_posed):
+                isotropic, num_skinned, grad_sink, accumulate, want_posed, plan=None):
         L = _lib.lib()
         if not xyz.is_cuda:
             raise _lib.ManusB200Error("manus_b200.render_fused needs CUDA tensors (there is no CPU path)")
@@ -271,7 +271,7 @@ class _RenderFused(torch.autograd.Function):
             posed_xyz = cov6 = colors = opacity = None
         # ONE kernel for LBS + covariance + SH->RGB + projection (mb_pose_project_forward), then binning + tile kernels
         color, radii, st = rasterize_forward(settings, posed_xyz, None if opacity is None else opacity.reshape(-1),
-                                             colors_precomp=colors, cov3D_precomp=cov6, pose_inputs=pi)
+                                             colors_precomp=colors, cov3D_precomp=cov6, pose_inputs=pi, plan=plan)
         st.keep += [v for v in t[:7]] + list(t[7] if isinstance(t[7], tuple) else [t[7]]) + [cam]
         ctx.saved = (t, cam, sh_degree, isotropic, num_skinned, st)
         ctx.grad_sink, ctx.accumulate = grad_sink, bool(accumulate) and grad_sink is not None
@@ -294,7 +294,7 @@ class _RenderFused(torch.autograd.Function):
             raise RuntimeError("render_fused: a loss term depends on posed_xyz / posed_cov / colors / cano_opacity; use "
                                "fuse_backward=False (pose_gaussians + render_gaussians) to differentiate through them")
         if g_color is None:
-            return (None,) * 17
+            return (None,) * 18
         if st.host_count is not None:
             st.resolve()
         dev = t[0].device
@@ -337,17 +337,18 @@ class _RenderFused(torch.autograd.Function):
         rs = lambda v, s: None if v is None else v.reshape(s)
         ctx.saved = None
         head = (None,) * 6 if sink is not None else tuple(rs(gk, s) for gk, s in zip(g, sh[:6]))
-        return head + (rs(g_skin, sh[6]), rs(g_means2D, sh[7])) + (None,) * 9
+        return head + (rs(g_skin, sh[6]), rs(g_means2D, sh[7])) + (None,) * 10
 
 
 def render_fused(params, skin_wts, bone_tf, camera, bg_color, sh_degree=3, isotropic=False, num_skinned=None, grad_sink=None,
-                 accumulate=False, fuse_backward=False, want_posed=True):
+                 accumulate=False, fuse_backward=False, want_posed=True, plan=None):
     """params: (xyz, log_scale, quat, opacity_logit, f_dc, f_rest) -- the six nn.Parameters of GaussianModel.
     Returns the render_gaussians dict plus the posed quantities (what TrainingModule.forward returns).
     bone_tf: [B,4,4] transforms, or a (bones_posed[nb,4,4], bones_rest_inv[nb,4,4], B) triple -- the kernels then build
     T_b = posed_b rest_b^-1 (+ identity rows up to B) themselves (hand_dynamic.py:93-102).
     want_posed=False (fused backward only): posed_xyz / posed_cov / colors / cano_opacity are not produced (None in the dict);
-    they never touch HBM."""
+    they never touch HBM.
+    plan: the rasterizer.CapacityPlan that sizes the frame's instance buffers (default: the device's plan)."""
     xyz, log_scale, quat, opacity_logit, f_dc, f_rest = params
     device = xyz.device
     campos = torch.as_tensor(camera.camera_center).to(device)
@@ -359,7 +360,7 @@ def render_fused(params, skin_wts, bone_tf, camera, bg_color, sh_degree=3, isotr
         image, radii, posed_xyz, posed_cov, colors, opacity = _RenderFused.apply(
             xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, screenspace, bone_tf, campos,
             _settings(camera, bg_color, sh_degree, device), int(sh_degree), bool(isotropic), int(num_skinned), grad_sink, accumulate,
-            bool(want_posed))
+            bool(want_posed), plan)
         return {"render": torch.permute(image, (1, 2, 0)), "viewspace_points": screenspace, "visibility_filter": radii > 0, "radii": radii,
                 "posed_xyz": posed_xyz, "posed_cov": posed_cov, "colors": colors, "cano_opacity": opacity}
     posed_xyz, posed_cov, colors, opacity = pose_gaussians(xyz, log_scale, quat, opacity_logit, f_dc, f_rest, skin_wts, bone_tf,

@@ -77,6 +77,40 @@ def test_graph_replay_equals_eager_step(built_lib):
         rz.set_capacity_mode("exact")
 
 
+def test_renderer_with_a_private_capacity_plan(built_lib):
+    """SceneRenderer(plan=CapacityPlan(...)): the renderer's frames are sized by ITS plan (here: reserve mode while the device's
+    default plan stays exact), the device plan sees none of them, and a reserve that is too small is reported by check_overflow."""
+    from manus_b200 import _lib, rasterizer as rz, synth
+    from manus_b200.dist import SceneRenderer
+
+    scene, r0 = _renderer()
+    dev = r0.device
+    rz.set_capacity_mode("exact")
+    _, c, b = r0.view_inputs_host(7)
+    c, b = c.to(dev), b.to(dev)
+    img0 = r0.render(7, cam_dev=c, bones_dev=b)["render"].detach().clone()
+    need = rz.check_overflow()
+    shared_last = rz.plan_for(dev).last_state
+    assert need > 0 and r0.plan is rz.plan_for(dev)
+    mine = rz.CapacityPlan("reserve", margin=1.2)
+    mine.reserve(scene.n, r0.H, r0.W, need)
+    r1 = SceneRenderer(scene, dev, r0.W, r0.H, plan=mine)
+    r1._cams = r0._cams
+    img1 = r1.render(7, cam_dev=c, bones_dev=b)["render"].detach()
+    assert mine.last_state is not None and mine.last_state.host_count is None          # sized without a host read
+    assert rz.plan_for(dev).last_state is shared_last and rz.plan_for(dev).mode == "exact"
+    assert rz.check_overflow(mine.last_state) == need and torch.equal(img0, img1)
+    with pytest.raises(ValueError):
+        r1.render(7, cam_dev=c, bones_dev=b, fuse_backward=False)
+    tight = rz.CapacityPlan("reserve", margin=1.0)
+    tight.reserve(scene.n, r0.H, r0.W, max(need // 2 - 1024, 1))
+    r2 = SceneRenderer(scene, dev, r0.W, r0.H, plan=tight)
+    r2._cams = r0._cams
+    r2.render(7, cam_dev=c, bones_dev=b)
+    with pytest.raises(_lib.ManusB200Error):
+        rz.check_overflow(tight.last_state)
+
+
 def test_accumulating_pose_backward_adds_to_the_sink(built_lib):
     """mb_pose_backward_accumulate (TMA reduce-add): sink_after = sink_before + gradient, also across the ragged last tile and
     the skinned / static boundary (runs that are not 16-byte sized take the atomicAdd path)."""

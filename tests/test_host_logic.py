@@ -85,3 +85,32 @@ def test_stale_step_guard_logic():
     r.flat = F()                                            # densify / prune replaced the buffers
     with pytest.raises(RuntimeError, match="replaced"):
         _check_fresh(step)
+
+
+def test_capacity_plans_are_per_device_objects():
+    """rasterizer.CapacityPlan: one default plan per device index, module-level helpers address them, a private plan shares nothing."""
+    from manus_b200 import rasterizer as rz
+
+    saved = (dict(rz._plans), list(rz._plan_defaults))
+    try:
+        rz._plans.clear()
+        rz.set_capacity_mode("exact")
+        p0, p1 = rz.plan_for(0), rz.plan_for(1)
+        assert p0 is rz.plan_for(0) and p0 is not p1 and p0.mode == p1.mode == "exact"
+        rz.set_capacity_mode("reserve", margin=1.2)                    # every device, and plans created later
+        assert (p0.mode, p0.margin, p1.mode) == ("reserve", 1.2, "reserve") and rz.plan_for(2).mode == "reserve"
+        rz.reserve_capacity(0, 1000, 48, 64, 5000)
+        rz.reserve_capacity(0, 1000, 48, 64, 4000)                     # a high-water mark: never lowered
+        assert p0.high_water == {(1000, 48, 64): 5000} and p1.high_water == {}
+        rz.set_capacity_mode("exact", device=1)                        # one device only
+        assert p1.mode == "exact" and p0.mode == "reserve" and p0.high_water
+        rz.set_capacity_mode("reserve", margin=1.3, device=0)          # switching modes forgets the marks
+        assert p0.high_water == {}
+        mine = rz.CapacityPlan("reserve", 1.5)
+        mine.reserve(10, 4, 4, 7)
+        assert mine.high_water == {(10, 4, 4): 7} and p0.high_water == {} and mine.last_state is None
+        assert rz.check_overflow(device=0) == 0                        # no frame yet
+    finally:
+        rz._plans.clear()
+        rz._plans.update(saved[0])
+        rz._plan_defaults[:] = saved[1]
