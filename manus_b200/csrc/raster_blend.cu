@@ -736,7 +736,7 @@ extern "C" int mb_raster_forward_render(const mb_raster_inputs *in, void *geom, 
     if (d.P > 0 && capacity > 0) {
         rc = build_instances(in, d, g, b, im, capacity, s);
         if (rc) return rc;
-        rc = tile_order(nullptr, im.ranges, d.tiles, im.order_fwd, im.order_ws, s, dbg);
+        rc = tile_order(nullptr, im.ranges, d.tiles, im.order_fwd, im.order_ws, s, dbg, true);   // also decodes the tile ranges
         if (rc) return rc;
         order = im.order_fwd;
     }

@@ -299,18 +299,6 @@ __global__ void __launch_bounds__(256) emit_big_kernel(int gx, const uint32_t *_
     hist_smem_flush(hist_s, key_passes, key_hist);
 }
 
-// tile ranges from the tile-sorted instance list, one thread per instance
-__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t *__restrict__ counters, int64_t capacity,
-                                                          const uint32_t *__restrict__ tile_sorted, uint2 *__restrict__ ranges) {
-    int64_t n = counters[kCntRendered];
-    if (n > capacity) n = capacity;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t t = tile_sorted[i];
-        if (i == 0 || tile_sorted[i - 1] != t) ranges[t].x = (uint32_t)i;
-        if (i == n - 1 || tile_sorted[i + 1] != t) ranges[t].y = (uint32_t)(i + 1);
-    }
-}
-
 // Work order of the tile kernels: tiles by descending weight (list length for the forward, deepest last-contributor for
 // the backward) so that the longest lists start first.  Counting sort over 129 quarter-octave buckets in ONE launch of a
 // few co-resident CTAs: bucket counts go to global memory, the CTAs meet at an arrival counter, then every tile takes the
@@ -324,8 +312,17 @@ __device__ __forceinline__ int weight_bucket(uint32_t w) {
 
 constexpr int kOrderThreads = 256;
 
-__global__ void __launch_bounds__(kOrderThreads) tile_order_kernel(const uint32_t *__restrict__ weight, const uint2 *__restrict__ ranges,
-                                                                   int tiles, uint32_t *__restrict__ order, uint32_t *ws) {
+//
+// decode != 0 (the forward's launch): on entry ranges[t] is what the last pass of the partition by tile left there --
+// (~first position, last position + 1) of tile t's run in the sorted list, (0, 0) for an empty tile; the kernel rewrites it as
+// the list range (first, last + 1) while it is at it (every tile is visited by exactly one thread), so no kernel reads the sorted
+// instance list just to find the tile boundaries.
+__device__ __forceinline__ uint2 decode_range(uint2 r, int decode) {
+    return (decode && r.y) ? make_uint2(~r.x, r.y) : r;
+}
+
+__global__ void __launch_bounds__(kOrderThreads) tile_order_kernel(const uint32_t *__restrict__ weight, uint2 *ranges,
+                                                                   int tiles, uint32_t *__restrict__ order, uint32_t *ws, int decode) {
     __shared__ uint32_t hist[kOrderBuckets], base[kOrderBuckets];
     __shared__ bool s_last;
     uint32_t *g_hist = ws, *g_cursor = ws + kOrderBuckets;
@@ -336,7 +333,14 @@ __global__ void __launch_bounds__(kOrderThreads) tile_order_kernel(const uint32_
     const int stride = gridDim.x * kOrderThreads;
     for (int t0 = blockIdx.x * kOrderThreads; t0 < tiles; t0 += stride) {
         const int t = t0 + tid;
-        const int bkt = t < tiles ? weight_bucket(weight ? weight[t] : ranges[t].y - ranges[t].x) : -1;
+        int bkt = -1;
+        if (t < tiles) {
+            if (weight) bkt = weight_bucket(weight[t]);
+            else {
+                const uint2 r = decode_range(ranges[t], decode);
+                bkt = weight_bucket(r.y - r.x);
+            }
+        }
         // empty tiles are the majority: one atomic per warp for bucket 0
         const unsigned zeros = __ballot_sync(0xffffffffu, bkt == 0);
         if (bkt > 0) atomicAdd(&hist[bkt], 1u);
@@ -373,7 +377,15 @@ __global__ void __launch_bounds__(kOrderThreads) tile_order_kernel(const uint32_
     __syncthreads();
     for (int t0 = blockIdx.x * kOrderThreads; t0 < tiles; t0 += stride) {
         const int t = t0 + tid;
-        const int bkt = t < tiles ? weight_bucket(weight ? weight[t] : ranges[t].y - ranges[t].x) : -1;
+        int bkt = -1;
+        if (t < tiles) {
+            if (weight) bkt = weight_bucket(weight[t]);
+            else {
+                const uint2 r = decode_range(ranges[t], decode);
+                bkt = weight_bucket(r.y - r.x);
+                if (decode && r.y) ranges[t] = r;
+            }
+        }
         const unsigned zeros = __ballot_sync(0xffffffffu, bkt == 0);
         const int leader = __ffs(zeros) - 1;
         uint32_t zstart = 0;
@@ -410,11 +422,11 @@ static cudaError_t launch_cooperative(void (*kernel)(Params...), int grid, int b
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
 }
 
-int tile_order(const uint32_t *weight_or_null, const uint2 *ranges_or_null, int tiles, uint32_t *order, uint32_t *ws,
-               cudaStream_t s, bool debug) {
+int tile_order(const uint32_t *weight_or_null, uint2 *ranges_or_null, int tiles, uint32_t *order, uint32_t *ws,
+               cudaStream_t s, bool debug, bool decode_runs) {
     KernelTimer kt("tile_order", s);
     const int grid = max(1, min((tiles + kOrderThreads - 1) / kOrderThreads, min(32, sm_count())));
-    MB_CUDA(launch_cooperative(tile_order_kernel, grid, kOrderThreads, s, weight_or_null, ranges_or_null, tiles, order, ws));
+    MB_CUDA(launch_cooperative(tile_order_kernel, grid, kOrderThreads, s, weight_or_null, ranges_or_null, tiles, order, ws, decode_runs ? 1 : 0));
     return check_launch("tile_order", debug, s);
 }
 
@@ -531,7 +543,7 @@ int build_instances(const mb_raster_inputs *in, const RasterDims &d, const GeomS
                     const ImageState &im, int64_t capacity, cudaStream_t s) {
     const bool dbg = in->debug != 0;
     const int grid_p = max(1, min((d.P + kEmitChunk - 1) / kEmitChunk, sm_count() * 8));
-    MB_CUDA(cudaMemsetAsync(im.ranges, 0, sizeof(uint2) * (size_t)d.tiles, s));
+    // (im.ranges was cleared by the caller)
     // the emission kernels count the digits of the tile ids they write (histogram of the partition by tile below): its
     // workspace is cleared here, in front of them
     SortWorkspace ws = carve_sort_workspace(b.sort_ws, capacity > 0 ? capacity : 1);
@@ -551,14 +563,10 @@ int build_instances(const mb_raster_inputs *in, const RasterDims &d, const GeomS
     }
     rc = check_launch("emit_big", dbg, s);
     if (rc) return rc;
-    rc = radix_sort_pairs(b.tile_a, b.gid_a, b.tile_b, b.gid_b, -1, g.counters + kCntRendered, capacity, 0, key_bits, ws, s, dbg, true);
-    if (rc) return rc;
-    const int grid_d = (int)max((int64_t)1, min((capacity + 255) / 256, (int64_t)sm_count() * 16));
-    {
-    KernelTimer kt("tile_ranges", s);
-    tile_ranges_kernel<<<grid_d, 256, 0, s>>>(g.counters, capacity, b.tile_b, im.ranges);
-    }
-    return check_launch("tile_ranges", dbg, s);
+    // stable partition by tile id; its last pass leaves every tile's run of the sorted list in im.ranges (encoded: decoded by
+    // tile_order, which the caller launches next)
+    return radix_sort_pairs(b.tile_a, b.gid_a, b.tile_b, b.gid_b, -1, g.counters + kCntRendered, capacity, 0, key_bits, ws, s, dbg, true,
+                            im.ranges);
 }
 
 }  // namespace mb

@@ -168,8 +168,9 @@ int validate_raster_inputs(const mb_raster_inputs *in, const char *who, bool nee
 
 // order[i] = tile with the i-th largest weight (approximately: descending quarter-octave buckets).  `ws` = kOrderWs zeroed
 // words; the kernel leaves them zeroed again.
-int tile_order(const uint32_t *weight_or_null, const uint2 *ranges_or_null, int tiles, uint32_t *order, uint32_t *ws,
-               cudaStream_t s, bool debug);
+// decode_runs: ranges[] holds what radix_sort_pairs(..., runs) left (~first, last + 1 | 0, 0) and is rewritten as (first, last + 1).
+int tile_order(const uint32_t *weight_or_null, uint2 *ranges_or_null, int tiles, uint32_t *order, uint32_t *ws,
+               cudaStream_t s, bool debug, bool decode_runs = false);
 // Backward work items: (tile, segment) for every kSeg-entry segment of every tile's consumed list [0, maxlast), full
 // segments first, then the partial ones by descending length.  *n_items = number of items.  `ws` as for tile_order.
 int segment_items(const uint32_t *maxlast, int tiles, uint2 *items, uint32_t *n_items, uint32_t *ws, cudaStream_t s, bool debug);

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kSortThreads, MB_SORT_MINBLOCKS) radix_pass_ke
                                                                   uint32_t *__restrict__ vals_out, int64_t n_host,
                                                                   const uint32_t *__restrict__ n_dev, int64_t max_n,
                                                                   int shift, const uint32_t *__restrict__ hist,
-                                                                  volatile uint32_t *status, uint32_t *cursor) {
+                                                                  volatile uint32_t *status, uint32_t *cursor, uint2 *runs) {
     const int64_t n = resolve_n(n_host, n_dev, max_n);
     const int64_t nchunks = (n + kSortChunk - 1) / kSortChunk;
     __shared__ uint32_t warp_cnt[kSortWarps][256];
@@ -89,8 +89,14 @@ __global__ void __launch_bounds__(kSortThreads, MB_SORT_MINBLOCKS) radix_pass_ke
         for (int r = 0; r < kSortItems; ++r) {
             const int e = r * kSortThreads + tid;
             if (e < nvalid) {
-                if (keys_out) keys_out[chunk_base + e] = keys_in[chunk_base + e];
+                const uint32_t k = keys_in[chunk_base + e];
+                if (keys_out) keys_out[chunk_base + e] = k;
                 vals_out[chunk_base + e] = vals_in[chunk_base + e];
+                if (runs) {
+                    const uint32_t pos = (uint32_t)(chunk_base + e);
+                    if (e == 0 || keys_in[chunk_base + e - 1] != k) atomicMax(&runs[k].x, ~pos);
+                    if (e == nvalid - 1 || keys_in[chunk_base + e + 1] != k) atomicMax(&runs[k].y, pos + 1u);
+                }
             }
         }
         return;
@@ -222,6 +228,13 @@ __global__ void __launch_bounds__(kSortThreads, MB_SORT_MINBLOCKS) radix_pass_ke
             const uint32_t pos = base_s[(k >> shift) & 255u] + (uint32_t)lp;
             if (keys_out) keys_out[pos] = k;
             vals_out[pos] = vals_s[lp];
+            // last pass of a sort whose caller wants the runs of equal keys: inside a chunk equal keys are neighbours (digit-major
+            // and stable) and land on consecutive positions, so the first / last element of each run of the chunk bounds the
+            // key's global run from below / above (a run that spans chunks: the extremes over its chunks)
+            if (runs) {
+                if (lp == 0 || keys_s[lp - 1] != k) atomicMax(&runs[k].x, ~pos);
+                if (lp == nvalid - 1 || keys_s[lp + 1] != k) atomicMax(&runs[k].y, pos + 1u);
+            }
         }
     }
 }
@@ -238,7 +251,7 @@ __global__ void copy_pairs_kernel(const uint32_t *__restrict__ ki, const uint32_
 
 int radix_sort_pairs(uint32_t *keys_in, uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out, int64_t n_host,
                      const uint32_t *n_dev, int64_t max_n, int begin_bit, int end_bit, const SortWorkspace &ws,
-                     cudaStream_t stream, bool debug, bool hist_ready) {
+                     cudaStream_t stream, bool debug, bool hist_ready, uint2 *runs) {
     const int64_t bound = n_host >= 0 ? n_host : max_n;
     if (bound <= 0) return MB_OK;
     const int passes = sort_passes(begin_bit, end_bit);
@@ -275,7 +288,8 @@ int radix_sort_pairs(uint32_t *keys_in, uint32_t *vals_in, uint32_t *keys_out, u
             KernelTimer kt("radix_pass", stream);
             radix_pass_kernel<<<(int)chunks, kSortThreads, 0, stream>>>(src_k, src_v, dst_k, dst_v, n_host, n_dev, max_n,
                                                                       begin_bit + 8 * p, ws.hist + p * 256,
-                                                                      ws.status + (size_t)p * ws.max_chunks * 256, ws.cursor + p);
+                                                                      ws.status + (size_t)p * ws.max_chunks * 256, ws.cursor + p,
+                                                                      p == passes - 1 ? runs : nullptr);
         }
         rc = check_launch("radix pass", debug, stream);
         if (rc) return rc;

@@ -54,9 +54,13 @@ inline SortWorkspace carve_sort_workspace(void *p, int64_t max_n) {
 // hist_ready: the caller cleared ws.zeroed (ws.zeroed_bytes) BEFORE the kernel that produced the keys ran, and that kernel
 // counted the digits of every key it wrote into ws.hist (hist_smem_* below): the sort is then the passes only -- no memset and
 // no histogram launch between the producer and the first pass.
+// runs (zeroed by the caller, indexed by key; needs at least one pass): the LAST pass also records where every key's run of equal keys
+// lies in the output -- runs[k] = (~first position, last position + 1) for the keys that occur, (0, 0) for the others (atomicMax
+// on zero-initialised words; the caller decodes x = ~runs[k].x) -- so that nobody has to read the sorted keys again to find the
+// boundaries.
 int radix_sort_pairs(uint32_t *keys_in, uint32_t *vals_in, uint32_t *keys_out, uint32_t *vals_out, int64_t n_host,
                      const uint32_t *n_dev, int64_t max_n, int begin_bit, int end_bit, const SortWorkspace &ws,
-                     cudaStream_t stream, bool debug, bool hist_ready = false);
+                     cudaStream_t stream, bool debug, bool hist_ready = false, uint2 *runs = nullptr);
 
 inline int sort_passes(int begin_bit, int end_bit) { return (end_bit - begin_bit + 7) / 8; }
 
