@@ -278,12 +278,16 @@ class CompactGradExchange:
         w = param_widths(flat.sh_coeffs, flat.isotropic)
         self.head = flat.grad[: n * (w["xyz"] + w["opacity_logit"] + w["log_scale"] + w["quat"])]
         self.rebuild = rebuild
+        self._flat_id, self._n = id(flat), n      # the staging buffers and `head` are views / sized for THIS flat buffer
         # a second communicator (own stream) for the all-reduce, so that it runs beside the all-gather and the rebuild
         self.group2 = dist.new_group() if self.world > 1 and group is None else group
 
     def __call__(self) -> None:
         r, flat = self.r, self.r.flat
         n = flat.n
+        if id(flat) != self._flat_id or n != self._n:
+            # densify / prune rebuilt the flat buffers (SceneRenderer.rebind): `head` would all-reduce the stale buffer
+            raise RuntimeError("this exchange was built on buffers that have been replaced (densify / prune): build a new CompactGradExchange")
         pending = None
         if self.world > 1:
             pending = dist.all_reduce(self.head, group=self.group2, async_op=True)     # see below

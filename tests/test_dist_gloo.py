@@ -212,3 +212,17 @@ def test_compact_exchange_equals_rebuilding_from_all_views(tmp_path):
                  torch.stack([i["campos"] for i in ins]), gfdc_all, flat.grads["f_dc"], flat.grads["f_rest"])
     for r in range(world):
         np.testing.assert_allclose(np.load(tmp_path / f"compact_{r}.npy"), flat.grad.numpy(), rtol=1e-6, atol=1e-6)
+
+
+def test_compact_exchange_refuses_replaced_buffers():
+    """After densify / prune the renderer points at NEW flat buffers (SceneRenderer.rebind); an exchange built on the old ones
+    holds views of the stale gradient buffer and must refuse to run."""
+    from manus_b200.dist import CompactGradExchange
+
+    flat = make_flat()
+    r = _FakeRenderer(flat, 0)
+    ex = CompactGradExchange(r, rebuild=_rebuild_ref)
+    ex()                                                   # single rank, no process group: runs
+    r.flat = make_flat()                                   # what rebind() does
+    with pytest.raises(RuntimeError, match="replaced"):
+        ex()
