@@ -348,7 +348,13 @@ def render_fused(params, skin_wts, bone_tf, camera, bg_color, sh_degree=3, isotr
     T_b = posed_b rest_b^-1 (+ identity rows up to B) themselves (hand_dynamic.py:93-102).
     want_posed=False (fused backward only): posed_xyz / posed_cov / colors / cano_opacity are not produced (None in the dict);
     they never touch HBM.
-    plan: the rasterizer.CapacityPlan that sizes the frame's instance buffers (default: the device's plan)."""
+    plan: the rasterizer.CapacityPlan that sizes the frame's instance buffers (default: the device's plan).
+    grad_sink: {name: dense fp32 tensor} -- the backward writes (accumulate=True: adds) the six parameter gradients of THIS
+    node there and returns None for them to autograd.  Only this node's contribution goes to the sink: a gradient that reaches a
+    parameter by another route -- skin weights looked up from xyz (skinning_weights_from_voxel_grid, the reference's
+    mano_init_voxel mode: its backward adds to xyz.grad through autograd), a regulariser on the leaves -- lands in the leaf's
+    .grad as usual and has to be added to the sink by the caller.  With fuse_backward=True the posed outputs are for
+    inspection only (a loss term on them raises in the backward)."""
     xyz, log_scale, quat, opacity_logit, f_dc, f_rest = params
     device = xyz.device
     campos = torch.as_tensor(camera.camera_center).to(device)
